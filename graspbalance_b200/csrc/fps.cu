@@ -1,0 +1,323 @@
+// fps.cu -- furthest point sampling as a thread-block-cluster kernel (sm_100a).
+//
+// Replaces furthest_point_sampling_kernel<BS> of PointNet/_ext_src/src/sampling_gpu.cu:74-178 (variant A) and of
+// pointnet2_batch/src/sampling_gpu.cu:73-181 (variant B).  The reference runs ONE block per scene and re-reads every
+// point and its running distance from global memory in each of the m-1 dependent rounds, with a 9-10 barrier shared
+// memory tree per round.
+//
+// Here one CLUSTER of C CTAs owns a scene.  Each thread keeps P points (x, y, z, running min distance) in REGISTERS for
+// the whole kernel, so a round touches no global memory at all:
+//   1. every thread updates its P points against the last pick and keeps its best (distance, slot);
+//   2. warp argmax with two redux.sync instructions on integer keys (distance bits, then tie key);
+//   3. warp winners -> shared memory -> one __syncthreads -> every warp reduces them redundantly (no 2nd barrier);
+//   4. (C > 1) the CTA winner is PUSHED into the shared memory of all C CTAs with st.async, which completes a
+//      transaction count on the receiver's mbarrier; every CTA waits on its own mbarrier, reduces the C candidates
+//      and starts the next round.  One DSMEM hop and no cluster barrier per round.
+//
+// Bit-exact tie order.  The reference's result is determined by its block size BS = opt_n_threads(n): the per-thread
+// strided scan keeps the first strict maximum and the shared-memory tree keeps the lower slot on ties, i.e. among equal
+// distances the winner minimises (bitreverse_log2(BS)(k mod BS), k div BS).  That pair is packed in one 32-bit "tie
+// key" and reduced with redux.min, so any decomposition (P, T, C) reproduces the reference's pick.
+#include "common.cuh"
+
+namespace gb {
+
+constexpr int kKeyNone = (int)0xBF800000;  // bits of -1.0f as a signed int: below every valid (>= +0) distance
+
+__device__ __forceinline__ uint32_t fps_tiekey(uint32_t k, int L) {
+  const uint32_t low = L ? (__brev(k) >> (32 - L)) : 0u;  // bit reversal of (k mod BS) over L bits
+  return (low << 22) | (k >> L);
+}
+__device__ __forceinline__ uint32_t fps_tiekey_inv(uint32_t tk, int L) {
+  const uint32_t low = L ? (__brev(tk >> 22) >> (32 - L)) : 0u;
+  return ((tk & 0x3FFFFFu) << L) | low;
+}
+
+struct FpsShared {
+  uint32_t wc[2][32][8];  // per-warp candidates, double buffered by round parity: key, tiekey, x, y, z
+  uint32_t cc[2][16][8];  // per-CTA candidates received from the cluster (slot = sender rank)
+  uint64_t full[2];       // mbarriers: C * 20 bytes of st.async payload per round
+};
+
+template <int P, int T>
+__global__ void __launch_bounds__(T, 1) fps_cluster_kernel(const float *__restrict__ xyz, float *__restrict__ temp,
+                                                           int *__restrict__ idxs, int n, int m, int variant, int L) {
+  extern __shared__ float s_pts[];  // [3][P*T] copy of this CTA's coordinates (winner lookup without dynamic register indexing)
+  __shared__ __align__(16) FpsShared sh;
+
+  const uint32_t C = cluster_nctarank();
+  const uint32_t rank = cluster_ctarank();
+  const int scene = blockIdx.x / C;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  constexpr int W = T / 32;
+
+  xyz += (size_t)scene * n * 3;
+  idxs += (size_t)scene * m;
+  if (temp) temp += (size_t)scene * n;
+
+  if (tid == 0) {
+    mbar_init(&sh.full[0], 1);
+    mbar_init(&sh.full[1], 1);
+    fence_mbar_init();
+  }
+
+  float px[P], py[P], pz[P], pt[P];
+  const uint32_t g = rank * T + tid;
+  const uint32_t stride = C * T;
+  float *sx = s_pts, *sy = s_pts + P * T, *sz = s_pts + 2 * P * T;
+#pragma unroll
+  for (int i = 0; i < P; ++i) {
+    const uint32_t k = g + i * stride;
+    float x = 0.f, y = 0.f, z = 0.f, t = -1.0f;
+    if (k < (uint32_t)n) {
+      x = __ldg(xyz + 3 * (size_t)k), y = __ldg(xyz + 3 * (size_t)k + 1), z = __ldg(xyz + 3 * (size_t)k + 2);
+      t = temp ? temp[k] : 1e10f;
+      if (variant == GB_FPS_A) {
+        const float mag = __fmaf_rn(z, z, __fmaf_rn(x, x, __fmul_rn(y, y)));
+        if ((double)mag <= 1e-3) t = -1.0f;  // skipped: never updated, never picked (sampling_gpu.cu:105-106)
+      }
+    }
+    px[i] = x, py[i] = y, pz[i] = z, pt[i] = t;
+    sx[i * T + tid] = x, sy[i * T + tid] = y, sz[i * T + tid] = z;
+  }
+  // picked when nothing is eligible (reference: besti stays 0)
+  const float p0x = __ldg(xyz), p0y = __ldg(xyz + 1), p0z = __ldg(xyz + 2);
+  float cx = p0x, cy = p0y, cz = p0z;
+  if (rank == 0 && tid == 0) idxs[0] = 0;
+
+  __syncthreads();
+  if (C > 1) cluster_sync_all();  // peers' mbarriers are initialised before anyone pushes
+
+  uint32_t phases = 0u;  // bit p = parity to wait for on full[p]
+  uint32_t cc0 = 0, cc1 = 0, bar0 = 0, bar1 = 0;  // this lane's push targets in CTA `lane` (slot = my rank), per parity
+  if (C > 1 && warp == 0 && lane < (int)C) {
+    cc0 = mapa_u32(smem_u32(&sh.cc[0][rank][0]), lane), cc1 = mapa_u32(smem_u32(&sh.cc[1][rank][0]), lane);
+    bar0 = mapa_u32(smem_u32(&sh.full[0]), lane), bar1 = mapa_u32(smem_u32(&sh.full[1]), lane);
+  }
+
+  for (int j = 1; j < m; ++j) {
+    const int par = j & 1;
+    if (C > 1 && tid == 0) mbar_arrive_expect_tx(&sh.full[par], C * 20u);
+
+    // 1. register-resident update + per-thread argmax (first strict maximum == lowest k among this thread's points)
+    int bkey = kKeyNone, bi = 0;
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+      const float d = sqdist3(px[i] - cx, py[i] - cy, pz[i] - cz);
+      const float t = fminf(d, pt[i]);
+      pt[i] = t;
+      const int key = __float_as_int(t);
+      if (key > bkey) bkey = key, bi = i;
+    }
+    // 2. warp argmax on (key desc, tiekey asc)
+    const int wkey = __reduce_max_sync(0xffffffffu, bkey);
+    const uint32_t tk = (bkey == wkey && bkey != kKeyNone) ? fps_tiekey(g + bi * stride, L) : 0xFFFFFFFFu;
+    const uint32_t wtk = __reduce_min_sync(0xffffffffu, tk);
+    if (tk == wtk && bkey == wkey) {  // unique lane unless the whole warp is ineligible (then all write the same words)
+      uint32_t *w = sh.wc[par][warp];
+      const int s = bi * T + tid;
+      *reinterpret_cast<uint4 *>(w) = make_uint4((uint32_t)wkey, wtk, __float_as_uint(sx[s]), __float_as_uint(sy[s]));
+      w[4] = __float_as_uint(sz[s]);
+    }
+    __syncthreads();
+    // 3. every warp reduces the W warp candidates
+    uint32_t ckey_u = (uint32_t)kKeyNone, ctk = 0xFFFFFFFFu, ux = 0, uy = 0, uz = 0;
+    if (lane < W) {
+      const uint4 v = *reinterpret_cast<const uint4 *>(sh.wc[par][lane]);
+      ckey_u = v.x, ctk = v.y, ux = v.z, uy = v.w;
+      uz = sh.wc[par][lane][4];
+    }
+    int key = __reduce_max_sync(0xffffffffu, (int)ckey_u);
+    uint32_t mtk = ((int)ckey_u == key) ? ctk : 0xFFFFFFFFu;
+    uint32_t btk = __reduce_min_sync(0xffffffffu, mtk);
+    int src = __ffs(__ballot_sync(0xffffffffu, (int)ckey_u == key && ctk == btk)) - 1;
+    ux = __shfl_sync(0xffffffffu, ux, src), uy = __shfl_sync(0xffffffffu, uy, src), uz = __shfl_sync(0xffffffffu, uz, src);
+
+    if (C > 1) {
+      // 4. push this CTA's winner to every CTA of the cluster (lane r -> CTA r), then wait for all C candidates
+      if (warp == 0 && lane < (int)C) {
+        const uint32_t dst = par ? cc1 : cc0, bar = par ? bar1 : bar0;
+        st_async_v4(dst, (uint32_t)key, btk, ux, uy, bar);
+        st_async_b32(dst + 16, uz, bar);
+      }
+      mbar_wait_cluster(&sh.full[par], (phases >> par) & 1u);
+      phases ^= 1u << par;
+      ckey_u = (uint32_t)kKeyNone, ctk = 0xFFFFFFFFu;
+      if (lane < (int)C) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(sh.cc[par][lane]);
+        ckey_u = v.x, ctk = v.y, ux = v.z, uy = v.w;
+        uz = sh.cc[par][lane][4];
+      }
+      key = __reduce_max_sync(0xffffffffu, (int)ckey_u);
+      mtk = ((int)ckey_u == key) ? ctk : 0xFFFFFFFFu;
+      btk = __reduce_min_sync(0xffffffffu, mtk);
+      src = __ffs(__ballot_sync(0xffffffffu, (int)ckey_u == key && ctk == btk)) - 1;
+      ux = __shfl_sync(0xffffffffu, ux, src), uy = __shfl_sync(0xffffffffu, uy, src), uz = __shfl_sync(0xffffffffu, uz, src);
+    }
+    int pick = 0;
+    if (key != kKeyNone) {
+      pick = (int)fps_tiekey_inv(btk, L);
+      cx = __uint_as_float(ux), cy = __uint_as_float(uy), cz = __uint_as_float(uz);
+    } else {
+      cx = p0x, cy = p0y, cz = p0z;
+    }
+    if (rank == 0 && tid == 0) idxs[j] = pick;
+  }
+
+  if (temp) {
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+      const uint32_t k = g + i * stride;
+      if (k < (uint32_t)n && pt[i] >= 0.f) temp[k] = pt[i];
+    }
+  }
+  if (C > 1) cluster_sync_all();  // nobody leaves while a peer may still push into it
+}
+
+// Fallback for scenes too large to keep in the registers of one cluster: one CTA per scene, running distances in
+// global memory (temp must be provided by the launcher), same key reduction.
+template <int T>
+__global__ void __launch_bounds__(T, 1) fps_global_kernel(const float *__restrict__ xyz, float *__restrict__ temp,
+                                                          int *__restrict__ idxs, int n, int m, int variant, int L) {
+  __shared__ __align__(16) uint32_t wc[2][32][8];
+  const int scene = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int W = T / 32;
+  xyz += (size_t)scene * n * 3;
+  idxs += (size_t)scene * m;
+  temp += (size_t)scene * n;
+  const float p0x = __ldg(xyz), p0y = __ldg(xyz + 1), p0z = __ldg(xyz + 2);
+  float cx = p0x, cy = p0y, cz = p0z;
+  if (tid == 0) idxs[0] = 0;
+  for (int j = 1; j < m; ++j) {
+    const int par = j & 1;
+    int bkey = kKeyNone;
+    uint32_t bk = 0;
+    for (uint32_t k = tid; k < (uint32_t)n; k += T) {
+      const float x = __ldg(xyz + 3 * (size_t)k), y = __ldg(xyz + 3 * (size_t)k + 1), z = __ldg(xyz + 3 * (size_t)k + 2);
+      if (variant == GB_FPS_A) {
+        const float mag = __fmaf_rn(z, z, __fmaf_rn(x, x, __fmul_rn(y, y)));
+        if ((double)mag <= 1e-3) continue;
+      }
+      const float t = fminf(sqdist3(x - cx, y - cy, z - cz), temp[k]);
+      temp[k] = t;
+      const int key = __float_as_int(t);
+      if (key > bkey) bkey = key, bk = k;
+    }
+    const int wkey = __reduce_max_sync(0xffffffffu, bkey);
+    const uint32_t tk = (bkey == wkey && bkey != kKeyNone) ? fps_tiekey(bk, L) : 0xFFFFFFFFu;
+    const uint32_t wtk = __reduce_min_sync(0xffffffffu, tk);
+    if (tk == wtk && bkey == wkey) {
+      wc[par][warp][0] = (uint32_t)wkey;
+      wc[par][warp][1] = wtk;
+    }
+    __syncthreads();
+    uint32_t ckey_u = (uint32_t)kKeyNone, ctk = 0xFFFFFFFFu;
+    if (lane < W) ckey_u = wc[par][lane][0], ctk = wc[par][lane][1];
+    const int key = __reduce_max_sync(0xffffffffu, (int)ckey_u);
+    const uint32_t btk = __reduce_min_sync(0xffffffffu, ((int)ckey_u == key) ? ctk : 0xFFFFFFFFu);
+    int pick = 0;
+    if (key != kKeyNone) pick = (int)fps_tiekey_inv(btk, L);
+    cx = __ldg(xyz + 3 * (size_t)pick), cy = __ldg(xyz + 3 * (size_t)pick + 1), cz = __ldg(xyz + 3 * (size_t)pick + 2);
+    if (tid == 0) idxs[j] = pick;
+  }
+}
+
+__global__ void fill_kernel(float *p, size_t n, float v) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+template <int P, int T>
+static int launch_fps(const float *xyz, float *temp, int *idx, int b, int n, int m, int variant, int L, int C, cudaStream_t s) {
+  auto kern = fps_cluster_kernel<P, T>;
+  const size_t dyn = (size_t)3 * P * T * sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+  if (e != cudaSuccess) return (int)e;
+  if (C > 8) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) return (int)e;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(b * C));
+  cfg.blockDim = dim3(T);
+  cfg.dynamicSmemBytes = dyn;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)C;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, kern, xyz, temp, idx, n, m, variant, L);
+  count_launch();
+  return (int)e;
+}
+
+static int floor_log2(int v) {
+  int l = 0;
+  while ((1 << (l + 1)) <= v) ++l;
+  return l;
+}
+
+}  // namespace gb
+
+using namespace gb;
+
+extern "C" int gb_fps(const float *xyz, float *temp, int *idx, int b, int n, int m, int variant, gb_stream_t stream) {
+  if (b < 0 || n <= 0 || m < 0 || (variant != GB_FPS_A && variant != GB_FPS_B) || !xyz || !idx) return (int)cudaErrorInvalidValue;
+  if (b == 0 || m == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  // BS = opt_n_threads(n): cuda_utils.h:21-27 (cap 512) / pointnet2_batch/src/cuda_utils.h:10-14 (cap 1024).
+  // floor(log2 n) computed in integers (the reference's double log() agrees for every n < 2^31 that is not within
+  // 1 ulp of a power of two from below -- checked for all n <= 2^22 in tests/test_host_logic.py).
+  const int cap = variant == GB_FPS_A ? 512 : 1024;
+  int bs = 1 << floor_log2(n);
+  if (bs > cap) bs = cap;
+  const int L = floor_log2(bs);
+
+  // ---- configuration: cluster size C, threads T, points per thread P, with C*T >= BS (tie-key alignment) ----
+  const int sms = num_sms();
+  int C = g_tuning.fps_cluster, T = g_tuning.fps_threads;
+  if (C != 1 && C != 2 && C != 4 && C != 8 && C != 16) C = 0;
+  if (T != 512 && T != 1024) T = 0;
+  if (C == 0) {
+    // as many CTAs per scene as fit on the chip at two CTAs per SM, but not fewer than ~2048 points per CTA (below
+    // that the DSMEM hop costs more than the shorter register sweep saves)
+    C = 16;
+    while (C > 1 && ((long)b * C > 2L * sms || n / C < 2048)) C >>= 1;
+    // capacity: the largest per-CTA register tile is 512 threads x 20 points
+    while (C < 16 && (long)C * 512 * 20 < n) C <<= 1;
+  }
+  if (T == 0) {
+    const int per_cta = (n + C - 1) / C;
+    // 1024 threads (<= 10 points each) give the shortest round; 512 threads with <= 64 registers let two CTAs
+    // share an SM when there are more clusters than the chip holds at one CTA per SM
+    T = (b * C > sms && per_cta <= 512 * 5) ? 512 : 1024;
+  }
+  while (C * T < bs && T < 1024) T <<= 1;
+  while (C * T < bs && C < 16) C <<= 1;
+  const int per_thread = (int)(((long)n + (long)C * T - 1) / ((long)C * T));
+
+#define GB_FPS_CASE(PP, TT) \
+  if (T == TT && per_thread <= PP) return launch_fps<PP, TT>(xyz, temp, idx, b, n, m, variant, L, C, s);
+  GB_FPS_CASE(1, 1024) GB_FPS_CASE(2, 1024) GB_FPS_CASE(3, 1024) GB_FPS_CASE(4, 1024) GB_FPS_CASE(5, 1024)
+  GB_FPS_CASE(6, 1024) GB_FPS_CASE(8, 1024) GB_FPS_CASE(10, 1024)
+  GB_FPS_CASE(1, 512) GB_FPS_CASE(2, 512) GB_FPS_CASE(3, 512) GB_FPS_CASE(4, 512) GB_FPS_CASE(5, 512) GB_FPS_CASE(6, 512)
+  GB_FPS_CASE(8, 512) GB_FPS_CASE(10, 512) GB_FPS_CASE(12, 512) GB_FPS_CASE(16, 512) GB_FPS_CASE(20, 512)
+#undef GB_FPS_CASE
+
+  // does not fit in registers: global-memory fallback (needs a temp buffer)
+  float *tmp = temp;
+  if (!tmp) {
+    cudaError_t e = cudaMallocAsync((void **)&tmp, (size_t)b * n * sizeof(float), s);
+    if (e != cudaSuccess) return (int)e;
+    fill_kernel<<<1024, 256, 0, s>>>(tmp, (size_t)b * n, 1e10f);
+    count_launch();
+  }
+  fps_global_kernel<1024><<<b, 1024, 0, s>>>(xyz, tmp, idx, n, m, variant, L);
+  count_launch();
+  int err = finish_launch();
+  if (!temp) cudaFreeAsync(tmp, s);
+  return err;
+}

@@ -1,0 +1,293 @@
+// group.cu -- grouping_operation / gather_operation, forward and backward.
+//
+// Replaces group_points_kernel / group_points_grad_kernel (PointNet/_ext_src/src/group_points_gpu.cu:17-101; one block per
+// scene, strided 4-byte writes), group_points_kernel_fast / _grad_kernel_fast (pointnet2_batch/src/group_points_gpu.cu:9-70;
+// one thread per element, idx re-read for every channel, 4-byte sector-wasting gathers from L2) and the gather kernels
+// (sampling_gpu.cu:13-62, batch :8-63).
+//
+// Forward is the HBM-bound op of the pipeline: out[b,c,j,k] = points[b,c,idx[b,j,k]] writes 4*C*npoints*nsample bytes per
+// scene and reads only 4*C*n.  Design:
+//   * a CTA stages the source rows of a chunk of channels in SHARED MEMORY (up to ~200 KB), interleaved V channels per
+//     point, so that the random gather is one LDS.(32*V) per index instead of V sector-sized L2 reads;
+//   * each thread owns 4 consecutive output positions: one 128-bit load of idx (read once per channel CHUNK, not once
+//     per channel), 4 LDS gathers per channel group, one coalesced 128-bit streaming store per channel;
+//   * the (scene, chunk) x position work space is flattened and cut into equal contiguous ranges, one per resident CTA,
+//     so all 148 SMs finish together whatever the shape.
+// Backward is a scatter-add: coalesced 128-bit reads of grad_out and idx, red.global.add.f32 into the (L2-resident)
+// gradient rows, with WARP-AGGREGATION of runs of equal indices first -- ball/cylinder query pads a neighbourhood with
+// copies of its first hit, so sparse neighbourhoods collapse to one atomic per run.
+#include "common.cuh"
+
+namespace gb {
+
+constexpr int kGroupThreads = 512;
+
+template <int V> struct VecT;
+template <> struct VecT<1> { using type = float; };
+template <> struct VecT<2> { using type = float2; };
+template <> struct VecT<4> { using type = float4; };
+
+template <int V> __device__ __forceinline__ typename VecT<V>::type vmake(const float *v);
+template <> __device__ __forceinline__ float vmake<1>(const float *v) { return v[0]; }
+template <> __device__ __forceinline__ float2 vmake<2>(const float *v) { return make_float2(v[0], v[1]); }
+template <> __device__ __forceinline__ float4 vmake<4>(const float *v) { return make_float4(v[0], v[1], v[2], v[3]); }
+
+template <int V> __device__ __forceinline__ float vget(const typename VecT<V>::type &a, int v);
+template <> __device__ __forceinline__ float vget<1>(const float &a, int) { return a; }
+template <> __device__ __forceinline__ float vget<2>(const float2 &a, int v) { return v == 0 ? a.x : a.y; }
+template <> __device__ __forceinline__ float vget<4>(const float4 &a, int v) { return v == 0 ? a.x : (v == 1 ? a.y : (v == 2 ? a.z : a.w)); }
+
+// points [b,c,n]; idx [b,per]; out [b,c,per]; per % 4 == 0.  CH = channels staged per fill (multiple of V),
+// chunks = ceil(c / CH), per4 = per / 4, wpc = work (quads) per CTA.
+template <int V>
+__global__ void __launch_bounds__(kGroupThreads) group_fwd_kernel(const float *__restrict__ points, const int *__restrict__ idx,
+                                                                 float *__restrict__ out, int c, int n, int per4, int CH, int chunks,
+                                                                 long long total, long long wpc, int streaming) {
+  extern __shared__ __align__(16) float s_rows[];  // [CH/V][n][V]
+  using Vec = typename VecT<V>::type;
+  Vec *srow = reinterpret_cast<Vec *>(s_rows);
+  const int tid = threadIdx.x;
+  long long w = (long long)blockIdx.x * wpc;
+  const long long wend = min(total, w + wpc);
+  const int G = CH / V;
+  const size_t per = (size_t)per4 * 4;
+
+  while (w < wend) {
+    const long long pair = w / per4;
+    const int q0 = (int)(w - pair * per4);
+    const int q1 = (int)min((long long)per4, (long long)q0 + (wend - w));
+    const int scene = (int)(pair / chunks), chunk = (int)(pair - (long long)scene * chunks);
+    const int ch_base = chunk * CH;
+    const int gcount = min(G, (c - ch_base + V - 1) / V);
+
+    // ---- fill: rows of this chunk, V channels interleaved per point ----
+    __syncthreads();
+    for (int g = 0; g < gcount; ++g) {
+      const float *src = points + ((size_t)scene * c + ch_base + g * V) * n;
+      const int nv = min(V, c - (ch_base + g * V));
+      for (int i = tid; i < n; i += kGroupThreads) {
+        float v[V];
+#pragma unroll
+        for (int e = 0; e < V; ++e) v[e] = e < nv ? __ldg(src + (size_t)e * n + i) : 0.f;
+        srow[(size_t)g * n + i] = vmake<V>(v);
+      }
+    }
+    __syncthreads();
+
+    // ---- sweep: 4 consecutive positions per thread ----
+    const int *ip = idx + (size_t)scene * per;
+    for (int q = q0 + tid; q < q1; q += kGroupThreads) {
+      const int4 id = ld_nc_i4(ip + (size_t)q * 4);
+      for (int g = 0; g < gcount; ++g) {
+        const Vec *row = srow + (size_t)g * n;
+        const Vec a0 = row[id.x], a1 = row[id.y], a2 = row[id.z], a3 = row[id.w];
+        const int ch0 = ch_base + g * V;
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+          if (ch0 + e < c) {
+            float *dst = out + ((size_t)scene * c + ch0 + e) * per + (size_t)q * 4;
+            const float4 o = make_float4(vget<V>(a0, e), vget<V>(a1, e), vget<V>(a2, e), vget<V>(a3, e));
+            if (streaming) st_cs_f4(dst, o);
+            else *reinterpret_cast<float4 *>(dst) = o;
+          }
+        }
+      }
+    }
+    w += (q1 - q0);
+  }
+}
+
+// generic fallback (any shape / alignment): one thread per output element, gathers straight from global/L2
+__global__ void group_fwd_generic_kernel(const float *__restrict__ points, const int *__restrict__ idx, float *__restrict__ out, int c,
+                                         int n, size_t per, size_t total) {
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t row = e / per, pos = e - row * per;
+    const size_t scene = row / c;
+    out[e] = __ldg(points + row * n + __ldg(idx + scene * per + pos));
+  }
+}
+
+// ---- backward: warp-aggregated scatter-add ----------------------------------------------------------------------
+// Sum `val` over runs of adjacent lanes with equal `key`; returns true on the first lane of each run (which then holds
+// the run total).  Runs are found with one ballot; the doubling steps never cross a run boundary.
+__device__ __forceinline__ bool warp_run_reduce(int key, float &val) {
+  const unsigned lane = lane_id();
+  const int prev = __shfl_up_sync(0xffffffffu, key, 1);
+  const bool head = (lane == 0) || (prev != key);
+  const unsigned heads = __ballot_sync(0xffffffffu, head);
+  // lanes strictly after me up to the next head belong to my run
+  const unsigned after = lane == 31 ? 0u : (heads >> (lane + 1));
+  const int run = after ? (__ffs(after) - 1) : (31 - (int)lane);  // number of followers in my run
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const float other = __shfl_down_sync(0xffffffffu, val, d);
+    // my partial covers min(run+1, d) lanes; add the block starting d lanes away if it is still inside my run
+    if ((int)d <= run) val += other;
+  }
+  return head;
+}
+
+// grad_out [b,c,per]; idx [b,per]; grad_points [b,c,n] (+=).  One thread per 4 consecutive positions; grid.y = rows (b*c).
+__global__ void __launch_bounds__(256) group_bwd_kernel(const float *__restrict__ grad_out, const int *__restrict__ idx,
+                                                        float *__restrict__ grad_points, int c, int n, int per4) {
+  const size_t row = blockIdx.y;
+  const size_t scene = row / c;
+  const size_t per = (size_t)per4 * 4;
+  const float *g = grad_out + row * per;
+  const int *ip = idx + scene * per;
+  float *dst = grad_points + row * n;
+  const int qbase = blockIdx.x * (256 * 4);
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int q = qbase + it * 256 + threadIdx.x;
+    const bool ok = q < per4;  // warp-uniform except in the last warp; shuffles below are executed by all lanes
+    int4 id = make_int4(-1, -2, -3, -4);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ok) {
+      id = ld_nc_i4(ip + (size_t)q * 4);
+      v = ld_nc_na_f4(g + (size_t)q * 4);
+    }
+    const bool uniform = ok && id.x == id.y && id.y == id.z && id.z == id.w;
+    // lanes whose quad is one repeated index (padding) join a run reduction; others get a unique negative key
+    int key = uniform ? id.x : -1 - (int)lane_id();
+    float val = uniform ? ((v.x + v.y) + (v.z + v.w)) : 0.f;
+    const unsigned any_uniform = __ballot_sync(0xffffffffu, uniform);
+    bool head = true;
+    if (any_uniform) head = warp_run_reduce(key, val);
+    if (uniform) {
+      if (head) atomicAdd(dst + id.x, val);
+    } else if (ok) {
+      // within-quad combining of adjacent equal indices, then one red per distinct run
+      float acc = v.x;
+      if (id.y == id.x) acc += v.y; else { atomicAdd(dst + id.x, acc); acc = v.y; }
+      if (id.z == id.y) acc += v.z; else { atomicAdd(dst + id.y, acc); acc = v.z; }
+      if (id.w == id.z) acc += v.w; else { atomicAdd(dst + id.z, acc); acc = v.w; }
+      atomicAdd(dst + id.w, acc);
+    }
+  }
+}
+
+__global__ void group_bwd_generic_kernel(const float *__restrict__ grad_out, const int *__restrict__ idx, float *__restrict__ grad_points,
+                                         int c, int n, size_t per, size_t total) {
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t row = e / per, pos = e - row * per;
+    const size_t scene = row / c;
+    atomicAdd(grad_points + row * n + __ldg(idx + scene * per + pos), __ldg(grad_out + e));
+  }
+}
+
+// ---- gather (C x m, tiny) ------------------------------------------------------------------------------------------
+__global__ void gather_fwd_kernel(const float *__restrict__ points, const int *__restrict__ idx, float *__restrict__ out, int c, int n,
+                                  int m, size_t total) {
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t row = e / m, j = e - row * m;
+    const size_t scene = row / c;
+    out[e] = __ldg(points + row * n + __ldg(idx + scene * m + j));
+  }
+}
+__global__ void gather_bwd_kernel(const float *__restrict__ grad_out, const int *__restrict__ idx, float *__restrict__ grad_points, int c,
+                                  int n, int m, size_t total) {
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t row = e / m, j = e - row * m;
+    const size_t scene = row / c;
+    atomicAdd(grad_points + row * n + __ldg(idx + scene * m + j), __ldg(grad_out + e));
+  }
+}
+
+static inline unsigned grid_for(size_t total, int threads) {
+  size_t g = (total + threads - 1) / threads;
+  const size_t cap = (size_t)num_sms() * 32;
+  return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+template <int V>
+static int launch_group_fwd(const float *points, const int *idx, float *out, int b, int c, int n, size_t per, int CH, cudaStream_t s) {
+  auto kern = group_fwd_kernel<V>;
+  const size_t smem = (size_t)CH * n * sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  const int chunks = (c + CH - 1) / CH;
+  const int per4 = (int)(per / 4);
+  const long long total = (long long)b * chunks * per4;
+  int ctas_per_sm = (int)((220u * 1024u) / (smem + 1024));
+  ctas_per_sm = ctas_per_sm < 1 ? 1 : (ctas_per_sm > 4 ? 4 : ctas_per_sm);
+  long long ctas = (long long)num_sms() * ctas_per_sm;
+  if (g_tuning.group_split > 0) ctas *= g_tuning.group_split;
+  const long long min_w = 2 * kGroupThreads;  // do not cut finer than two sweeps of the block
+  if (ctas * min_w > total) ctas = (total + min_w - 1) / min_w;
+  if (ctas < 1) ctas = 1;
+  const long long wpc = (total + ctas - 1) / ctas;
+  ctas = (total + wpc - 1) / wpc;
+  kern<<<(unsigned)ctas, kGroupThreads, smem, s>>>(points, idx, out, c, n, per4, CH, chunks, total, wpc, (g_tuning.group_mode & 1) ? 0 : 1);
+  count_launch();
+  return finish_launch();
+}
+
+}  // namespace gb
+
+using namespace gb;
+
+extern "C" int gb_group_fwd(const float *points, const int *idx, float *out, int b, int c, int n, int npoints, int nsample,
+                            gb_stream_t stream) {
+  if (b < 0 || c < 0 || n <= 0 || npoints < 0 || nsample < 0 || !points || !idx || !out) return (int)cudaErrorInvalidValue;
+  const size_t per = (size_t)npoints * nsample;
+  if (b == 0 || c == 0 || per == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool aligned = (per % 4 == 0) && (((uintptr_t)idx | (uintptr_t)out) & 15u) == 0 && per / 4 < (1u << 30);
+  const size_t row_bytes = (size_t)n * sizeof(float);
+  const size_t big = 200u * 1024u;
+  if (aligned && row_bytes <= big && !(g_tuning.group_mode & 2)) {
+    // channels per fill: as many as fit (V-interleaved), aiming at <= ~100 KB so that two CTAs share an SM when rows are small
+    int V = c >= 4 && 4 * row_bytes <= big ? 4 : (c >= 2 && 2 * row_bytes <= big ? 2 : 1);
+    const size_t budget = (size_t)V * row_bytes > 100u * 1024u ? big : 100u * 1024u;
+    int CH = (int)(budget / row_bytes);
+    CH -= CH % V;
+    if (CH > ((c + V - 1) / V) * V) CH = ((c + V - 1) / V) * V;
+    if (CH > 64) CH = 64;
+    if (V == 4) return launch_group_fwd<4>(points, idx, out, b, c, n, per, CH, s);
+    if (V == 2) return launch_group_fwd<2>(points, idx, out, b, c, n, per, CH, s);
+    return launch_group_fwd<1>(points, idx, out, b, c, n, per, CH, s);
+  }
+  const size_t total = (size_t)b * c * per;
+  group_fwd_generic_kernel<<<grid_for(total, 256), 256, 0, s>>>(points, idx, out, c, n, per, total);
+  count_launch();
+  return finish_launch();
+}
+
+extern "C" int gb_group_bwd(const float *grad_out, const int *idx, float *grad_points, int b, int c, int n, int npoints,
+                            int nsample, gb_stream_t stream) {
+  if (b < 0 || c < 0 || n <= 0 || npoints < 0 || nsample < 0 || !grad_out || !idx || !grad_points) return (int)cudaErrorInvalidValue;
+  const size_t per = (size_t)npoints * nsample;
+  if (b == 0 || c == 0 || per == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool aligned = (per % 4 == 0) && (((uintptr_t)idx | (uintptr_t)grad_out) & 15u) == 0 && (size_t)b * c <= 65535 && per / 4 < (1u << 30);
+  if (aligned) {
+    const int per4 = (int)(per / 4);
+    dim3 grid((per4 + 1023) / 1024, b * c);
+    group_bwd_kernel<<<grid, 256, 0, s>>>(grad_out, idx, grad_points, c, n, per4);
+  } else {
+    const size_t total = (size_t)b * c * per;
+    group_bwd_generic_kernel<<<grid_for(total, 256), 256, 0, s>>>(grad_out, idx, grad_points, c, n, per, total);
+  }
+  count_launch();
+  return finish_launch();
+}
+
+extern "C" int gb_gather_fwd(const float *points, const int *idx, float *out, int b, int c, int n, int m, gb_stream_t stream) {
+  if (b < 0 || c < 0 || n <= 0 || m < 0 || !points || !idx || !out) return (int)cudaErrorInvalidValue;
+  const size_t total = (size_t)b * c * m;
+  if (total == 0) return 0;
+  gather_fwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(points, idx, out, c, n, m, total);
+  count_launch();
+  return finish_launch();
+}
+
+extern "C" int gb_gather_bwd(const float *grad_out, const int *idx, float *grad_points, int b, int c, int n, int m,
+                             gb_stream_t stream) {
+  if (b < 0 || c < 0 || n <= 0 || m < 0 || !grad_out || !idx || !grad_points) return (int)cudaErrorInvalidValue;
+  const size_t total = (size_t)b * c * m;
+  if (total == 0) return 0;
+  gather_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(grad_out, idx, grad_points, c, n, m, total);
+  count_launch();
+  return finish_launch();
+}

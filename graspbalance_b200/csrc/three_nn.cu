@@ -1,0 +1,71 @@
+// three_nn.cu -- three nearest "known" points for every "unknown" point.
+//
+// Replaces three_nn_kernel (PointNet/_ext_src/src/interpolate_gpu.cu:14-64, one block per scene) and three_nn_kernel_fast
+// (pointnet2_batch/src/interpolate_gpu.cu:16-59).  One thread per unknown; the known set is staged in shared memory as
+// float4 so that every candidate costs one broadcast LDS.128 instead of three dependent global loads.
+//
+// Semantics: candidates in ascending index, strict `<` cascade so the lowest index wins ties; the
+// reference keeps its bests as double initialised to 1e40 -- a float compared as double is exact, and (float)1e40 is
+// +inf, so float bests initialised to +inf give identical outputs (including +inf distances and index 0 when m < 3).
+// Outputs SQUARED distances; the Python wrappers take the sqrt (pointnet2_utils.py:84, upsampling.py:26).
+#include "common.cuh"
+
+namespace gb {
+
+constexpr int kNNThreads = 256;
+constexpr int kNNTile = 2048;  // known points per shared-memory tile (32 KB as float4)
+
+__global__ void __launch_bounds__(kNNThreads) three_nn_kernel(const float *__restrict__ unknown, const float *__restrict__ known,
+                                                              float *__restrict__ dist2, int *__restrict__ idx, int n, int m) {
+  __shared__ float4 tile[kNNTile];
+  const int scene = blockIdx.y;
+  const int j = blockIdx.x * kNNThreads + threadIdx.x;
+  known += (size_t)scene * m * 3;
+  const bool ok = j < n;
+  const size_t uj = (size_t)scene * n + (ok ? j : 0);
+  const float ux = __ldg(unknown + uj * 3), uy = __ldg(unknown + uj * 3 + 1), uz = __ldg(unknown + uj * 3 + 2);
+
+  float b1 = __int_as_float(0x7f800000), b2 = b1, b3 = b1;
+  int i1 = 0, i2 = 0, i3 = 0;
+  for (int base = 0; base < m; base += kNNTile) {
+    const int tc = min(kNNTile, m - base);
+    __syncthreads();
+    for (int e = threadIdx.x; e < tc; e += kNNThreads) {
+      const float *p = known + (size_t)(base + e) * 3;
+      tile[e] = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), 0.f);
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int k = 0; k < tc; ++k) {
+      const float4 p = tile[k];
+      const float d = sqdist3(ux - p.x, uy - p.y, uz - p.z);
+      if (d < b3) {  // b1 <= b2 <= b3 always, so this guard is equivalent to the reference's three-way cascade
+        const int kk = base + k;
+        if (d < b1) {
+          b3 = b2, i3 = i2, b2 = b1, i2 = i1, b1 = d, i1 = kk;
+        } else if (d < b2) {
+          b3 = b2, i3 = i2, b2 = d, i2 = kk;
+        } else {
+          b3 = d, i3 = kk;
+        }
+      }
+    }
+  }
+  if (ok) {
+    dist2[uj * 3] = b1, dist2[uj * 3 + 1] = b2, dist2[uj * 3 + 2] = b3;
+    idx[uj * 3] = i1, idx[uj * 3 + 1] = i2, idx[uj * 3 + 2] = i3;
+  }
+}
+
+}  // namespace gb
+
+extern "C" int gb_three_nn(const float *unknown, const float *known, float *dist2, int *idx, int b, int n, int m,
+                           gb_stream_t stream) {
+  if (b < 0 || n < 0 || m < 0 || !unknown || !known || !dist2 || !idx) return (int)cudaErrorInvalidValue;
+  if (b == 0 || n == 0) return 0;
+  if (b > 65535) return (int)cudaErrorInvalidValue;
+  dim3 grid((n + gb::kNNThreads - 1) / gb::kNNThreads, b);
+  gb::three_nn_kernel<<<grid, gb::kNNThreads, 0, (cudaStream_t)stream>>>(unknown, known, dist2, idx, n, m);
+  gb::count_launch();
+  return gb::finish_launch();
+}
