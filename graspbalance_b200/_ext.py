@@ -1,0 +1,207 @@
+"""Drop-in for the reference's native module A, `pointnet2._ext` (PointNet/_ext_src/src/bindings.cpp:12-27).
+
+Same ten function names, argument order, dtypes, layouts and ownership (outputs are allocated here and returned) as the
+pybind11 module; the input checks raise RuntimeError with the reference's TORCH_CHECK messages (_ext_src/include/utils.h:
+10-30, "CPU not supported" for CPU tensors).  The work is done by libgbops.so through the C ABI (include/gbops.h) on
+torch's current stream.  Unlike the reference, a CUDA failure raises instead of calling exit(-1) (cuda_utils.h:38-47).
+"""
+import torch
+
+from . import _lib
+
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+class _on:
+    """Make the tensor's device current for the launch (the reference relies on the caller's current device)."""
+
+    def __init__(self, t):
+        self.dev = t.device.index
+        self.prev = None
+
+    def __enter__(self):
+        cur = torch.cuda.current_device()
+        if self.dev is not None and self.dev != cur:
+            self.prev = cur
+            torch.cuda.set_device(self.dev)
+
+    def __exit__(self, *a):
+        if self.prev is not None:
+            torch.cuda.set_device(self.prev)
+
+
+def _contig(x, name):
+    if not x.is_contiguous():
+        raise RuntimeError(f"{name} must be a contiguous tensor")
+
+
+def _is_float(x, name):
+    if x.dtype != torch.float32:
+        raise RuntimeError(f"{name} must be a float tensor")
+
+
+def _is_int(x, name):
+    if x.dtype != torch.int32:
+        raise RuntimeError(f"{name} must be an int tensor")
+
+
+def _cuda(x, name):
+    if not x.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+
+
+def _need_cuda(x):
+    if not x.is_cuda:
+        raise RuntimeError("CPU not supported")
+
+
+def gather_points(points, idx):
+    """sampling.cpp:20-43.  points [B,C,N] f32, idx [B,M] i32 -> [B,C,M]."""
+    _contig(points, "points"); _contig(idx, "idx"); _is_float(points, "points"); _is_int(idx, "idx")
+    if points.is_cuda:
+        _cuda(idx, "idx")
+    _need_cuda(points)
+    B, C, N = points.shape
+    M = idx.shape[1]
+    out = torch.empty((B, C, M), dtype=torch.float32, device=points.device)
+    with _on(points):
+        _lib.check(_lib.lib().gb_gather_fwd(points.data_ptr(), idx.data_ptr(), out.data_ptr(), B, C, N, M, _stream(points)),
+                   "gather_points")
+    return out
+
+
+def gather_points_grad(grad_out, idx, n):
+    """sampling.cpp:45-69.  grad_out [B,C,M], idx [B,M] -> [B,C,n]."""
+    _contig(grad_out, "grad_out"); _contig(idx, "idx"); _is_float(grad_out, "grad_out"); _is_int(idx, "idx")
+    if grad_out.is_cuda:
+        _cuda(idx, "idx")
+    _need_cuda(grad_out)
+    B, C, M = grad_out.shape
+    out = torch.zeros((B, C, n), dtype=torch.float32, device=grad_out.device)
+    with _on(grad_out):
+        _lib.check(_lib.lib().gb_gather_bwd(grad_out.data_ptr(), idx.data_ptr(), out.data_ptr(), B, C, int(n), M,
+                                            _stream(grad_out)), "gather_points_grad")
+    return out
+
+
+def furthest_point_sampling(points, nsamples):
+    """sampling.cpp:70-91.  points [B,N,3] f32 -> [B,nsamples] i32 (variant A: norm skip, 512-thread tie order)."""
+    _contig(points, "points"); _is_float(points, "points")
+    _need_cuda(points)
+    B, N = points.shape[0], points.shape[1]
+    out = torch.zeros((B, int(nsamples)), dtype=torch.int32, device=points.device)
+    with _on(points):
+        _lib.check(_lib.lib().gb_fps(points.data_ptr(), None, out.data_ptr(), B, N, int(nsamples), 0, _stream(points)),
+                   "furthest_point_sampling")
+    return out
+
+
+def three_nn(unknowns, knows):
+    """interpolate.cpp:19-45.  unknowns [B,n,3], knows [B,m,3] -> [dist2 [B,n,3] f32 (squared), idx [B,n,3] i32]."""
+    _contig(unknowns, "unknowns"); _contig(knows, "knows"); _is_float(unknowns, "unknowns"); _is_float(knows, "knows")
+    if unknowns.is_cuda:
+        _cuda(knows, "knows")
+    _need_cuda(unknowns)
+    B, n = unknowns.shape[0], unknowns.shape[1]
+    m = knows.shape[1]
+    idx = torch.empty((B, n, 3), dtype=torch.int32, device=unknowns.device)
+    dist2 = torch.empty((B, n, 3), dtype=torch.float32, device=unknowns.device)
+    with _on(unknowns):
+        _lib.check(_lib.lib().gb_three_nn(unknowns.data_ptr(), knows.data_ptr(), dist2.data_ptr(), idx.data_ptr(), B, n, m,
+                                          _stream(unknowns)), "three_nn")
+    return [dist2, idx]
+
+
+def three_interpolate(points, idx, weight):
+    """interpolate.cpp:47-75.  points [B,C,m], idx/weight [B,n,3] -> [B,C,n]."""
+    _contig(points, "points"); _contig(idx, "idx"); _contig(weight, "weight")
+    _is_float(points, "points"); _is_int(idx, "idx"); _is_float(weight, "weight")
+    if points.is_cuda:
+        _cuda(idx, "idx"); _cuda(weight, "weight")
+    _need_cuda(points)
+    B, C, m = points.shape
+    n = idx.shape[1]
+    out = torch.empty((B, C, n), dtype=torch.float32, device=points.device)
+    with _on(points):
+        _lib.check(_lib.lib().gb_three_interp_fwd(points.data_ptr(), idx.data_ptr(), weight.data_ptr(), out.data_ptr(), B, C, m,
+                                                  n, _stream(points)), "three_interpolate")
+    return out
+
+
+def three_interpolate_grad(grad_out, idx, weight, m):
+    """interpolate.cpp:76-104.  grad_out [B,C,n] -> [B,C,m]."""
+    _contig(grad_out, "grad_out"); _contig(idx, "idx"); _contig(weight, "weight")
+    _is_float(grad_out, "grad_out"); _is_int(idx, "idx"); _is_float(weight, "weight")
+    if grad_out.is_cuda:
+        _cuda(idx, "idx"); _cuda(weight, "weight")
+    _need_cuda(grad_out)
+    B, C, n = grad_out.shape
+    out = torch.zeros((B, C, int(m)), dtype=torch.float32, device=grad_out.device)
+    with _on(grad_out):
+        _lib.check(_lib.lib().gb_three_interp_bwd(grad_out.data_ptr(), idx.data_ptr(), weight.data_ptr(), out.data_ptr(), B, C,
+                                                  n, int(m), _stream(grad_out)), "three_interpolate_grad")
+    return out
+
+
+def ball_query(new_xyz, xyz, radius, nsample):
+    """ball_query.cpp:13-37.  new_xyz [B,m,3], xyz [B,N,3] -> idx [B,m,nsample] i32."""
+    _contig(new_xyz, "new_xyz"); _contig(xyz, "xyz"); _is_float(new_xyz, "new_xyz"); _is_float(xyz, "xyz")
+    if new_xyz.is_cuda:
+        _cuda(xyz, "xyz")
+    _need_cuda(new_xyz)
+    B, m = new_xyz.shape[0], new_xyz.shape[1]
+    N = xyz.shape[1]
+    idx = torch.empty((B, m, int(nsample)), dtype=torch.int32, device=new_xyz.device)
+    with _on(new_xyz):
+        _lib.check(_lib.lib().gb_ball_query(new_xyz.data_ptr(), xyz.data_ptr(), idx.data_ptr(), B, N, m, float(radius),
+                                            int(nsample), _stream(new_xyz)), "ball_query")
+    return idx
+
+
+def cylinder_query(new_xyz, xyz, rot, radius, hmin, hmax, nsample):
+    """cylinder_query.cpp:10-47.  rot [B,m,9] row-major 3x3 per query."""
+    _contig(new_xyz, "new_xyz"); _contig(xyz, "xyz"); _contig(rot, "rot")
+    _is_float(new_xyz, "new_xyz"); _is_float(xyz, "xyz"); _is_float(rot, "rot")
+    if new_xyz.is_cuda:
+        _cuda(xyz, "xyz"); _cuda(rot, "rot")
+    _need_cuda(new_xyz)
+    B, m = new_xyz.shape[0], new_xyz.shape[1]
+    N = xyz.shape[1]
+    idx = torch.empty((B, m, int(nsample)), dtype=torch.int32, device=new_xyz.device)
+    with _on(new_xyz):
+        _lib.check(_lib.lib().gb_cylinder_query(new_xyz.data_ptr(), xyz.data_ptr(), rot.data_ptr(), idx.data_ptr(), B, N, m,
+                                                float(radius), float(hmin), float(hmax), int(nsample), _stream(new_xyz)),
+                   "cylinder_query")
+    return idx
+
+
+def group_points(points, idx):
+    """group_points.cpp:21-47.  points [B,C,N], idx [B,npoints,nsample] -> [B,C,npoints,nsample]."""
+    _contig(points, "points"); _contig(idx, "idx"); _is_float(points, "points"); _is_int(idx, "idx")
+    if points.is_cuda:
+        _cuda(idx, "idx")
+    _need_cuda(points)
+    B, C, N = points.shape
+    npoints, nsample = idx.shape[1], idx.shape[2]
+    out = torch.empty((B, C, npoints, nsample), dtype=torch.float32, device=points.device)
+    with _on(points):
+        _lib.check(_lib.lib().gb_group_fwd(points.data_ptr(), idx.data_ptr(), out.data_ptr(), B, C, N, npoints, nsample,
+                                           _stream(points)), "group_points")
+    return out
+
+
+def group_points_grad(grad_out, idx, n):
+    """group_points.cpp:49-75.  grad_out [B,C,npoints,nsample] -> [B,C,n]."""
+    _contig(grad_out, "grad_out"); _contig(idx, "idx"); _is_float(grad_out, "grad_out"); _is_int(idx, "idx")
+    if grad_out.is_cuda:
+        _cuda(idx, "idx")
+    _need_cuda(grad_out)
+    B, C = grad_out.shape[0], grad_out.shape[1]
+    npoints, nsample = idx.shape[1], idx.shape[2]
+    out = torch.zeros((B, C, int(n)), dtype=torch.float32, device=grad_out.device)
+    with _on(grad_out):
+        _lib.check(_lib.lib().gb_group_bwd(grad_out.data_ptr(), idx.data_ptr(), out.data_ptr(), B, C, int(n), npoints, nsample,
+                                           _stream(grad_out)), "group_points_grad")
+    return out

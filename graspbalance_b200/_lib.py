@@ -1,0 +1,94 @@
+"""ctypes binding of libgbops.so (the C ABI declared in include/gbops.h).
+
+The library is built in-tree by `make -C graspbalance_b200/csrc` (see __graft_entry__.build).  There is NO fallback:
+if the shared object is missing or a CUDA call fails, the operators raise.
+"""
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgbops.so")
+CSRC = os.path.join(_HERE, "csrc")
+ABI_VERSION = 1
+
+_lib = None
+
+_vp, _i, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+
+# name -> argtypes (restype is int unless listed in _RESTYPES); must match include/gbops.h
+SIGNATURES = {
+    "gb_abi_version": [],
+    "gb_error_string": [_i],
+    "gb_fps": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "gb_gather_fwd": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "gb_gather_bwd": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "gb_ball_query": [_vp, _vp, _vp, _i, _i, _i, _f, _i, _vp],
+    "gb_cylinder_query": [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _f, _i, _vp],
+    "gb_group_fwd": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "gb_group_bwd": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "gb_three_nn": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp],
+    "gb_three_interp_fwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "gb_three_interp_bwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "gb_knn": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "gb_collision_counts": [_vp, _i, _vp, _vp, _vp, _i, _vp, _vp],
+    "gb_collision_counts_host": [_vp, _i, _vp, _vp, _vp, _i, _vp],
+    "gb_set_tuning": [ctypes.c_char_p, _i],
+    "gb_get_tuning": [ctypes.c_char_p, ctypes.POINTER(ctypes.c_int)],
+    "gb_launch_count": [],
+}
+_RESTYPES = {"gb_error_string": ctypes.c_char_p, "gb_launch_count": ctypes.c_uint64}
+
+
+def build(force=False, verbose=False):
+    """Compile libgbops.so for sm_100a with nvcc (cross-compiles without a GPU)."""
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))]
+    srcs.append(os.path.join(os.path.dirname(_HERE), "include", "gbops.h"))
+    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
+        return LIB_PATH
+    r = subprocess.run(["make", "-C", CSRC, "-j8"] + (["-B"] if force else []), stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True)
+    if verbose or r.returncode != 0:
+        print(r.stdout)
+    if r.returncode != 0:
+        raise RuntimeError("building libgbops.so failed (see output above)")
+    return LIB_PATH
+
+
+def lib():
+    """The loaded library.  Raises (never falls back) when it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(graspbalance_b200 has no CPU or PyTorch fallback)")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, args in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.argtypes = args
+            fn.restype = _RESTYPES.get(name, ctypes.c_int)
+        if L.gb_abi_version() != ABI_VERSION:
+            raise RuntimeError("libgbops.so ABI version mismatch: rebuild it")
+        _lib = L
+    return _lib
+
+
+def check(err, what):
+    if err != 0:
+        msg = lib().gb_error_string(err)
+        raise RuntimeError(f"{what}: CUDA error {err} ({msg.decode() if msg else '?'})")
+
+
+def set_tuning(key, value):
+    check(lib().gb_set_tuning(key.encode(), int(value)), f"gb_set_tuning({key})")
+
+
+def get_tuning(key):
+    v = ctypes.c_int(0)
+    check(lib().gb_get_tuning(key.encode(), ctypes.byref(v)), f"gb_get_tuning({key})")
+    return v.value
+
+
+def launch_count():
+    return int(lib().gb_launch_count())

@@ -227,6 +227,8 @@ __global__ void fill_kernel(float *p, size_t n, float v) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }
 
+constexpr int kFpsRetrySmallerCluster = -1001;  // internal: cluster shape not schedulable, try half the size
+
 template <int P, int T>
 static int launch_fps(const float *xyz, float *temp, int *idx, int b, int n, int m, int variant, int L, int C, cudaStream_t s) {
   auto kern = fps_cluster_kernel<P, T>;
@@ -249,6 +251,15 @@ static int launch_fps(const float *xyz, float *temp, int *idx, int b, int n, int
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
+  if (C > 1) {
+    // can the device co-schedule a cluster of this size with this much shared memory?  (C = 16 is non-portable)
+    int nclusters = 0;
+    e = cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg);
+    if (e != cudaSuccess || nclusters < 1) {
+      (void)cudaGetLastError();
+      return kFpsRetrySmallerCluster;
+    }
+  }
   e = cudaLaunchKernelEx(&cfg, kern, xyz, temp, idx, n, m, variant, L);
   count_launch();
   return (int)e;
@@ -278,34 +289,41 @@ extern "C" int gb_fps(const float *xyz, float *temp, int *idx, int b, int n, int
 
   // ---- configuration: cluster size C, threads T, points per thread P, with C*T >= BS (tie-key alignment) ----
   const int sms = num_sms();
-  int C = g_tuning.fps_cluster, T = g_tuning.fps_threads;
+  int C = g_tuning.fps_cluster;
   if (C != 1 && C != 2 && C != 4 && C != 8 && C != 16) C = 0;
-  if (T != 512 && T != 1024) T = 0;
   if (C == 0) {
     // as many CTAs per scene as fit on the chip at two CTAs per SM, but not fewer than ~2048 points per CTA (below
     // that the DSMEM hop costs more than the shorter register sweep saves)
     C = 16;
     while (C > 1 && ((long)b * C > 2L * sms || n / C < 2048)) C >>= 1;
-    // capacity: the largest per-CTA register tile is 512 threads x 20 points
+    // capacity: the largest per-CTA register tile is 512 threads x 20 points (= 1024 x 10)
     while (C < 16 && (long)C * 512 * 20 < n) C <<= 1;
   }
-  if (T == 0) {
-    const int per_cta = (n + C - 1) / C;
-    // 1024 threads (<= 10 points each) give the shortest round; 512 threads with <= 64 registers let two CTAs
-    // share an SM when there are more clusters than the chip holds at one CTA per SM
-    T = (b * C > sms && per_cta <= 512 * 5) ? 512 : 1024;
-  }
-  while (C * T < bs && T < 1024) T <<= 1;
-  while (C * T < bs && C < 16) C <<= 1;
-  const int per_thread = (int)(((long)n + (long)C * T - 1) / ((long)C * T));
-
+  for (; C >= 1; C >>= 1) {
+    int T = g_tuning.fps_threads;
+    if (T != 512 && T != 1024) {
+      const int per_cta = (n + C - 1) / C;
+      // 1024 threads (<= 10 points each) give the shortest round; 512 threads with <= 64 registers let two CTAs
+      // share an SM when there are more clusters than the chip holds at one CTA per SM
+      T = (b * C > sms && per_cta <= 512 * 5) ? 512 : 1024;
+    }
+    int Ce = C;
+    while (Ce * T < bs && T < 1024) T <<= 1;
+    while (Ce * T < bs && Ce < 16) Ce <<= 1;
+    const int per_thread = (int)(((long)n + (long)Ce * T - 1) / ((long)Ce * T));
+    int rc = kFpsRetrySmallerCluster - 1;  // "no instantiation"
 #define GB_FPS_CASE(PP, TT) \
-  if (T == TT && per_thread <= PP) return launch_fps<PP, TT>(xyz, temp, idx, b, n, m, variant, L, C, s);
-  GB_FPS_CASE(1, 1024) GB_FPS_CASE(2, 1024) GB_FPS_CASE(3, 1024) GB_FPS_CASE(4, 1024) GB_FPS_CASE(5, 1024)
-  GB_FPS_CASE(6, 1024) GB_FPS_CASE(8, 1024) GB_FPS_CASE(10, 1024)
-  GB_FPS_CASE(1, 512) GB_FPS_CASE(2, 512) GB_FPS_CASE(3, 512) GB_FPS_CASE(4, 512) GB_FPS_CASE(5, 512) GB_FPS_CASE(6, 512)
-  GB_FPS_CASE(8, 512) GB_FPS_CASE(10, 512) GB_FPS_CASE(12, 512) GB_FPS_CASE(16, 512) GB_FPS_CASE(20, 512)
+  else if (T == TT && per_thread <= PP) rc = launch_fps<PP, TT>(xyz, temp, idx, b, n, m, variant, L, Ce, s);
+    if (false) {}
+    GB_FPS_CASE(1, 1024) GB_FPS_CASE(2, 1024) GB_FPS_CASE(3, 1024) GB_FPS_CASE(4, 1024) GB_FPS_CASE(5, 1024)
+    GB_FPS_CASE(6, 1024) GB_FPS_CASE(8, 1024) GB_FPS_CASE(10, 1024)
+    GB_FPS_CASE(1, 512) GB_FPS_CASE(2, 512) GB_FPS_CASE(3, 512) GB_FPS_CASE(4, 512) GB_FPS_CASE(5, 512) GB_FPS_CASE(6, 512)
+    GB_FPS_CASE(8, 512) GB_FPS_CASE(10, 512) GB_FPS_CASE(12, 512) GB_FPS_CASE(16, 512) GB_FPS_CASE(20, 512)
 #undef GB_FPS_CASE
+    if (rc == kFpsRetrySmallerCluster) continue;     // this cluster size cannot be scheduled: halve it
+    if (rc == kFpsRetrySmallerCluster - 1) break;    // scene does not fit in the registers of C CTAs
+    return rc;
+  }
 
   // does not fit in registers: global-memory fallback (needs a temp buffer)
   float *tmp = temp;

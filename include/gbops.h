@@ -28,71 +28,77 @@ extern "C" {
 
 typedef void *gb_stream_t; /* cudaStream_t */
 
+#if defined(__GNUC__)
+#define GB_API __attribute__((visibility("default")))
+#else
+#define GB_API
+#endif
+
 /* FPS variant: GB_FPS_A = pointnet2._ext semantics (points with |p|^2 <= 1e-3 are skipped, tie order of a
  * 512-thread block: sampling_gpu.cu:74-178); GB_FPS_B = pointnet2_batch_cuda semantics (no skip, tie order of a
  * 1024-thread block: pointnet2_batch/src/sampling_gpu.cu:73-181). */
 enum { GB_FPS_A = 0, GB_FPS_B = 1 };
 
-int gb_abi_version(void);
-const char *gb_error_string(int err);
+GB_API int gb_abi_version(void);
+GB_API const char *gb_error_string(int err);
 
 /* A: furthest_point_sampling_kernel_wrapper (sampling_gpu.cu:180-234); B: furthest_point_sampling_kernel_launcher
  * (pointnet2_batch/src/sampling_gpu.cu:183-220).
  * xyz [b,n,3] f32; idx [b,m] i32 (fully overwritten); temp [b,n] f32 or NULL.  When temp is given it is read as the
  * initial running min-distance (both reference callers fill it with 1e10) and receives the final values, as in the
  * reference; when NULL, 1e10 is used and nothing is written back. */
-int gb_fps(const float *xyz, float *temp, int *idx, int b, int n, int m, int variant, gb_stream_t stream);
+GB_API int gb_fps(const float *xyz, float *temp, int *idx, int b, int n, int m, int variant, gb_stream_t stream);
 
 /* A: gather_points_kernel_wrapper (sampling_gpu.cu:27-35); B: gather_points_kernel_launcher_fast (:21-34).
  * points [b,c,n], idx [b,m] -> out [b,c,m]. */
-int gb_gather_fwd(const float *points, const int *idx, float *out, int b, int c, int n, int m, gb_stream_t stream);
+GB_API int gb_gather_fwd(const float *points, const int *idx, float *out, int b, int c, int n, int m, gb_stream_t stream);
 
 /* A: gather_points_grad_kernel_wrapper (sampling_gpu.cu:54-62); B: gather_points_grad_kernel_launcher_fast (:50-63).
  * grad_out [b,c,m], idx [b,m]; ACCUMULATES into grad_points [b,c,n] (callers pass zeros, as the reference's do). */
-int gb_gather_bwd(const float *grad_out, const int *idx, float *grad_points, int b, int c, int n, int m,
+GB_API int gb_gather_bwd(const float *grad_out, const int *idx, float *grad_points, int b, int c, int n, int m,
                   gb_stream_t stream);
 
 /* A: query_ball_point_kernel_wrapper (ball_query_gpu.cu:46-54); B: ball_query_kernel_launcher_fast (:45-58).
  * new_xyz [b,m,3], xyz [b,n,3] -> idx [b,m,nsample] i32: the first nsample indices k (ascending) with
  * d2(k) < radius*radius, unfilled slots = first hit, all zero when there is no hit.  Every slot is written (the
  * reference relies on a zero-filled output instead). */
-int gb_ball_query(const float *new_xyz, const float *xyz, int *idx, int b, int n, int m, float radius, int nsample,
+GB_API int gb_ball_query(const float *new_xyz, const float *xyz, int *idx, int b, int n, int m, float radius, int nsample,
                   gb_stream_t stream);
 
 /* A only: query_cylinder_point_kernel_wrapper (cylinder_query_gpu.cu:89-101).  rot [b,m,9] row-major. */
-int gb_cylinder_query(const float *new_xyz, const float *xyz, const float *rot, int *idx, int b, int n, int m,
+GB_API int gb_cylinder_query(const float *new_xyz, const float *xyz, const float *rot, int *idx, int b, int n, int m,
                       float radius, float hmin, float hmax, int nsample, gb_stream_t stream);
 
 /* A: group_points_kernel_wrapper (group_points_gpu.cu:51-65); B: group_points_kernel_launcher_fast (:58-70).
  * points [b,c,n], idx [b,npoints,nsample] -> out [b,c,npoints,nsample]. */
-int gb_group_fwd(const float *points, const int *idx, float *out, int b, int c, int n, int npoints, int nsample,
+GB_API int gb_group_fwd(const float *points, const int *idx, float *out, int b, int c, int n, int npoints, int nsample,
                  gb_stream_t stream);
 
 /* A: group_points_grad_kernel_wrapper (group_points_gpu.cu:92-101); B: group_points_grad_kernel_launcher_fast (:24-37).
  * ACCUMULATES into grad_points [b,c,n]. */
-int gb_group_bwd(const float *grad_out, const int *idx, float *grad_points, int b, int c, int n, int npoints,
+GB_API int gb_group_bwd(const float *grad_out, const int *idx, float *grad_points, int b, int c, int n, int npoints,
                  int nsample, gb_stream_t stream);
 
 /* A: three_nn_kernel_wrapper (interpolate_gpu.cu:66-73); B: three_nn_kernel_launcher_fast (:62-81).
  * unknown [b,n,3], known [b,m,3] -> dist2 [b,n,3] f32 (SQUARED), idx [b,n,3] i32. */
-int gb_three_nn(const float *unknown, const float *known, float *dist2, int *idx, int b, int n, int m,
+GB_API int gb_three_nn(const float *unknown, const float *known, float *dist2, int *idx, int b, int n, int m,
                 gb_stream_t stream);
 
 /* A: three_interpolate_kernel_wrapper (interpolate_gpu.cu:108-116); B: three_interpolate_kernel_launcher_fast (:106-124).
  * points [b,c,m], idx/weight [b,n,3] -> out [b,c,n]. */
-int gb_three_interp_fwd(const float *points, const int *idx, const float *weight, float *out, int b, int c, int m,
+GB_API int gb_three_interp_fwd(const float *points, const int *idx, const float *weight, float *out, int b, int c, int m,
                         int n, gb_stream_t stream);
 
 /* A: three_interpolate_grad_kernel_wrapper (interpolate_gpu.cu:150-159); B: ..._grad_kernel_launcher_fast (:151-168).
  * ACCUMULATES into grad_points [b,c,m]. */
-int gb_three_interp_bwd(const float *grad_out, const int *idx, const float *weight, float *grad_points, int b, int c,
+GB_API int gb_three_interp_bwd(const float *grad_out, const int *idx, const float *weight, float *grad_points, int b, int c,
                         int n, int m, gb_stream_t stream);
 
 /* C: knn_device (knn.cu:217-263) looped over the batch as knn.h:31-38 does.
  * ref [b,dim,nref], query [b,dim,nquery] (channel first) -> idx [b,k,nquery] int64, 1-BASED, ascending (dist, index).
  * Needs no distance-matrix scratch (the reference allocates nref*nquery floats, knn.h:29).  Requires 1 <= k <= nref
  * and k <= 1024. */
-int gb_knn(const float *ref, const float *query, int64_t *idx, int b, int dim, int nref, int nquery, int k,
+GB_API int gb_knn(const float *ref, const float *query, int64_t *idx, int b, int dim, int nref, int nquery, int k,
            gb_stream_t stream);
 
 /* collision_detector.ModelFreeCollisionDetector.detect's grasp x point occupancy test (collision_detector.py:23-41,55),
@@ -100,12 +106,12 @@ int gb_knn(const float *ref, const float *query, int64_t *idx, int b, int dim, i
  *   {-h/2, h/2, d-fl, d, -(w/2+fw), -w/2, w/2+fw, w/2, d-fl-fw, d-fl-fw-approach}
  * evaluated by the caller with the reference's numpy expressions; counts [g,6] int64 =
  *   {global, left, right, bottom, shifting, inner} mask sums (fully overwritten). */
-int gb_collision_counts(const double *points, int np, const double *T, const double *R, const double *thr, int g,
+GB_API int gb_collision_counts(const double *points, int np, const double *T, const double *R, const double *thr, int g,
                         int64_t *counts, gb_stream_t stream);
 
 /* Host-buffer convenience entry (what a non-torch host language would bind): copies the inputs to the device,
  * runs gb_collision_counts and copies the counts back, synchronising the stream.  All pointers are HOST pointers. */
-int gb_collision_counts_host(const double *points, int np, const double *T, const double *R, const double *thr, int g,
+GB_API int gb_collision_counts_host(const double *points, int np, const double *T, const double *R, const double *thr, int g,
                              int64_t *counts);
 
 /* Tuning knobs for benchmarking sweeps (never change results).  Unknown keys return cudaErrorInvalidValue.
@@ -113,11 +119,11 @@ int gb_collision_counts_host(const double *points, int np, const double *T, cons
  *   "fps_threads"  0 = auto, else 256/512/1024
  *   "group_split"  0 = auto, else output splits per (scene, channel chunk)
  */
-int gb_set_tuning(const char *key, int value);
-int gb_get_tuning(const char *key, int *value);
+GB_API int gb_set_tuning(const char *key, int value);
+GB_API int gb_get_tuning(const char *key, int *value);
 
 /* Number of kernel launches issued through this library since load (for bench.py's gpu_launches). */
-uint64_t gb_launch_count(void);
+GB_API uint64_t gb_launch_count(void);
 
 #ifdef __cplusplus
 }

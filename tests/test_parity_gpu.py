@@ -1,0 +1,357 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).
+
+Every op is called through the reference-facing Python API of graspbalance_b200 (which goes through the C ABI of
+libgbops.so) and compared
+  * with the CPU oracle (oracle/gb_oracle.c) on seeded inputs the oracle finishes in seconds, and
+  * with the UNMODIFIED reference extensions compiled into oracle/_ref/ on the BASELINE.json shapes.
+Indices, masks and forward fp32 values must be BIT-EXACT; scatter-add gradients within 1e-5 relative (the reference's
+own float atomics are order-nondeterministic).
+"""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from graspbalance_b200 import _lib, scenes
+from graspbalance_b200 import group as gb_group
+from graspbalance_b200 import knn_modules as gb_knn
+from graspbalance_b200 import pointnet2_batch_cuda as gb_b
+from graspbalance_b200 import pointnet2_utils as pu
+from graspbalance_b200 import subsample as gb_sub
+from graspbalance_b200 import upsampling as gb_up
+from graspbalance_b200 import _ext as gb_a
+from graspbalance_b200.collision_detector import ModelFreeCollisionDetector
+
+pytestmark = pytest.mark.gpu
+
+GRAD_RTOL = 1e-5  # north_star: gradients within 1e-5 relative in fp32
+
+
+def T(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def assert_grad_close(a, b, scale=None):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    s = np.abs(b).max() if scale is None else scale
+    assert np.abs(a - b).max() <= GRAD_RTOL * max(s, 1e-30), f"max abs diff {np.abs(a - b).max()} vs scale {s}"
+
+
+def scene_with_origin_points(seed, n):
+    """tabletop scene with 32 points inside the |p|^2 <= 1e-3 skip ball of FPS variant A (incl. index 0)."""
+    xyz = scenes.tabletop_scene(seed, n)
+    rng = np.random.default_rng(seed + 7)
+    where = np.concatenate([[0], rng.choice(np.arange(1, n), 31, replace=False)])
+    xyz[where] = rng.uniform(-0.015, 0.015, (32, 3)).astype(np.float32)
+    return xyz
+
+
+# --------------------------------------------------------------------------------------------------------------- FPS
+@pytest.mark.parametrize("variant", ["A", "B"])
+@pytest.mark.parametrize("B,N,m,kind", [(2, 20000, 256, "tabletop"), (3, 2048, 512, "tabletop"), (2, 777, 300, "uniform"),
+                                        (1, 5, 9, "uniform"), (2, 1, 3, "uniform"), (1, 1500, 1500, "tabletop"),
+                                        (2, 4099, 64, "uniform")])
+def test_fps_vs_oracle(dev, variant, B, N, m, kind):
+    xyz = scenes.scene_batch(range(B), N, kind)
+    want = oracle.furthest_point_sample(xyz, m, variant)
+    x = T(xyz, dev)
+    got = pu.furthest_point_sample(x, m) if variant == "A" else gb_sub.furthest_point_sample(x, m)
+    assert got.dtype == torch.int32 and tuple(got.shape) == (B, m)
+    np.testing.assert_array_equal(got.cpu().numpy(), want)
+
+
+def test_fps_norm_skip_and_ties(dev):
+    xyz = np.stack([scene_with_origin_points(s, 6000) for s in range(2)])
+    xyz[1, 3000:] = xyz[1, :3000]  # half the cloud duplicated: every distance ties
+    x = T(xyz, dev)
+    for variant, fn in (("A", pu.furthest_point_sample), ("B", gb_sub.furthest_point_sample)):
+        np.testing.assert_array_equal(fn(x, 700).cpu().numpy(), oracle.furthest_point_sample(xyz, 700, variant))
+    # everything skipped: variant A returns index 0 throughout
+    tiny = (np.random.default_rng(0).uniform(-0.01, 0.01, (1, 300, 3))).astype(np.float32)
+    np.testing.assert_array_equal(pu.furthest_point_sample(T(tiny, dev), 20).cpu().numpy(), 0)
+
+
+@pytest.mark.parametrize("cluster", [1, 2, 4, 8, 16])
+@pytest.mark.parametrize("threads", [512, 1024])
+def test_fps_every_decomposition_gives_the_same_picks(dev, cluster, threads):
+    xyz = scenes.scene_batch([5, 6], 20000, "tabletop")
+    want = oracle.furthest_point_sample(xyz, 300, "A")
+    _lib.set_tuning("fps_cluster", cluster)
+    _lib.set_tuning("fps_threads", threads)
+    try:
+        got = pu.furthest_point_sample(T(xyz, dev), 300).cpu().numpy()
+        gotb = gb_sub.furthest_point_sample(T(xyz, dev), 300).cpu().numpy()
+    finally:
+        _lib.set_tuning("fps_cluster", 0)
+        _lib.set_tuning("fps_threads", 0)
+    np.testing.assert_array_equal(got, want)
+    np.testing.assert_array_equal(gotb, oracle.furthest_point_sample(xyz, 300, "B"))
+
+
+def test_fps_full_size_vs_reference(dev, ref_a, ref_b):
+    xyz = T(scenes.scene_batch(range(4), 20000, "tabletop"), dev)
+    got = pu.furthest_point_sample(xyz, 1024)
+    want = ref_a.furthest_point_sampling(xyz, 1024)
+    assert torch.equal(got, want)
+    got2048 = pu.furthest_point_sample(xyz, 2048)
+    assert torch.equal(got2048, ref_a.furthest_point_sampling(xyz, 2048))
+    temp = torch.full((4, 20000), 1e10, device=dev)
+    out = torch.empty((4, 1024), dtype=torch.int32, device=dev)
+    ref_b.furthest_point_sampling_wrapper(4, 20000, 1024, xyz, temp, out)
+    temp2 = torch.full((4, 20000), 1e10, device=dev)
+    out2 = torch.empty((4, 1024), dtype=torch.int32, device=dev)
+    gb_b.furthest_point_sampling_wrapper(4, 20000, 1024, xyz, temp2, out2)
+    assert torch.equal(out2, out)
+    assert torch.equal(temp2, temp)  # the running distances left in `temp` match too
+    # FPS chain of the backbone: 2048 -> 1024 -> 512 -> 256 on the sampled clouds
+    cur = pu.gather_operation(xyz.transpose(1, 2).contiguous(), got2048).transpose(1, 2).contiguous()
+    for m in (1024, 512, 256):
+        a, b = pu.furthest_point_sample(cur, m), ref_a.furthest_point_sampling(cur, m)
+        assert torch.equal(a, b)
+        cur = pu.gather_operation(cur.transpose(1, 2).contiguous(), a).transpose(1, 2).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------- ball / cylinder
+def _queries(xyz, m, seed):
+    rng = np.random.default_rng(seed)
+    B, N, _ = xyz.shape
+    pick = np.stack([rng.choice(N, m, replace=m > N) for _ in range(B)])
+    return np.take_along_axis(xyz, pick[..., None], axis=1)
+
+
+@pytest.mark.parametrize("B,N,m,r,ns,kind", [(2, 20000, 256, 0.05, 64, "tabletop"), (2, 2048, 300, 0.08, 64, "tabletop"),
+                                             (1, 1001, 77, 0.2, 16, "uniform"), (2, 37, 5, 0.5, 7, "uniform"),
+                                             (1, 5000, 128, 1e-4, 32, "uniform"), (1, 4032, 64, 10.0, 100, "uniform"),
+                                             (3, 20000, 96, 0.02, 1, "tabletop")])
+def test_ball_query_vs_oracle(dev, B, N, m, r, ns, kind):
+    xyz = scenes.scene_batch(range(B), N, kind)
+    new_xyz = _queries(xyz, m, 3)
+    want = oracle.ball_query(r, ns, xyz, new_xyz)
+    got = pu.ball_query(r, ns, T(xyz, dev), T(new_xyz, dev))
+    assert got.dtype == torch.int32
+    np.testing.assert_array_equal(got.cpu().numpy(), want)
+    got_b = gb_group.ball_query(r, ns, T(xyz, dev), T(new_xyz, dev))
+    np.testing.assert_array_equal(got_b.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("qpw", [1, 2, 4])
+def test_ball_query_queries_per_warp(dev, qpw):
+    xyz = scenes.scene_batch(range(2), 6000, "tabletop")
+    new_xyz = _queries(xyz, 203, 9)
+    want = oracle.ball_query(0.06, 48, xyz, new_xyz)
+    _lib.set_tuning("query_qpw", qpw)
+    try:
+        got = pu.ball_query(0.06, 48, T(xyz, dev), T(new_xyz, dev)).cpu().numpy()
+    finally:
+        _lib.set_tuning("query_qpw", 0)
+    np.testing.assert_array_equal(got, want)
+
+
+def _cyl_inputs(B, N, m, seed, kind="tabletop"):
+    xyz = scenes.scene_batch(range(seed, seed + B), N, kind)
+    new_xyz = _queries(xyz, m, seed)
+    rng = np.random.default_rng(seed)
+    v = rng.normal(size=(B, m, 3)).astype(np.float32)
+    rot = scenes.viewpoint_rotations(-v, rng.uniform(0, np.pi, (B, m)).astype(np.float32))
+    return xyz, new_xyz, np.ascontiguousarray(rot.reshape(B, m, 9))
+
+
+@pytest.mark.parametrize("B,N,m,ns,hmax", [(2, 20000, 128, 64, 0.04), (1, 3001, 50, 16, 0.01), (2, 2048, 64, 32, 0.02)])
+def test_cylinder_query_vs_oracle(dev, B, N, m, ns, hmax):
+    xyz, new_xyz, rot = _cyl_inputs(B, N, m, 21)
+    want = oracle.cylinder_query(0.05, -0.02, hmax, ns, xyz, new_xyz, rot)
+    got = pu.cylinder_query(0.05, -0.02, hmax, ns, T(xyz, dev), T(new_xyz, dev), T(rot, dev))
+    np.testing.assert_array_equal(got.cpu().numpy(), want)
+
+
+def test_queries_full_size_vs_reference(dev, ref_a, ref_b):
+    xyz = T(scenes.scene_batch(range(4), 20000, "tabletop"), dev)
+    fidx = pu.furthest_point_sample(xyz, 1024)
+    new_xyz = pu.gather_operation(xyz.transpose(1, 2).contiguous(), fidx).transpose(1, 2).contiguous()
+    for r, ns in ((0.05, 64), (0.04, 64), (0.1, 32), (0.3, 16)):
+        want = ref_a.ball_query(new_xyz, xyz, r, ns)
+        assert torch.equal(pu.ball_query(r, ns, xyz, new_xyz), want)
+        idx_b = torch.zeros((4, 1024, ns), dtype=torch.int32, device=dev)
+        ref_b.ball_query_wrapper(4, 20000, 1024, r, ns, new_xyz, xyz, idx_b)
+        assert torch.equal(gb_group.ball_query(r, ns, xyz, new_xyz), idx_b)
+    uni = T(scenes.scene_batch(range(2), 20000, "uniform"), dev)
+    q = uni[:, :1024].contiguous()
+    assert torch.equal(pu.ball_query(0.05, 64, uni, q), ref_a.ball_query(q, uni, 0.05, 64))
+    # cylinder: 12 in-plane angles x 4 depths (BASELINE config 4), one scene pair
+    rng = np.random.default_rng(0)
+    v = rng.normal(size=(4, 1024, 3)).astype(np.float32)
+    for a in range(0, 12, 5):
+        rot = T(scenes.viewpoint_rotations(-v, np.full((4, 1024), a * np.pi / 12, np.float32)).reshape(4, 1024, 9), dev)
+        for hmax in (0.01, 0.02, 0.03, 0.04):
+            want = ref_a.cylinder_query(new_xyz, xyz, rot, 0.05, -0.02, hmax, 64)
+            assert torch.equal(pu.cylinder_query(0.05, -0.02, hmax, 64, xyz, new_xyz, rot), want)
+
+
+# ------------------------------------------------------------------------------------------------- group / gather
+@pytest.mark.parametrize("B,C,N,m,ns", [(2, 3, 20000, 256, 64), (2, 128, 20000, 64, 64), (1, 131, 2048, 128, 32),
+                                        (2, 5, 100, 7, 3), (1, 259, 1024, 512, 16), (1, 1, 50, 4, 4), (2, 16, 60000, 16, 8)])
+def test_group_forward_backward_vs_oracle(dev, B, C, N, m, ns):
+    rng = np.random.default_rng(B * 1000 + C)
+    feats = rng.normal(size=(B, C, N)).astype(np.float32)
+    idx = rng.integers(0, N, (B, m, ns)).astype(np.int32)
+    idx[:, :, ns // 2:] = idx[:, :, :1]  # padded tails, like a ball query with few hits
+    gout = rng.normal(size=(B, C, m, ns)).astype(np.float32)
+    for mod in (pu, gb_group):
+        f = T(feats, dev).requires_grad_(True)
+        out = mod.grouping_operation(f, T(idx, dev))
+        np.testing.assert_array_equal(out.detach().cpu().numpy(), oracle.grouping_operation(feats, idx))
+        out.backward(T(gout, dev))
+        assert_grad_close(f.grad.cpu().numpy(), oracle.grouping_operation_grad(gout, idx, N))
+    assert torch.equal(gb_group.torch_grouping_operation(T(feats, dev), T(idx, dev)), out.detach())
+
+
+def test_gather_forward_backward_vs_oracle(dev):
+    rng = np.random.default_rng(5)
+    feats = rng.normal(size=(3, 7, 5000)).astype(np.float32)
+    idx = rng.integers(0, 5000, (3, 333)).astype(np.int32)
+    gout = rng.normal(size=(3, 7, 333)).astype(np.float32)
+    for mod in (pu, gb_group, gb_sub):
+        f = T(feats, dev).requires_grad_(True)
+        out = mod.gather_operation(f, T(idx, dev))
+        np.testing.assert_array_equal(out.detach().cpu().numpy(), oracle.gather_operation(feats, idx))
+        out.backward(T(gout, dev))
+        assert_grad_close(f.grad.cpu().numpy(), oracle.gather_operation_grad(gout, idx, 5000))
+    # the one relation the reference itself asserts (subsample.py:145-157)
+    ref = torch.gather(T(feats, dev), 2, T(idx, dev).long().unsqueeze(1).expand(-1, 7, -1))
+    assert torch.equal(out.detach(), ref)
+
+
+def test_group_full_size_vs_reference(dev, ref_a, ref_b):
+    B, N, m, ns = 4, 20000, 1024, 64
+    xyz = T(scenes.scene_batch(range(B), N, "tabletop"), dev)
+    fidx = pu.furthest_point_sample(xyz, m)
+    new_xyz = pu.gather_operation(xyz.transpose(1, 2).contiguous(), fidx).transpose(1, 2).contiguous()
+    idx = pu.ball_query(0.05, ns, xyz, new_xyz)
+    g = torch.Generator(device="cpu").manual_seed(1)
+    feats = torch.randn((B, 128, N), generator=g).to(dev)
+    xyz_t = xyz.transpose(1, 2).contiguous()
+    for f in (xyz_t, feats):
+        want = ref_a.group_points(f, idx)
+        assert torch.equal(gb_a.group_points(f, idx), want)
+        out_b = torch.empty_like(want)
+        ref_b.group_points_wrapper(B, f.shape[1], N, m, ns, f, idx, out_b)
+        assert torch.equal(out_b, want)
+        gout = torch.randn(want.shape, generator=g).to(dev)
+        want_g = ref_a.group_points_grad(gout, idx, N)
+        got_g = gb_a.group_points_grad(gout, idx, N)
+        assert_grad_close(got_g.cpu().numpy(), want_g.cpu().numpy())
+
+
+# ------------------------------------------------------------------------------------------- three_nn / interpolate
+@pytest.mark.parametrize("B,n,m", [(2, 20000, 1024), (1, 513, 2), (2, 1000, 3), (1, 64, 1), (2, 4000, 2500)])
+def test_three_nn_vs_oracle(dev, B, n, m):
+    unknown = scenes.scene_batch(range(B), n, "tabletop" if n >= 1000 else "uniform")
+    known = _queries(unknown, m, 4)
+    want_d2, want_i = oracle.three_nn_dist2(unknown, known)
+    d2, idx = gb_a.three_nn(T(unknown, dev), T(known, dev))
+    np.testing.assert_array_equal(idx.cpu().numpy(), want_i)
+    np.testing.assert_array_equal(d2.cpu().numpy(), want_d2)
+    for mod in (pu, gb_up):
+        dist, idx2 = mod.three_nn(T(unknown, dev), T(known, dev))
+        np.testing.assert_array_equal(idx2.cpu().numpy(), want_i)
+        np.testing.assert_array_equal(dist.cpu().numpy(), np.sqrt(want_d2))
+
+
+@pytest.mark.parametrize("B,C,m,n", [(2, 256, 1024, 20000), (1, 7, 50, 333), (2, 64, 256, 512), (1, 130, 512, 1024)])
+def test_three_interpolate_vs_oracle(dev, B, C, m, n):
+    rng = np.random.default_rng(C)
+    feats = rng.normal(size=(B, C, m)).astype(np.float32)
+    idx = rng.integers(0, m, (B, n, 3)).astype(np.int32)
+    w = rng.uniform(0, 1, (B, n, 3)).astype(np.float32)
+    w /= w.sum(-1, keepdims=True)
+    gout = rng.normal(size=(B, C, n)).astype(np.float32)
+    for mod in (pu, gb_up):
+        f = T(feats, dev).requires_grad_(True)
+        out = mod.three_interpolate(f, T(idx, dev), T(w, dev))
+        np.testing.assert_array_equal(out.detach().cpu().numpy(), oracle.three_interpolate(feats, idx, w))
+        out.backward(T(gout, dev))
+        assert_grad_close(f.grad.cpu().numpy(), oracle.three_interpolate_grad(gout, idx, w, m))
+
+
+def test_fp_chain_full_size_vs_reference(dev, ref_a, ref_b):
+    B, n, m, C = 4, 20000, 1024, 256
+    xyz = T(scenes.scene_batch(range(B), n, "tabletop"), dev)
+    fidx = pu.furthest_point_sample(xyz, m)
+    known = pu.gather_operation(xyz.transpose(1, 2).contiguous(), fidx).transpose(1, 2).contiguous()
+    d2, idx = gb_a.three_nn(xyz, known)
+    rd2, ridx = ref_a.three_nn(xyz, known)
+    assert torch.equal(idx, ridx) and torch.equal(d2, rd2)
+    dist = torch.sqrt(d2)
+    recip = 1.0 / (dist + 1e-8)
+    w = (recip / recip.sum(dim=2, keepdim=True)).contiguous()
+    g = torch.Generator(device="cpu").manual_seed(2)
+    feats = torch.randn((B, C, m), generator=g).to(dev)
+    want = ref_a.three_interpolate(feats, idx, w)
+    assert torch.equal(gb_a.three_interpolate(feats, idx, w), want)
+    out_b = torch.empty_like(want)
+    ref_b.three_interpolate_wrapper(B, C, m, n, feats, idx, w, out_b)
+    assert torch.equal(out_b, want)
+    gout = torch.randn(want.shape, generator=g).to(dev)
+    assert_grad_close(gb_a.three_interpolate_grad(gout, idx, w, m).cpu().numpy(),
+                      ref_a.three_interpolate_grad(gout, idx, w, m).cpu().numpy())
+
+
+# ---------------------------------------------------------------------------------------------------------------- KNN
+@pytest.mark.parametrize("B,D,R,Q,k", [(2, 3, 300, 300, 1), (1, 3, 5000, 200, 1), (2, 3, 2000, 100, 64), (1, 5, 700, 33, 8),
+                                       (1, 3, 64, 10, 64), (1, 20, 1000, 17, 3), (1, 3, 20000, 64, 64)])
+def test_knn_vs_oracle(dev, B, D, R, Q, k):
+    rng = np.random.default_rng(R + k)
+    ref = rng.uniform(-1, 1, (B, D, R)).astype(np.float32)
+    ref[:, :, R // 2:R // 2 + 20] = ref[:, :, :20]  # exact duplicates: (distance, index) tie order
+    query = rng.uniform(-1, 1, (B, D, Q)).astype(np.float32)
+    want = oracle.knn(ref, query, k)
+    got = gb_knn.knn_k(T(ref, dev), T(query, dev), k)
+    assert got.dtype == torch.int64 and tuple(got.shape) == (B, k, Q)
+    np.testing.assert_array_equal(got.cpu().numpy(), want)
+    if k == 1:
+        np.testing.assert_array_equal(gb_knn.myknn(T(ref, dev), T(query, dev)).cpu().numpy(), want)
+
+
+def test_knn_full_size_vs_reference(dev, ref_c):
+    xyz = T(scenes.scene_batch(range(2), 20000, "tabletop"), dev)
+    ref = xyz.transpose(1, 2).contiguous()
+    query = ref[:, :, ::19][:, :, :1024].contiguous() + 0.001
+    for k in (1, 64):
+        want = torch.empty((2, k, 1024), dtype=torch.int64, device=dev)
+        ref_c.knn(ref, query, want)
+        assert torch.equal(gb_knn.knn_k(ref, query, k), want)
+
+
+# ---------------------------------------------------------------------------------------------------------- collision
+def test_collision_vs_golden_and_oracle(dev):
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "collision_ref.npz"))
+    for tag in "ab":
+        pts, voxel = z[tag + "_points"], float(z[tag + "_voxel"])
+        det = ModelFreeCollisionDetector.__new__(ModelFreeCollisionDetector)
+        det.finger_width, det.finger_length, det.voxel_size = 0.01, 0.06, voxel
+        det.scene_points, det.device = pts, dev
+        det._scene_dev = T(pts, dev)
+        gg = scenes.GraspGroupStandIn(z[tag + "_translations"], z[tag + "_rotation_matrices"], z[tag + "_heights"],
+                                      z[tag + "_depths"], z[tag + "_widths"])
+        plain = det.detect(gg, approach_dist=0.05, collision_thresh=0.01)
+        full = det.detect(gg, approach_dist=0.05, collision_thresh=0.01, return_empty_grasp=True, return_ious=True)
+        assert plain.dtype == np.bool_ and (plain == z[tag + "_collision"]).all()
+        assert (full[0] == z[tag + "_collision"]).all() and (full[1] == z[tag + "_empty"]).all()
+        for a, b in zip(full[2], z[tag + "_ious"]):
+            np.testing.assert_array_equal(a, b)
+
+
+def test_collision_full_size_vs_oracle(dev):
+    raw = scenes.tabletop_scene(3, 20000).astype(np.float64)
+    det = ModelFreeCollisionDetector(raw, voxel_size=0.01, device=dev)
+    gs = scenes.grasp_set(4, det.scene_points, 1024)
+    gg = scenes.GraspGroupStandIn(**gs)
+    got = det.detect(gg, approach_dist=0.05, collision_thresh=0.01, return_empty_grasp=True, return_ious=True)
+    want = oracle.collision_detect(det.scene_points, 0.01, gs["translations"], gs["rotation_matrices"], gs["heights"],
+                                   gs["depths"], gs["widths"], approach_dist=0.05, collision_thresh=0.01,
+                                   return_empty_grasp=True, return_ious=True)
+    assert (got[0] == want[0]).all() and (got[1] == want[1]).all()
+    for a, b in zip(got[2], want[2]):
+        np.testing.assert_array_equal(a, b)
+    assert 0 < got[0].sum() < 1024
