@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""bench.py -- point-op pipeline scenes/sec @20k pts (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py --gpus 1 --steps K --warmup W                      # this framework (libgbops, sm_100a)
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...                                # the reference's CPU path (oracle port) on host cores
+
+A "step" is one forward+backward pass of the GraspBalance operator pipeline (graspbalance_b200/pipeline.py: SA1-4 with
+FPS/gather/ball query/group, 15 InvResMLP groupings, FP1/FP2 and the 20k-point up-sampling, the 16 cylinder-query grasp
+crops, the 1024-grasp collision test) over `--batch` synthetic 20k-point scenes per GPU (default 32 = BASELINE config 5).
+Scenes shard by batch across ranks with no collective on the op path ("scaling": "weak": per-GPU work is fixed); each
+step ends with one NCCL all_gather of the small per-scene outputs.
+
+One JSON line is printed by rank 0; see DESIGN.md "Measurement" for how every field is produced.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "point-op pipeline scenes/sec @20k pts"
+UNIT = "scenes/s"
+N_POINTS = 20000
+
+
+def read_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ts, line in self.rows:
+            if ts < t0 or ts > t1 + 0.1:
+                continue
+            p = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples inside the timed region"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# synthetic inputs (host side, pinned)
+# ------------------------------------------------------------------------------------------------------------------
+def make_host_inputs(scene_ids, pin=True):
+    import torch
+    from graspbalance_b200 import pipeline, scenes
+    from graspbalance_b200.collision_detector import voxel_down_sample
+    B = len(scene_ids)
+    xyz = scenes.scene_batch(scene_ids, N_POINTS, "tabletop")
+    rot = pipeline.make_view_rotations(B, seed=int(scene_ids[0])).astype(np.float32)
+    pts, Ts, Rs, thrs = [], [], [], []
+    fw, fl, ad = 0.01, 0.06, 0.03
+    for b, sid in enumerate(scene_ids):
+        p = voxel_down_sample(xyz[b].astype(np.float64), 0.01)  # what ModelFreeCollisionDetector.__init__ does (host)
+        g = scenes.grasp_set(int(sid) + 1000, p, pipeline.NUM_GRASP)
+        h, d, w = g["heights"][:, None], g["depths"][:, None], g["widths"][:, None]
+        thr = np.concatenate([-h / 2, h / 2, d - fl, d, -(w / 2 + fw), -w / 2, (w / 2 + fw), w / 2, d - fl - fw, d - fl - fw - ad], axis=1)
+        pts.append(p); Ts.append(g["translations"]); Rs.append(g["rotation_matrices"]); thrs.append(thr)
+    offs = np.cumsum([0] + [p.shape[0] for p in pts])
+    host = {
+        "xyz": torch.from_numpy(xyz),
+        "rot": torch.from_numpy(np.ascontiguousarray(rot)),
+        "scene_points": torch.from_numpy(np.ascontiguousarray(np.concatenate(pts, axis=0))),
+        "T": torch.from_numpy(np.ascontiguousarray(np.stack(Ts))),
+        "R": torch.from_numpy(np.ascontiguousarray(np.stack(Rs))),
+        "thr": torch.from_numpy(np.ascontiguousarray(np.stack(thrs))),
+    }
+    if pin:
+        host = {k: v.pin_memory() for k, v in host.items()}
+    return host, offs
+
+
+def to_device(host, offs, dev):
+    d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+    grasps = {"scene_points": [d["scene_points"][offs[b]:offs[b + 1]] for b in range(len(offs) - 1)],
+              "T": d["T"], "R": d["R"], "thr": d["thr"]}
+    return d["xyz"], d["rot"], grasps
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# the reference's CPU path: oracle port of the same chain, one scene (used by cpu_baseline and --impl reference)
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_pipeline_scene(scene_id, backward=True):
+    """One scene through the same op chain on the host cores: oracle/gb_oracle.c (pthreads over independent
+    scenes/queries, i.e. every host thread) for the CUDA ops' arithmetic and the whole-array numpy restatement of
+    collision_detector.detect for the collision test.  Returns seconds."""
+    import oracle
+    from graspbalance_b200 import pipeline, scenes
+    rng = np.random.default_rng(scene_id)
+    xyz = scenes.scene_batch([scene_id], N_POINTS, "tabletop")
+    rot = pipeline.make_view_rotations(1, seed=scene_id).reshape(1, pipeline.NUM_SEED, 9)
+    pts = oracle.voxel_down_sample(xyz[0].astype(np.float64), 0.01)
+    g = scenes.grasp_set(scene_id + 1000, pts, pipeline.NUM_GRASP)
+    feats = {}
+    for lvl, (m, _, ns, c_in) in enumerate(pipeline.SA_SPECS):
+        n_in = N_POINTS if lvl == 0 else pipeline.SA_SPECS[lvl - 1][0]
+        if c_in:
+            feats[("sa", lvl)] = (rng.normal(size=(1, c_in, n_in)).astype(np.float32), rng.normal(size=(1, c_in, m, ns)).astype(np.float32))
+        blocks, c, _, nsb = pipeline.IRM_SPECS[lvl]
+        feats[("irm", lvl)] = (rng.normal(size=(1, c, m)).astype(np.float32), rng.normal(size=(1, c, m, nsb)).astype(np.float32))
+    fp = [(rng.normal(size=(1, 256, mm)).astype(np.float32), rng.normal(size=(1, 256, nn)).astype(np.float32))
+          for (nn, mm) in ((512, 256), (1024, 512), (N_POINTS, 1024))]
+
+    t0 = time.perf_counter()
+    cur, levels = xyz, []
+    for lvl, (m, radius, ns, c_in) in enumerate(pipeline.SA_SPECS):
+        inds = oracle.furthest_point_sample(cur, m, "A")
+        cur_t = np.ascontiguousarray(cur.transpose(0, 2, 1))
+        new_xyz = np.ascontiguousarray(oracle.gather_operation(cur_t, inds).transpose(0, 2, 1))
+        idx = oracle.ball_query(radius, ns, cur, new_xyz)
+        gx = oracle.grouping_operation(cur_t, idx)
+        gx -= new_xyz.transpose(0, 2, 1)[..., None]
+        gx /= radius
+        if c_in:
+            f, go = feats[("sa", lvl)]
+            oracle.grouping_operation(f, idx)
+            if backward:
+                oracle.grouping_operation_grad(go, idx, f.shape[2])
+        blocks, c, r2, nsb = pipeline.IRM_SPECS[lvl]
+        f, go = feats[("irm", lvl)]
+        new_t = np.ascontiguousarray(new_xyz.transpose(0, 2, 1))
+        for _ in range(blocks):
+            idx = oracle.ball_query(r2, nsb, new_xyz, new_xyz)
+            dp = oracle.grouping_operation(new_t, idx)
+            dp = dp - new_xyz.transpose(0, 2, 1)[..., None]
+            oracle.grouping_operation(f, idx)
+            if backward:
+                oracle.grouping_operation_grad(go, idx, m)
+        cur = new_xyz
+        levels.append(new_xyz)
+    for (unk, kn), (f, go) in zip(((levels[2], levels[3]), (levels[1], levels[2]), (xyz, levels[1])), fp):
+        dist, idx = oracle.three_nn(unk, kn)
+        recip = 1.0 / (dist + 1e-8)
+        w = (recip / recip.sum(axis=2, keepdims=True)).astype(np.float32)
+        oracle.three_interpolate(f, idx, w)
+        if backward:
+            oracle.three_interpolate_grad(go, idx, w, f.shape[2])
+    seed = levels[1]
+    xyz_t = np.ascontiguousarray(xyz.transpose(0, 2, 1))
+    rot33 = rot.reshape(1, pipeline.NUM_SEED, 3, 3)
+    for r in pipeline.CROP_RADII:
+        for hmax in pipeline.CROP_HMAX:
+            idx = oracle.cylinder_query(r, pipeline.CROP_HMIN, hmax, 64, xyz, seed, rot)
+            gx = oracle.grouping_operation(xyz_t, idx)
+            gx -= seed.transpose(0, 2, 1)[..., None]
+            np.matmul(gx.transpose(0, 2, 3, 1), rot33)
+    oracle.collision_detect_numpy(pts, 0.01, g["translations"], g["rotation_matrices"], g["heights"], g["depths"], g["widths"])
+    return time.perf_counter() - t0
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    import oracle
+    oracle.build()
+    cores = oracle.num_threads()
+    for w in range(args.warmup):
+        cpu_pipeline_scene(10_000 + w)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        cpu_pipeline_scene(20_000 + k)
+    dt = time.perf_counter() - t0
+    value = args.steps / dt
+    sample = "1 scene per step (the full op chain fwd+bwd of one 20k-point scene) out of the 32-scene batch"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args), "scenes_per_step": 1, "n_points": N_POINTS},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(args):
+    return (f"BASELINE config 5: full GraspBalance backbone op pipeline forward{'+backward' if not args.no_backward else ''} "
+            f"(SA1-4 + 15 InvResMLP + FP1/2 + 20k up-sampling + 16 cylinder crops + 1024-grasp collision), "
+            f"{args.batch} synthetic 20k-point scenes per GPU")
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="gbops", choices=["gbops", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="scenes per GPU per step")
+    ap.add_argument("--no-backward", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "gbops" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from graspbalance_b200 import _lib, pipeline, sharding
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: graspbalance_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    _lib.lib()  # fail loudly now if libgbops.so is missing
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B = args.batch
+    scene_ids = sharding.scene_ids_for_rank(rank, world, B)
+    host, offs = make_host_inputs(scene_ids)
+    pipe = pipeline.OpPipeline(B, N_POINTS, dev, seed=rank, backward=not args.no_backward)
+    gather_buf = torch.empty((world * B, pipeline.NUM_SEED + 6 * pipeline.NUM_GRASP), dtype=torch.int64, device=dev) if world > 1 else None
+
+    def step(resident, inputs=None):
+        """One pipeline pass.  resident=True: inputs already on the device.  resident=False: the e2e path -- pinned host
+        buffers are copied in, the per-scene results are copied back to the host."""
+        if resident:
+            xyz, rot, grasps = inputs
+        else:
+            xyz, rot, grasps = to_device(host, offs, dev)
+        out = pipe.run(xyz, rot, grasps)
+        result = torch.cat([out["seed_inds"].to(torch.int64), out["collision_counts"].reshape(B, -1)], dim=1)
+        if world > 1:
+            sharding.gather_scene_outputs(result, world, gather_buf)  # NCCL: gather per-scene outputs only
+        if not resident:
+            res_h = result.to("cpu", non_blocking=True)
+            chk_h = torch.stack([out["up_checksum"], out["crop_checksum"]] + ([out["grad_checksum"]] if "grad_checksum" in out else [])).to("cpu", non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return res_h, chk_h
+        return result
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n_steps, resident, inputs=None):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_wall0 = time.time()
+        e0.record()
+        for _ in range(n_steps):
+            step(resident, inputs)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, t_wall0, time.time()
+
+    resident_inputs = to_device(host, offs, dev)
+    torch.cuda.synchronize()
+    for _ in range(args.warmup):
+        step(True, resident_inputs)
+
+    # ---- device-resident throughput ("value"), with per-launch events for the roofline ----
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    _lib.PROFILER = {}
+    launches0 = _lib.launch_count()
+    ms, tw0, tw1 = timed(args.steps, True, resident_inputs)
+    launches = _lib.launch_count() - launches0
+    prof, _lib.PROFILER = _lib.PROFILER, None
+    clocks = sampler.stop(tw0, tw1) if rank == 0 else None
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # ---- e2e: host buffers in, results out, every step ----
+    e2e = None
+    if not args.no_e2e:
+        for _ in range(2):
+            step(False)
+        ms_e2e, _, _ = timed(args.steps, False)
+        h2d = sum(v.numel() * v.element_size() for v in host.values())
+        d2h = B * (pipeline.NUM_SEED + 6 * pipeline.NUM_GRASP) * 8 + 3 * 4
+        e2e = {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / args.steps}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel family (largest share of the summed launch time) ----
+    peak, peak_src = read_peaks()
+    fam = {}
+    for name, evs in prof.items():
+        tot_ms = sum(a.elapsed_time(b) for a, b, _ in evs)
+        fam[name] = {"launches": len(evs), "ms": tot_ms, "bytes": sum(x for _, _, x in evs)}
+    total_ms = sum(f["ms"] for f in fam.values()) or 1.0
+    per_op = []
+    for name, f in sorted(fam.items(), key=lambda kv: -kv[1]["ms"]):
+        gbs = f["bytes"] / (f["ms"] * 1e-3) / 1e9 if f["ms"] > 0 else 0.0
+        per_op.append({"kernel": name, "launches_per_step": f["launches"] / args.steps, "ms_per_step": f["ms"] / args.steps,
+                       "share": f["ms"] / total_ms, "achieved_gbs": gbs, "hbm_frac": gbs / peak})
+    top = per_op[0]
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "dram_traffic.json")) as f:
+            traffic = json.load(f).get(top["kernel"])
+    except Exception:
+        pass
+    roofline = {"kernel": top["kernel"], "bound": "hbm", "achieved": top["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                "frac": top["achieved_gbs"] / peak, "traffic": traffic, "peak_source": peak_src,
+                "avg_launch_us": top["ms_per_step"] / max(top["launches_per_step"], 1e-9) * 1e3, "share_of_step": top["share"]}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        import oracle
+        oracle.build()
+        cpu_pipeline_scene(9_999)  # warm the page cache / thread pool
+        n_cpu = 2
+        t_cpu = sum(cpu_pipeline_scene(30_000 + i) for i in range(n_cpu))
+        cpu = {"value": n_cpu / t_cpu, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port",
+               "sample": f"{n_cpu} scenes (full op chain fwd+bwd each) of the {B}-scene batch, oracle/gb_oracle.c + numpy detect"}
+
+    algo = pipeline.algorithmic_bytes_per_scene(N_POINTS, not args.no_backward)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args), "scenes_per_gpu": B, "n_points": N_POINTS, "parallelism": f"scene-sharded x{world}",
+                       "l2": "per-step working set (>10 GB of grouped features) exceeds the 126 MB L2; no explicit flush",
+                       "algorithmic_bytes_per_scene": int(sum(algo.values()))},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "pipeline_hbm_frac": (sum(algo.values()) * world * B * args.steps / (ms * 1e-3) / 1e9) / (peak * world),
+            "per_op": per_op}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

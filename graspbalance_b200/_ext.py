@@ -10,28 +10,6 @@ import torch
 from . import _lib
 
 
-def _stream(t):
-    return torch.cuda.current_stream(t.device).cuda_stream
-
-
-class _on:
-    """Make the tensor's device current for the launch (the reference relies on the caller's current device)."""
-
-    def __init__(self, t):
-        self.dev = t.device.index
-        self.prev = None
-
-    def __enter__(self):
-        cur = torch.cuda.current_device()
-        if self.dev is not None and self.dev != cur:
-            self.prev = cur
-            torch.cuda.set_device(self.dev)
-
-    def __exit__(self, *a):
-        if self.prev is not None:
-            torch.cuda.set_device(self.prev)
-
-
 def _contig(x, name):
     if not x.is_contiguous():
         raise RuntimeError(f"{name} must be a contiguous tensor")
@@ -66,9 +44,7 @@ def gather_points(points, idx):
     B, C, N = points.shape
     M = idx.shape[1]
     out = torch.empty((B, C, M), dtype=torch.float32, device=points.device)
-    with _on(points):
-        _lib.check(_lib.lib().gb_gather_fwd(points.data_ptr(), idx.data_ptr(), out.data_ptr(), B, C, N, M, _stream(points)),
-                   "gather_points")
+    _lib.call("gb_gather_fwd", points, points.data_ptr(), idx.data_ptr(), out.data_ptr(), B, C, N, M)
     return out
 
 
@@ -80,9 +56,7 @@ def gather_points_grad(grad_out, idx, n):
     _need_cuda(grad_out)
     B, C, M = grad_out.shape
     out = torch.zeros((B, C, n), dtype=torch.float32, device=grad_out.device)
-    with _on(grad_out):
-        _lib.check(_lib.lib().gb_gather_bwd(grad_out.data_ptr(), idx.data_ptr(), out.data_ptr(), B, C, int(n), M,
-                                            _stream(grad_out)), "gather_points_grad")
+    _lib.call("gb_gather_bwd", grad_out, grad_out.data_ptr(), idx.data_ptr(), out.data_ptr(), B, C, int(n), M)
     return out
 
 
@@ -92,9 +66,7 @@ def furthest_point_sampling(points, nsamples):
     _need_cuda(points)
     B, N = points.shape[0], points.shape[1]
     out = torch.zeros((B, int(nsamples)), dtype=torch.int32, device=points.device)
-    with _on(points):
-        _lib.check(_lib.lib().gb_fps(points.data_ptr(), None, out.data_ptr(), B, N, int(nsamples), 0, _stream(points)),
-                   "furthest_point_sampling")
+    _lib.call("gb_fps", points, points.data_ptr(), None, out.data_ptr(), B, N, int(nsamples), 0)
     return out
 
 
@@ -108,9 +80,7 @@ def three_nn(unknowns, knows):
     m = knows.shape[1]
     idx = torch.empty((B, n, 3), dtype=torch.int32, device=unknowns.device)
     dist2 = torch.empty((B, n, 3), dtype=torch.float32, device=unknowns.device)
-    with _on(unknowns):
-        _lib.check(_lib.lib().gb_three_nn(unknowns.data_ptr(), knows.data_ptr(), dist2.data_ptr(), idx.data_ptr(), B, n, m,
-                                          _stream(unknowns)), "three_nn")
+    _lib.call("gb_three_nn", unknowns, unknowns.data_ptr(), knows.data_ptr(), dist2.data_ptr(), idx.data_ptr(), B, n, m)
     return [dist2, idx]
 
 
@@ -124,9 +94,7 @@ def three_interpolate(points, idx, weight):
     B, C, m = points.shape
     n = idx.shape[1]
     out = torch.empty((B, C, n), dtype=torch.float32, device=points.device)
-    with _on(points):
-        _lib.check(_lib.lib().gb_three_interp_fwd(points.data_ptr(), idx.data_ptr(), weight.data_ptr(), out.data_ptr(), B, C, m,
-                                                  n, _stream(points)), "three_interpolate")
+    _lib.call("gb_three_interp_fwd", points, points.data_ptr(), idx.data_ptr(), weight.data_ptr(), out.data_ptr(), B, C, m, n)
     return out
 
 
@@ -139,9 +107,7 @@ def three_interpolate_grad(grad_out, idx, weight, m):
     _need_cuda(grad_out)
     B, C, n = grad_out.shape
     out = torch.zeros((B, C, int(m)), dtype=torch.float32, device=grad_out.device)
-    with _on(grad_out):
-        _lib.check(_lib.lib().gb_three_interp_bwd(grad_out.data_ptr(), idx.data_ptr(), weight.data_ptr(), out.data_ptr(), B, C,
-                                                  n, int(m), _stream(grad_out)), "three_interpolate_grad")
+    _lib.call("gb_three_interp_bwd", grad_out, grad_out.data_ptr(), idx.data_ptr(), weight.data_ptr(), out.data_ptr(), B, C, n, int(m))
     return out
 
 
@@ -154,9 +120,7 @@ def ball_query(new_xyz, xyz, radius, nsample):
     B, m = new_xyz.shape[0], new_xyz.shape[1]
     N = xyz.shape[1]
     idx = torch.empty((B, m, int(nsample)), dtype=torch.int32, device=new_xyz.device)
-    with _on(new_xyz):
-        _lib.check(_lib.lib().gb_ball_query(new_xyz.data_ptr(), xyz.data_ptr(), idx.data_ptr(), B, N, m, float(radius),
-                                            int(nsample), _stream(new_xyz)), "ball_query")
+    _lib.call("gb_ball_query", new_xyz, new_xyz.data_ptr(), xyz.data_ptr(), idx.data_ptr(), B, N, m, float(radius), int(nsample))
     return idx
 
 
@@ -170,10 +134,7 @@ def cylinder_query(new_xyz, xyz, rot, radius, hmin, hmax, nsample):
     B, m = new_xyz.shape[0], new_xyz.shape[1]
     N = xyz.shape[1]
     idx = torch.empty((B, m, int(nsample)), dtype=torch.int32, device=new_xyz.device)
-    with _on(new_xyz):
-        _lib.check(_lib.lib().gb_cylinder_query(new_xyz.data_ptr(), xyz.data_ptr(), rot.data_ptr(), idx.data_ptr(), B, N, m,
-                                                float(radius), float(hmin), float(hmax), int(nsample), _stream(new_xyz)),
-                   "cylinder_query")
+    _lib.call("gb_cylinder_query", new_xyz, new_xyz.data_ptr(), xyz.data_ptr(), rot.data_ptr(), idx.data_ptr(), B, N, m, float(radius), float(hmin), float(hmax), int(nsample))
     return idx
 
 
@@ -186,9 +147,7 @@ def group_points(points, idx):
     B, C, N = points.shape
     npoints, nsample = idx.shape[1], idx.shape[2]
     out = torch.empty((B, C, npoints, nsample), dtype=torch.float32, device=points.device)
-    with _on(points):
-        _lib.check(_lib.lib().gb_group_fwd(points.data_ptr(), idx.data_ptr(), out.data_ptr(), B, C, N, npoints, nsample,
-                                           _stream(points)), "group_points")
+    _lib.call("gb_group_fwd", points, points.data_ptr(), idx.data_ptr(), out.data_ptr(), B, C, N, npoints, nsample)
     return out
 
 
@@ -201,7 +160,5 @@ def group_points_grad(grad_out, idx, n):
     B, C = grad_out.shape[0], grad_out.shape[1]
     npoints, nsample = idx.shape[1], idx.shape[2]
     out = torch.zeros((B, C, int(n)), dtype=torch.float32, device=grad_out.device)
-    with _on(grad_out):
-        _lib.check(_lib.lib().gb_group_bwd(grad_out.data_ptr(), idx.data_ptr(), out.data_ptr(), B, C, int(n), npoints, nsample,
-                                           _stream(grad_out)), "group_points_grad")
+    _lib.call("gb_group_bwd", grad_out, grad_out.data_ptr(), idx.data_ptr(), out.data_ptr(), B, C, int(n), npoints, nsample)
     return out

@@ -80,6 +80,54 @@ def check(err, what):
         raise RuntimeError(f"{what}: CUDA error {err} ({msg.decode() if msg else '?'})")
 
 
+# ---- optional per-launch profiler (bench.py): name -> list of (start_event, end_event, algorithmic_bytes) ----
+PROFILER = None
+
+
+# ALGORITHMIC bytes of one launch from its integer arguments (SURVEY.md 8d / DESIGN.md "Roofline accounting"):
+# the bytes the op must read and write at minimum, whatever the implementation does.
+ALGO_BYTES = {
+    "gb_fps": lambda a: a[3] * (12 * a[4] + 4 * a[5]),                                   # b*(12n + 4m)
+    "gb_gather_fwd": lambda a: a[3] * (4 * a[4] * a[5] + 4 * a[6] + 4 * a[4] * a[6]),     # b*(4cn + 4m + 4cm)
+    "gb_gather_bwd": lambda a: a[3] * (4 * a[4] * a[5] + 4 * a[6] + 4 * a[4] * a[6]),
+    "gb_ball_query": lambda a: a[3] * (12 * a[4] + 12 * a[5] + 4 * a[5] * a[7]),          # b*(12n + 12m + 4 m ns)
+    "gb_cylinder_query": lambda a: a[4] * (12 * a[5] + 48 * a[6] + 4 * a[6] * a[10]),     # b*(12n + 48m + 4 m ns)
+    "gb_group_fwd": lambda a: a[3] * (4 * a[4] * a[5] + 4 * a[6] * a[7] + 4 * a[4] * a[6] * a[7]),
+    "gb_group_bwd": lambda a: a[3] * (4 * a[4] * a[5] + 4 * a[6] * a[7] + 4 * a[4] * a[6] * a[7]),
+    "gb_three_nn": lambda a: a[4] * (12 * a[5] + 12 * a[6] + 24 * a[5]),                  # b*(12n + 12m + 24n)
+    "gb_three_interp_fwd": lambda a: a[4] * (4 * a[5] * a[6] + 24 * a[7] + 4 * a[5] * a[7]),   # b*(4cm + 24n + 4cn)
+    "gb_three_interp_bwd": lambda a: a[4] * (4 * a[5] * a[7] + 24 * a[6] + 4 * a[5] * a[6]),   # args (b,c,n,m)
+    "gb_knn": lambda a: a[3] * (4 * a[4] * (a[5] + a[6]) + 8 * a[7] * a[6]),              # b*(4d(R+Q) + 8kQ)
+    "gb_collision_counts": lambda a: 24 * a[1] + 176 * a[5] + 48 * a[5],
+}
+
+
+def call(name, ref_tensor, *args):
+    """Launch entry point `name` on torch's current stream of ref_tensor's device (making that device current for the
+    launch), raise on error, and -- when PROFILER is a dict -- bracket the launch with CUDA events on that stream."""
+    import torch
+    dev = ref_tensor.device
+    prev = None
+    if dev.index is not None and dev.index != torch.cuda.current_device():
+        prev = torch.cuda.current_device()
+        torch.cuda.set_device(dev.index)
+    try:
+        stream = torch.cuda.current_stream(dev)
+        fn = getattr(lib(), name)
+        if PROFILER is None:
+            err = fn(*args, stream.cuda_stream)
+        else:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            err = fn(*args, stream.cuda_stream)
+            e1.record(stream)
+            PROFILER.setdefault(name, []).append((e0, e1, ALGO_BYTES[name](args)))
+    finally:
+        if prev is not None:
+            torch.cuda.set_device(prev)
+    check(err, name)
+
+
 def set_tuning(key, value):
     check(lib().gb_set_tuning(key.encode(), int(value)), f"gb_set_tuning({key})")
 

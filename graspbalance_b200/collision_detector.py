@@ -17,7 +17,6 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._ext import _on, _stream
 
 
 def voxel_down_sample(points, voxel_size):
@@ -54,10 +53,8 @@ def collision_counts(scene_points_dev, T, R, thr):
             raise RuntimeError(f"{name} must be a contiguous float64 CUDA tensor")
     G = T.shape[0]
     counts = torch.empty((G, 6), dtype=torch.int64, device=T.device)
-    with _on(T):
-        _lib.check(_lib.lib().gb_collision_counts(scene_points_dev.data_ptr(), scene_points_dev.shape[0], T.data_ptr(),
-                                                  R.data_ptr(), thr.data_ptr(), G, counts.data_ptr(), _stream(T)),
-                   "collision_counts")
+    _lib.call("gb_collision_counts", T, scene_points_dev.data_ptr(), scene_points_dev.shape[0], T.data_ptr(), R.data_ptr(),
+              thr.data_ptr(), G, counts.data_ptr())
     return counts
 
 

@@ -7,7 +7,6 @@ CUDA tensors only: the reference's CPU path (cpu/knn_cpu.cpp) is not reproduced 
 import torch
 
 from . import _lib
-from ._ext import _on, _stream
 
 
 def knn(ref, query, idx):
@@ -23,6 +22,5 @@ def knn(ref, query, idx):
     k = idx.shape[1]
     if query.shape[0] != B or query.shape[1] != D or idx.shape[0] != B or idx.shape[2] != Q:
         raise RuntimeError("knn: inconsistent shapes")
-    with _on(ref):
-        _lib.check(_lib.lib().gb_knn(ref.data_ptr(), query.data_ptr(), idx.data_ptr(), B, D, R, Q, k, _stream(ref)), "knn")
+    _lib.call("gb_knn", ref, ref.data_ptr(), query.data_ptr(), idx.data_ptr(), B, D, R, Q, k)
     return 1

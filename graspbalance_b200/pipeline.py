@@ -1,0 +1,175 @@
+"""The GraspBalance point-op pipeline: the exact sequence of hot-path operator calls one forward + backward of the
+reference model issues per batch of 20k-point scenes, with random tensors standing in for the
+dense MLP outputs between them (the MLPs/heads are cuDNN/cuBLAS work and out of scope).
+
+Stages and the reference call sites they reproduce:
+  SA1..SA4   PointnetSAModuleVotes.forward (PointNet/pointnet2_modules.py:148-188): furthest_point_sample ->
+             gather_operation -> QueryAndGroup (ball_query + grouping_operation on xyz and features), variant A;
+             npoint/radius/nsample from TrainModel/drp.py:161-246.
+  InvResMLP  3+6+3+3 LocalAggregation blocks (drp.py:62-67): group.QueryAndGroup (ball_query + two grouping_operations),
+             variant B; radii/nsample from drp.py:169-247.
+  FP1, FP2   PointnetFPModule.forward (pointnet2_modules.py:407-435): three_nn -> weights -> three_interpolate.
+  UP         seed features back to the full cloud (TrainModel/graspbalance.py:37-41): three_nn + three_interpolate, C=256.
+  CROP       4 GraspWidthGrouping x 4 depths = 16 CylinderQueryAndGroup calls (TrainModel/modules.py:104-124,
+             graspbalance.py:84-87,123: radii 0.08 x {.25,.5,.75,1}, hmin -0.02, hmax {.01,.02,.03,.04}, nsample 64).
+  COLLISION  ModelFreeCollisionDetector.detect's occupancy test for 1024 grasps per scene (collision_detector.py:16-64).
+Every grouped / interpolated feature tensor is back-propagated with a random upstream gradient through the reference's
+autograd Functions (GroupingOperation / GatherOperation / ThreeInterpolate backward).
+
+Everything here goes through the public drop-in API (pointnet2_utils, group, upsampling, collision_detector).
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import group as gb_group
+from . import pointnet2_utils as pu
+from .collision_detector import collision_counts
+
+# (npoint, radius, nsample, C_in) of the four SA modules and (blocks, C, radius, nsample) of the InvResMLP groups
+SA_SPECS = [(2048, 0.04, 64, 0), (1024, 0.1, 32, 128), (512, 0.2, 16, 256), (256, 0.3, 16, 256)]
+IRM_SPECS = [(3, 128, 0.08, 64), (6, 256, 0.2, 32), (3, 256, 0.4, 16), (3, 256, 0.6, 16)]
+CROP_RADII = [0.08 * s for s in (0.25, 0.5, 0.75, 1.0)]
+CROP_HMAX = [0.01, 0.02, 0.03, 0.04]
+CROP_HMIN = -0.02
+NUM_SEED = 1024
+NUM_GRASP = 1024
+
+
+def _randn(shape, gen, device):
+    return torch.randn(shape, generator=gen, device=device, dtype=torch.float32)
+
+
+class OpPipeline:
+    """Holds the stand-in feature / gradient tensors (allocated once, outside any timed region) and runs the chain."""
+
+    def __init__(self, batch, n_points=20000, device="cuda", seed=0, backward=True):
+        self.B, self.N, self.device, self.backward = batch, n_points, torch.device(device), backward
+        gen = torch.Generator(device=self.device).manual_seed(seed)
+        B = batch
+        self.sa_groupers = [pu.QueryAndGroup(r, ns, use_xyz=True, ret_grouped_xyz=True, normalize_xyz=True)
+                            for (_, r, ns, _) in SA_SPECS]
+        self.irm_groupers = [gb_group.QueryAndGroup(r, ns) for (_, _, r, ns) in IRM_SPECS]
+        self.crop_groupers = [[pu.CylinderQueryAndGroup(r, CROP_HMIN, h, 64, use_xyz=True) for h in CROP_HMAX]
+                              for r in CROP_RADII]
+        # stand-ins for MLP outputs (features entering each stage) and for upstream gradients
+        self.sa_in_feats = [None] + [_randn((B, c, SA_SPECS[i - 1][0]), gen, self.device) for i, (_, _, _, c) in
+                                     enumerate(SA_SPECS) if i > 0]
+        self.irm_feats = [_randn((B, c, SA_SPECS[i][0]), gen, self.device) for i, (_, c, _, _) in enumerate(IRM_SPECS)]
+        self.sa_grads = [None] + [_randn((B, SA_SPECS[i][3], SA_SPECS[i][0], SA_SPECS[i][2]), gen, self.device)
+                                  for i in range(1, 4)]
+        self.irm_grads = [_randn((B, c, SA_SPECS[i][0], ns), gen, self.device) for i, (_, c, _, ns) in enumerate(IRM_SPECS)]
+        self.fp_feats = [_randn((B, 256, 256), gen, self.device), _randn((B, 256, 512), gen, self.device),
+                         _randn((B, 256, 1024), gen, self.device)]
+        self.fp_grads = [_randn((B, 256, 512), gen, self.device), _randn((B, 256, 1024), gen, self.device),
+                         _randn((B, 256, n_points), gen, self.device)]
+        for t in self.sa_in_feats[1:] + self.irm_feats + self.fp_feats:
+            t.requires_grad_(backward)
+
+    # ------------------------------------------------------------------------------------------------------------
+    @staticmethod
+    def _interp(unknown, known, feats, grad):
+        dist, idx = pu.three_nn(unknown, known)
+        dist_recip = 1.0 / (dist + 1e-8)
+        weight = dist_recip / torch.sum(dist_recip, dim=2, keepdim=True)  # pointnet2_modules.py:413-416
+        out = pu.three_interpolate(feats, idx, weight)
+        if grad is not None:
+            out.backward(grad)
+        return out
+
+    def run(self, xyz, view_rot, grasps=None):
+        """xyz [B,N,3] f32 CUDA; view_rot [B,1024,3,3] f32 CUDA (approach frames of the seeds); grasps = optional dict of
+        per-scene fp64 CUDA tensors {scene_points: list of [N'_b,3], T [B,G,3], R [B,G,3,3], thr [B,G,10]}.
+        Returns a dict of the per-scene outputs a caller would keep."""
+        bw = self.backward
+        out = {}
+        cur_xyz, level_xyz = xyz, []
+        for lvl, (npoint, radius, nsample, c_in) in enumerate(SA_SPECS):
+            # ---- SA module (variant A) ----
+            inds = pu.furthest_point_sample(cur_xyz, npoint)
+            new_xyz = pu.gather_operation(cur_xyz.transpose(1, 2).contiguous(), inds).transpose(1, 2).contiguous()
+            feats = self.sa_in_feats[lvl]
+            grouped, _ = self.sa_groupers[lvl](cur_xyz, new_xyz, feats)
+            if bw and feats is not None:
+                grouped[:, 3:].backward(self.sa_grads[lvl])
+            if lvl == 0:
+                out["sa1_inds"] = inds
+            # ---- InvResMLP blocks (variant B) ----
+            blocks, c, _, _ = IRM_SPECS[lvl]
+            f = self.irm_feats[lvl]
+            for _ in range(blocks):
+                dp, fj = self.irm_groupers[lvl](new_xyz, new_xyz, f)
+                if bw:
+                    fj.backward(self.irm_grads[lvl])
+            cur_xyz = new_xyz
+            level_xyz.append(new_xyz)
+        sa1_xyz, sa2_xyz, sa3_xyz, sa4_xyz = level_xyz
+        # ---- FP modules + up-sampling of the seed features to the full cloud ----
+        self._interp(sa3_xyz, sa4_xyz, self.fp_feats[0], self.fp_grads[0] if bw else None)
+        self._interp(sa2_xyz, sa3_xyz, self.fp_feats[1], self.fp_grads[1] if bw else None)
+        up = self._interp(xyz, sa2_xyz, self.fp_feats[2], self.fp_grads[2] if bw else None)
+        out["up_checksum"] = up[:, :, ::997].sum()
+        seed_xyz = sa2_xyz  # fp2_xyz: 1024 seeds (drp.py:301-303)
+        out["seed_inds"] = out["sa1_inds"][:, :NUM_SEED]
+        # ---- grasp crop: 4 radii x 4 depths cylinder query + group ----
+        crop_sum = None
+        for groupers in self.crop_groupers:
+            for gq in groupers:
+                g = gq(xyz, seed_xyz, view_rot)  # [B,3,1024,64]
+                s = g[:, :, :, 0].sum()
+                crop_sum = s if crop_sum is None else crop_sum + s
+        out["crop_checksum"] = crop_sum
+        # ---- collision test ----
+        if grasps is not None:
+            out["collision_counts"] = torch.stack([
+                collision_counts(grasps["scene_points"][b], grasps["T"][b], grasps["R"][b], grasps["thr"][b])
+                for b in range(len(grasps["scene_points"]))])
+        if bw:
+            out["grad_checksum"] = sum(t.grad[:, :, ::61].sum() for t in self.sa_in_feats[1:] + self.irm_feats + self.fp_feats)
+            for t in self.sa_in_feats[1:] + self.irm_feats + self.fp_feats:
+                t.grad = None
+        return out
+
+
+def algorithmic_bytes_per_scene(n=20000, backward=True):
+    """HBM bytes one scene's pipeline must move at minimum (SURVEY.md 8d formulas), by op family."""
+    by = {"fps": 0, "gather": 0, "ball_query": 0, "cylinder_query": 0, "group_fwd": 0, "group_bwd": 0, "three_nn": 0,
+          "interp_fwd": 0, "interp_bwd": 0, "collision": 0}
+    cur = n
+    for lvl, (m, _, ns, c_in) in enumerate(SA_SPECS):
+        by["fps"] += 12 * cur + 4 * m
+        by["gather"] += 4 * 3 * cur + 4 * m + 4 * 3 * m
+        by["ball_query"] += 12 * cur + 12 * m + 4 * m * ns
+        for c in ([3] if c_in == 0 else [3, c_in]):
+            by["group_fwd"] += 4 * c * cur + 4 * m * ns + 4 * c * m * ns
+        if c_in and backward:
+            by["group_bwd"] += 4 * c_in * cur + 4 * m * ns + 4 * c_in * m * ns
+        blocks, c, _, nsb = IRM_SPECS[lvl]
+        by["ball_query"] += blocks * (24 * m + 4 * m * nsb)
+        by["group_fwd"] += blocks * ((4 * 3 * m + 4 * m * nsb + 4 * 3 * m * nsb) + (4 * c * m + 4 * m * nsb + 4 * c * m * nsb))
+        if backward:
+            by["group_bwd"] += blocks * (4 * c * m + 4 * m * nsb + 4 * c * m * nsb)
+        cur = m
+    for (nn, mm) in ((512, 256), (1024, 512), (n, 1024)):
+        by["three_nn"] += 12 * nn + 12 * mm + 24 * nn
+        by["interp_fwd"] += 4 * 256 * mm + 24 * nn + 4 * 256 * nn
+        if backward:
+            by["interp_bwd"] += 4 * 256 * mm + 24 * nn + 4 * 256 * nn
+    by["cylinder_query"] += 16 * (12 * n + 48 * NUM_SEED + 4 * NUM_SEED * 64)
+    by["group_fwd"] += 16 * (4 * 3 * n + 4 * NUM_SEED * 64 + 4 * 3 * NUM_SEED * 64)
+    by["collision"] += 24 * 5000 + 120 * NUM_GRASP + NUM_GRASP
+    return by
+
+
+def make_view_rotations(batch, seed=0, num_seed=NUM_SEED):
+    """Approach frames for the seeds, built like the reference's view templates + batch_viewpoint_params_to_matrix
+    (loss_utils.py:15-49): Fibonacci-sphere views, zero in-plane angle."""
+    from .scenes import viewpoint_rotations
+    rng = np.random.default_rng(seed)
+    phi = (math.sqrt(5) - 1) / 2
+    i = rng.integers(0, 300, (batch, num_seed))
+    z = (2 * i + 1) / 300.0 - 1
+    views = np.stack([np.sqrt(1 - z ** 2) * np.cos(2 * i * np.pi * phi), np.sqrt(1 - z ** 2) * np.sin(2 * i * np.pi * phi), z],
+                     axis=-1).astype(np.float32)
+    return viewpoint_rotations(-views, np.zeros((batch, num_seed), np.float32))

@@ -1,0 +1,176 @@
+"""CPU-only tests: the C-ABI library loads and exports every symbol include/gbops.h declares (no compute without a
+GPU), the Python drop-in surface has the reference's names, and the host-side logic behaves."""
+import ctypes
+import json
+import math
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    txt = open(os.path.join(ROOT, "include", "gbops.h")).read()
+    return sorted(set(re.findall(r"GB_API [\w \*]*?\b(gb_[a-z0-9_]+)\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    from graspbalance_b200 import _lib
+    _lib.build()
+    syms = _header_symbols()
+    assert len(syms) >= 18
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for s in syms:
+        assert hasattr(L, s), f"{s} declared in include/gbops.h but not exported by libgbops.so"
+    assert sorted(_lib.SIGNATURES) == syms, "ctypes signature table and header disagree"
+    assert _lib.lib().gb_abi_version() == 1
+    assert _lib.lib().gb_error_string(1)  # cudaErrorInvalidValue has a message
+
+
+def test_tuning_knobs_round_trip_and_reject_unknown_keys():
+    from graspbalance_b200 import _lib
+    _lib.set_tuning("fps_cluster", 8)
+    assert _lib.get_tuning("fps_cluster") == 8
+    _lib.set_tuning("fps_cluster", 0)
+    with pytest.raises(RuntimeError):
+        _lib.set_tuning("no_such_knob", 1)
+
+
+def test_library_is_sm100a_with_blackwell_instructions():
+    from graspbalance_b200 import _lib
+    r = subprocess.run(["cuobjdump", "--list-elf", _lib.LIB_PATH], capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    assert "sm_100a" in r.stdout
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "UBLKCP" in sass          # cp.async.bulk: TMA engine stages the query tiles
+    assert "REDUX" in sass           # redux.sync argmax in FPS
+    assert "SYNCS" in sass           # mbarrier transactions
+
+
+def test_drop_in_surface_has_the_reference_names():
+    from graspbalance_b200 import (_ext, collision_detector, group, knn_C, knn_modules, pointnet2_batch_cuda, pointnet2_utils,
+                                   subsample, upsampling)
+    for n in ["gather_points", "gather_points_grad", "furthest_point_sampling", "three_nn", "three_interpolate",
+              "three_interpolate_grad", "ball_query", "group_points", "group_points_grad", "cylinder_query"]:
+        assert callable(getattr(_ext, n))                                   # bindings.cpp:13-26
+    for n in ["ball_query_wrapper", "group_points_wrapper", "group_points_grad_wrapper", "gather_points_wrapper",
+              "gather_points_grad_wrapper", "furthest_point_sampling_wrapper", "three_nn_wrapper", "three_interpolate_wrapper",
+              "three_interpolate_grad_wrapper"]:
+        assert callable(getattr(pointnet2_batch_cuda, n))                   # pointnet2_api.cpp:11-23
+    assert callable(knn_C.knn) and callable(knn_modules.myknn)
+    for n in ["furthest_point_sample", "gather_operation", "three_nn", "three_interpolate", "grouping_operation", "ball_query",
+              "cylinder_query", "FurthestPointSampling", "GatherOperation", "ThreeNN", "ThreeInterpolate", "GroupingOperation",
+              "BallQuery", "CylinderQuery", "QueryAndGroup", "GroupAll", "CylinderQueryAndGroup", "RandomDropout"]:
+        assert hasattr(pointnet2_utils, n)
+    for n in ["create_grouper", "get_aggregation_feautres", "grouping_operation", "gather_operation", "ball_query", "QueryAndGroup",
+              "KNNGroup", "GroupAll", "KNN", "DilatedKNN", "torch_grouping_operation"]:
+        assert hasattr(group, n)
+    for n in ["furthest_point_sample", "random_sample", "gather_operation", "fps", "RandomSample"]:
+        assert hasattr(subsample, n)
+    for n in ["three_nn", "three_interpolate", "three_interpolation"]:
+        assert hasattr(upsampling, n)
+    assert hasattr(collision_detector, "ModelFreeCollisionDetector")
+
+
+def test_cpu_tensors_are_rejected_like_the_reference():
+    from graspbalance_b200 import _ext, knn_C, pointnet2_batch_cuda
+    x = torch.zeros(1, 8, 3)
+    with pytest.raises(RuntimeError, match="CPU not supported"):
+        _ext.furthest_point_sampling(x, 4)                                  # sampling.cpp:88
+    with pytest.raises(RuntimeError, match="CPU not supported"):
+        _ext.ball_query(x, x, 0.1, 4)                                       # ball_query.cpp:33
+    with pytest.raises(RuntimeError, match="must be a contiguous tensor"):
+        _ext.gather_points(torch.zeros(1, 3, 8).transpose(1, 2), torch.zeros(1, 2, dtype=torch.int32))
+    with pytest.raises(RuntimeError, match="must be an int tensor"):
+        _ext.gather_points(torch.zeros(1, 3, 8), torch.zeros(1, 2, dtype=torch.int64))
+    with pytest.raises(RuntimeError, match="must be CUDA tensor"):
+        pointnet2_batch_cuda.ball_query_wrapper(1, 8, 8, 0.1, 4, x, x, torch.zeros(1, 8, 4, dtype=torch.int32))
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        knn_C.knn(torch.zeros(1, 3, 8), torch.zeros(1, 3, 2), torch.zeros(1, 1, 2, dtype=torch.int64))
+
+
+def test_install_as_reference_modules_registers_the_native_names():
+    import graspbalance_b200
+    saved = {k: sys.modules.get(k) for k in ("pointnet2", "pointnet2._ext", "pointnet2_batch_cuda", "KNN", "KNN._C")}
+    try:
+        graspbalance_b200.install_as_reference_modules()
+        import pointnet2._ext as e
+        import pointnet2_batch_cuda as b
+        from KNN import _C
+        assert e.ball_query is graspbalance_b200._ext.ball_query and callable(b.three_nn_wrapper) and callable(_C.knn)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+
+def test_block_size_formula_matches_the_reference_expression():
+    """gb_fps computes floor(log2 n) in integers; the reference uses (int)(log(n)/log(2)) in doubles
+    (cuda_utils.h:21-27).  They must agree, or the tie order changes."""
+    import oracle
+    ns = list(range(1, 5000)) + [2 ** e + d for e in range(1, 23) for d in (-1, 0, 1)] + [20000, 40960, 50000]
+    for n in ns:
+        for cap in (512, 1024):
+            assert oracle.opt_n_threads(n, cap) == max(min(1 << (n.bit_length() - 1), cap), 1), n
+
+
+def test_scene_generator_is_deterministic_and_has_duplicates():
+    from graspbalance_b200 import scenes
+    a, b = scenes.tabletop_scene(7), scenes.tabletop_scene(7)
+    assert a.shape == (20000, 3) and a.dtype == np.float32 and (a == b).all()
+    assert len(np.unique(a, axis=0)) <= 20000 - 400
+    assert not (scenes.tabletop_scene(8) == a).all()
+    r = scenes.random_rotations(np.random.default_rng(0), (16,))
+    np.testing.assert_allclose(np.linalg.det(r), 1.0, atol=1e-12)
+    np.testing.assert_allclose(r @ r.transpose(0, 2, 1), np.broadcast_to(np.eye(3), (16, 3, 3)), atol=1e-12)
+    v = scenes.viewpoint_rotations(np.array([[0, 0, 1.0], [1, 2, 3.0]], np.float32), np.array([0.3, 1.0], np.float32))
+    np.testing.assert_allclose(v @ v.transpose(0, 2, 1), np.broadcast_to(np.eye(3), (2, 3, 3)), atol=1e-5)
+
+
+def test_pipeline_accounting_and_sharding_helpers():
+    from graspbalance_b200 import pipeline, sharding
+    by = pipeline.algorithmic_bytes_per_scene()
+    # group fwd C=128 at N=20000, m=1024, ns=64 is 44,056,576 B; check the same formula on the SA2 feature group
+    assert by["group_fwd"] > 4e8 and by["fps"] == sum(12 * n + 4 * m for n, m in ((20000, 2048), (2048, 1024), (1024, 512), (512, 256)))
+    assert sharding.scene_ids_for_rank(1, 4, 8) == list(range(8, 16))
+    assert sharding.shard_batch(32, 8) == [(4 * r, 4 * r + 4) for r in range(8)]
+    assert sharding.shard_batch(10, 4) == [(0, 3), (3, 6), (6, 8), (8, 10)]
+    with pytest.raises(ValueError):
+        sharding.scene_ids_for_rank(4, 4, 8)
+    assert pipeline.make_view_rotations(2).shape == (2, 1024, 3, 3)
+
+
+def test_missing_library_fails_loudly(tmp_path, monkeypatch):
+    from graspbalance_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(RuntimeError, match="no CPU or PyTorch fallback"):
+        _lib.lib()
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "graspbalance_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r"^\s*(import|from)\s+oracle\b", src, re.M), fn
+
+
+@pytest.mark.timeout(300)
+def test_bench_reference_arm_prints_the_contract_line():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=280)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "scenes/s" and line["higher_is_better"] is True
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and math.isfinite(line["value"]) and line["value"] > 0
