@@ -234,6 +234,8 @@ def main():
     ap.add_argument("--no-backward", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cuda-profiler-range", action="store_true",
+                    help="bracket the timed steps with cudaProfilerStart/Stop (for `ncu --profile-from-start off`)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "gbops" else args.warmup
 
@@ -313,7 +315,12 @@ def main():
         time.sleep(0.3)
     _lib.PROFILER = {}
     launches0 = _lib.launch_count()
+    if args.cuda_profiler_range:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
     ms, tw0, tw1 = timed(args.steps, True, resident_inputs)
+    if args.cuda_profiler_range:
+        torch.cuda.profiler.stop()
     launches = _lib.launch_count() - launches0
     prof, _lib.PROFILER = _lib.PROFILER, None
     clocks = sampler.stop(tw0, tw1) if rank == 0 else None
