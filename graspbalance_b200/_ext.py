@@ -106,8 +106,8 @@ def three_interpolate_grad(grad_out, idx, weight, m):
         _cuda(idx, "idx"); _cuda(weight, "weight")
     _need_cuda(grad_out)
     B, C, n = grad_out.shape
-    out = torch.zeros((B, C, int(m)), dtype=torch.float32, device=grad_out.device)
-    _lib.call("gb_three_interp_bwd", grad_out, grad_out.data_ptr(), idx.data_ptr(), weight.data_ptr(), out.data_ptr(), B, C, n, int(m))
+    out = torch.empty((B, C, int(m)), dtype=torch.float32, device=grad_out.device)  # fully written by the _set entry
+    _lib.call("gb_three_interp_bwd_set", grad_out, grad_out.data_ptr(), idx.data_ptr(), weight.data_ptr(), out.data_ptr(), B, C, n, int(m))
     return out
 
 
@@ -159,6 +159,6 @@ def group_points_grad(grad_out, idx, n):
     _need_cuda(grad_out)
     B, C = grad_out.shape[0], grad_out.shape[1]
     npoints, nsample = idx.shape[1], idx.shape[2]
-    out = torch.zeros((B, C, int(n)), dtype=torch.float32, device=grad_out.device)
-    _lib.call("gb_group_bwd", grad_out, grad_out.data_ptr(), idx.data_ptr(), out.data_ptr(), B, C, int(n), npoints, nsample)
+    out = torch.empty((B, C, int(n)), dtype=torch.float32, device=grad_out.device)  # fully written by the _set entry
+    _lib.call("gb_group_bwd_set", grad_out, grad_out.data_ptr(), idx.data_ptr(), out.data_ptr(), B, C, int(n), npoints, nsample)
     return out

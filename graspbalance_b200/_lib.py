@@ -27,9 +27,11 @@ SIGNATURES = {
     "gb_cylinder_query": [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _f, _i, _vp],
     "gb_group_fwd": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "gb_group_bwd": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "gb_group_bwd_set": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "gb_three_nn": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp],
     "gb_three_interp_fwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "gb_three_interp_bwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "gb_three_interp_bwd_set": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "gb_knn": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "gb_collision_counts": [_vp, _i, _vp, _vp, _vp, _i, _vp, _vp],
     "gb_collision_counts_host": [_vp, _i, _vp, _vp, _vp, _i, _vp],
@@ -97,6 +99,8 @@ ALGO_BYTES = {
     "gb_three_nn": lambda a: a[4] * (12 * a[5] + 12 * a[6] + 24 * a[5]),                  # b*(12n + 12m + 24n)
     "gb_three_interp_fwd": lambda a: a[4] * (4 * a[5] * a[6] + 24 * a[7] + 4 * a[5] * a[7]),   # b*(4cm + 24n + 4cn)
     "gb_three_interp_bwd": lambda a: a[4] * (4 * a[5] * a[7] + 24 * a[6] + 4 * a[5] * a[6]),   # args (b,c,n,m)
+    "gb_group_bwd_set": lambda a: a[3] * (4 * a[4] * a[5] + 4 * a[6] * a[7] + 4 * a[4] * a[6] * a[7]),
+    "gb_three_interp_bwd_set": lambda a: a[4] * (4 * a[5] * a[7] + 24 * a[6] + 4 * a[5] * a[6]),
     "gb_knn": lambda a: a[3] * (4 * a[4] * (a[5] + a[6]) + 8 * a[7] * a[6]),              # b*(4d(R+Q) + 8kQ)
     "gb_collision_counts": lambda a: 24 * a[1] + 176 * a[5] + 48 * a[5],
 }

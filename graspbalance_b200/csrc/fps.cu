@@ -292,20 +292,21 @@ extern "C" int gb_fps(const float *xyz, float *temp, int *idx, int b, int n, int
   int C = g_tuning.fps_cluster;
   if (C != 1 && C != 2 && C != 4 && C != 8 && C != 16) C = 0;
   if (C == 0) {
-    // as many CTAs per scene as fit on the chip at two CTAs per SM, but not fewer than ~2048 points per CTA (below
-    // that the DSMEM hop costs more than the shorter register sweep saves)
-    C = 16;
-    while (C > 1 && ((long)b * C > 2L * sms || n / C < 2048)) C >>= 1;
-    // capacity: the largest per-CTA register tile is 512 threads x 20 points (= 1024 x 10)
-    while (C < 16 && (long)C * 512 * 20 < n) C <<= 1;
+    // as many CTAs per scene as the chip holds at ONE CTA per SM (co-resident CTAs would share the issue slots of the
+    // register sweep), but not fewer than ~1024 points per CTA (below that the DSMEM hop costs more than the shorter
+    // sweep saves).  Measured on B200, 32 scenes of 20000 points: C=4 x 256 threads 0.75 us/round, C=8 x 1024 3.3 us.
+    C = 8;
+    while (C > 1 && ((long)b * C > (long)sms || n / C < 1024)) C >>= 1;
+    // capacity: the largest per-CTA register tile is 256 threads x 40 points (= 512 x 20 = 1024 x 10)
+    while (C < 16 && (long)C * 256 * 40 < n) C <<= 1;
   }
   for (; C >= 1; C >>= 1) {
     int T = g_tuning.fps_threads;
-    if (T != 512 && T != 1024) {
+    if (T != 256 && T != 512 && T != 1024) {
+      // the fewest warps that hold the CTA's points in registers: the per-round barrier and the redundant per-warp
+      // reduction grow with the warp count, the sweep itself is issue-bound whatever the split
       const int per_cta = (n + C - 1) / C;
-      // 1024 threads (<= 10 points each) give the shortest round; 512 threads with <= 64 registers let two CTAs
-      // share an SM when there are more clusters than the chip holds at one CTA per SM
-      T = (b * C > sms && per_cta <= 512 * 5) ? 512 : 1024;
+      T = per_cta <= 256 * 40 ? 256 : (per_cta <= 512 * 20 ? 512 : 1024);
     }
     int Ce = C;
     while (Ce * T < bs && T < 1024) T <<= 1;
@@ -319,6 +320,8 @@ extern "C" int gb_fps(const float *xyz, float *temp, int *idx, int b, int n, int
     GB_FPS_CASE(6, 1024) GB_FPS_CASE(8, 1024) GB_FPS_CASE(10, 1024)
     GB_FPS_CASE(1, 512) GB_FPS_CASE(2, 512) GB_FPS_CASE(3, 512) GB_FPS_CASE(4, 512) GB_FPS_CASE(5, 512) GB_FPS_CASE(6, 512)
     GB_FPS_CASE(8, 512) GB_FPS_CASE(10, 512) GB_FPS_CASE(12, 512) GB_FPS_CASE(16, 512) GB_FPS_CASE(20, 512)
+    GB_FPS_CASE(1, 256) GB_FPS_CASE(2, 256) GB_FPS_CASE(4, 256) GB_FPS_CASE(6, 256) GB_FPS_CASE(8, 256) GB_FPS_CASE(10, 256)
+    GB_FPS_CASE(12, 256) GB_FPS_CASE(16, 256) GB_FPS_CASE(20, 256) GB_FPS_CASE(24, 256) GB_FPS_CASE(32, 256) GB_FPS_CASE(40, 256)
 #undef GB_FPS_CASE
     if (rc == kFpsRetrySmallerCluster) continue;     // this cluster size cannot be scheduled: halve it
     if (rc == kFpsRetrySmallerCluster - 1) break;    // scene does not fit in the registers of C CTAs

@@ -13,9 +13,11 @@
 //     per channel), 4 LDS gathers per channel group, one coalesced 128-bit streaming store per channel;
 //   * the (scene, chunk) x position work space is flattened and cut into equal contiguous ranges, one per resident CTA,
 //     so all 148 SMs finish together whatever the shape.
-// Backward is a scatter-add: coalesced 128-bit reads of grad_out and idx, red.global.add.f32 into the (L2-resident)
-// gradient rows, with WARP-AGGREGATION of runs of equal indices first -- ball/cylinder query pads a neighbourhood with
-// copies of its first hit, so sparse neighbourhoods collapse to one atomic per run.
+// Backward is a scatter-add.  With >= 4 channels it runs as the atomic-free sorted segmented sum of scatter.cu; the
+// kernels kept here serve few-channel calls (the xyz rows): coalesced 128-bit reads of grad_out and idx,
+// red.global.add.f32 into the (L2-resident) gradient rows, with WARP-AGGREGATION of runs of equal indices first --
+// ball/cylinder query pads a neighbourhood with copies of its first hit, so sparse neighbourhoods collapse to one
+// atomic per run.
 #include "common.cuh"
 
 namespace gb {
@@ -167,237 +169,6 @@ __global__ void __launch_bounds__(256) group_bwd_kernel(const float *__restrict_
   }
 }
 
-// ---- backward without atomics: per-tile counting sort + shared-memory row accumulators -------------------------------
-// The scatter-add grad[b,c,idx[b,e]] += g[b,c,e] is rewritten as a segmented sum.  Pass 1 (once per call, shared by all
-// channels): every tile of kBwdTile consecutive positions is counting-sorted by target index in shared memory, giving
-// skey (sorted targets) and tperm (the tile-local position of each sorted entry).  Pass 2: a CTA owns CC channel rows of
-// one scene as fp32 accumulators in shared memory; per tile it stages g[c, tile] (coalesced 128-bit loads), and the
-// thread sitting on the FIRST entry of each run of equal targets sums the run from the staged tile and adds it to the
-// accumulator -- a plain read-modify-write, because inside a tile every target belongs to exactly one thread and tiles
-// are separated by __syncthreads.  Rows are written out once, coalesced.  No atomics touch global memory; HBM traffic is
-// the algorithmic minimum plus 6 bytes of sort output per position per CHUNK of channels.
-constexpr int kBwdTile = 2048;
-constexpr int kBwdSortThreads = 512;
-constexpr int kBwdThreads = 512;
-
-// grid (tiles_per_scene, b); dynamic smem: (n + 1) ints of bins + 32 ints of scan scratch
-__global__ void __launch_bounds__(kBwdSortThreads) group_bwd_sort_kernel(const int *__restrict__ idx, int per, int n,
-                                                                        int *__restrict__ skey, unsigned short *__restrict__ tperm) {
-  extern __shared__ int s_bins[];  // [n] counts -> running cursors, then [32] warp partials
-  int *wsum = s_bins + n;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const size_t base = (size_t)blockIdx.y * per + (size_t)blockIdx.x * kBwdTile;
-  const int tc = min(kBwdTile, per - blockIdx.x * kBwdTile);
-  for (int i = tid; i < n; i += kBwdSortThreads) s_bins[i] = 0;
-  __syncthreads();
-  int key[kBwdTile / kBwdSortThreads];
-#pragma unroll
-  for (int r = 0; r < kBwdTile / kBwdSortThreads; ++r) {
-    const int e = r * kBwdSortThreads + tid;
-    int k = -1;
-    if (e < tc) {
-      k = __ldg(idx + base + e);
-      if ((unsigned)k >= (unsigned)n) k = -1;  // out-of-range indices are dropped (undefined behaviour in the reference)
-      else atomicAdd(&s_bins[k], 1);
-    }
-    key[r] = k;
-  }
-  __syncthreads();
-  // exclusive scan of s_bins[0..n): each thread owns a contiguous chunk
-  const int chunk = (n + kBwdSortThreads - 1) / kBwdSortThreads;
-  const int c0 = min(n, tid * chunk), c1 = min(n, c0 + chunk);
-  int local = 0;
-  for (int i = c0; i < c1; ++i) local += s_bins[i];
-  int incl = local;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const int o = __shfl_up_sync(0xffffffffu, incl, d);
-    if (lane >= d) incl += o;
-  }
-  if (lane == 31) wsum[warp] = incl;
-  __syncthreads();
-  if (warp == 0) {
-    int w = lane < kBwdSortThreads / 32 ? wsum[lane] : 0;
-    int wi = w;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const int o = __shfl_up_sync(0xffffffffu, wi, d);
-      if (lane >= d) wi += o;
-    }
-    wsum[lane] = wi - w;  // exclusive prefix of the warp totals; lane 31 slot unused beyond 16 warps
-    if (lane == kBwdSortThreads / 32 - 1) wsum[31] = wi;  // total number of valid entries
-  }
-  __syncthreads();
-  int run = wsum[warp] + incl - local;
-  const int total = wsum[31];
-  for (int i = c0; i < c1; ++i) {
-    const int cnt = s_bins[i];
-    s_bins[i] = run;
-    run += cnt;
-  }
-  __syncthreads();
-#pragma unroll
-  for (int r = 0; r < kBwdTile / kBwdSortThreads; ++r) {
-    const int e = r * kBwdSortThreads + tid;
-    if (key[r] >= 0) {
-      const int pos = atomicAdd(&s_bins[key[r]], 1);
-      skey[base + pos] = key[r];
-      tperm[base + pos] = (unsigned short)e;
-    }
-  }
-  for (int e = total + tid; e < tc; e += kBwdSortThreads) skey[base + e] = -1, tperm[base + e] = 0;
-}
-
-// Shared-memory stage of the accumulate kernel: one tile of CC gradient rows + its sort output.
-template <int CC>
-struct BwdStage {
-  float gt[CC][kBwdTile];
-  int sk[kBwdTile];
-  unsigned short tp[kBwdTile];
-};
-
-// phase A + B of one tile (see the comment above): `acc` [CC][n] accumulators, stage `st`, tc valid entries
-template <int CC>
-__device__ __forceinline__ void bwd_process_tile(float *acc, int n, const BwdStage<CC> &st, int tc, int *contk, float *contv) {
-  constexpr int kSteps = kBwdTile / 32;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // phase A: one sorted entry per lane, segmented (by target) warp reduction, run heads update the accumulators
-  for (int stp = warp; stp < kSteps; stp += kBwdThreads / 32) {
-    const int o = stp * 32 + lane;
-    const int k = o < tc ? st.sk[o] : -1;
-    const int p = st.tp[o];
-    float v[CC];
-#pragma unroll
-    for (int cc = 0; cc < CC; ++cc) v[cc] = k >= 0 ? st.gt[cc][p] : 0.f;
-    const int prev = __shfl_up_sync(0xffffffffu, k, 1);
-    const bool head = (lane == 0) || (prev != k);
-    const unsigned heads = __ballot_sync(0xffffffffu, head);
-    const unsigned after = lane == 31 ? 0u : (heads >> (lane + 1));
-    const int run = after ? (__ffs(after) - 1) : (31 - lane);
-    if (heads != 0xffffffffu) {  // some run is longer than one entry
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-#pragma unroll
-        for (int cc = 0; cc < CC; ++cc) {
-          const float other = __shfl_down_sync(0xffffffffu, v[cc], d);
-          if (d <= run) v[cc] += other;
-        }
-      }
-    }
-    const bool cont = lane == 0 && o > 0 && k >= 0 && st.sk[o - 1] == k;  // my run started in the previous warp step
-    if (lane == 0) {
-      contk[stp] = cont ? k : -1;
-      if (cont) {
-#pragma unroll
-        for (int cc = 0; cc < CC; ++cc) contv[cc * kSteps + stp] = v[cc];
-      }
-    }
-    if (head && k >= 0 && !cont) {
-#pragma unroll
-      for (int cc = 0; cc < CC; ++cc) acc[(size_t)cc * n + k] += v[cc];
-    }
-  }
-  __syncthreads();
-  // phase B: fold the continuation partials (ascending targets), passes of 32 by warp 0
-  if (warp == 0) {
-#pragma unroll
-    for (int pass = 0; pass < kSteps / 32; ++pass) {
-      const int e = pass * 32 + lane;
-      const int k = contk[e];
-      if (__any_sync(0xffffffffu, k >= 0)) {
-        float v[CC];
-#pragma unroll
-        for (int cc = 0; cc < CC; ++cc) v[cc] = k >= 0 ? contv[cc * kSteps + e] : 0.f;
-        const int key = k >= 0 ? k : -2 - lane;  // unique keys for empty slots so they never merge
-        const int prev = __shfl_up_sync(0xffffffffu, key, 1);
-        const bool head = (lane == 0) || (prev != key);
-        const unsigned heads = __ballot_sync(0xffffffffu, head);
-        const unsigned after = lane == 31 ? 0u : (heads >> (lane + 1));
-        const int run = after ? (__ffs(after) - 1) : (31 - lane);
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-#pragma unroll
-          for (int cc = 0; cc < CC; ++cc) {
-            const float other = __shfl_down_sync(0xffffffffu, v[cc], d);
-            if (d <= run) v[cc] += other;
-          }
-        }
-        if (head && k >= 0) {
-#pragma unroll
-          for (int cc = 0; cc < CC; ++cc) acc[(size_t)cc * n + k] += v[cc];
-        }
-      }
-      __syncwarp();
-    }
-  }
-}
-
-// grid b * chunks.  dynamic smem: BwdStage<CC>[2] (double buffered, filled by the TMA engine) | contk[64] | contv[CC][64] |
-// acc[CC][n].  bulk_ok: per % 8 == 0 and 16-byte aligned pointers (cp.async.bulk); otherwise tiles are loaded by the threads.
-template <int CC>
-__global__ void __launch_bounds__(kBwdThreads) group_bwd_accum_kernel(const float *__restrict__ grad_out, const int *__restrict__ skey,
-                                                                     const unsigned short *__restrict__ tperm,
-                                                                     float *__restrict__ grad_points, int c, int n, int per,
-                                                                     int chunks, int bulk_ok) {
-  extern __shared__ __align__(128) unsigned char s_raw[];
-  constexpr int kSteps = kBwdTile / 32;
-  BwdStage<CC> *stage = reinterpret_cast<BwdStage<CC> *>(s_raw);
-  int *contk = reinterpret_cast<int *>(stage + 2);
-  float *contv = reinterpret_cast<float *>(contk + kSteps);
-  float *acc = contv + CC * kSteps;
-  __shared__ uint64_t full[2];
-  const int tid = threadIdx.x;
-  const int scene = blockIdx.x / chunks, chunk = blockIdx.x - scene * chunks;
-  const int ch0 = chunk * CC;
-  const int nch = min(CC, c - ch0);
-  for (int i = tid; i < CC * n; i += kBwdThreads) acc[i] = 0.f;
-  for (int i = tid; i < 2 * (int)(sizeof(BwdStage<CC>) / 4); i += kBwdThreads) reinterpret_cast<int *>(stage)[i] = 0;  // rows >= nch stay 0
-  const float *g = grad_out + ((size_t)scene * c + ch0) * per;
-  const size_t sbase = (size_t)scene * per;
-  const int ntiles = (per + kBwdTile - 1) / kBwdTile;
-
-  if (bulk_ok) {
-    if (tid == 0) {
-      mbar_init(&full[0], 1);
-      mbar_init(&full[1], 1);
-      fence_mbar_init();
-    }
-    fence_proxy_async();  // the zero fill above (generic proxy) is ordered before the bulk writes (async proxy)
-    __syncthreads();
-    auto issue = [&](int t) {
-      const int e0 = t * kBwdTile, tc = min(kBwdTile, per - e0);
-      BwdStage<CC> &st = stage[t & 1];
-      mbar_arrive_expect_tx(&full[t & 1], (uint32_t)tc * (4u * nch + 6u));
-      for (int cc = 0; cc < nch; ++cc) bulk_g2s(st.gt[cc], g + (size_t)cc * per + e0, (uint32_t)tc * 4u, &full[t & 1]);
-      bulk_g2s(st.sk, skey + sbase + e0, (uint32_t)tc * 4u, &full[t & 1]);
-      bulk_g2s(st.tp, tperm + sbase + e0, (uint32_t)tc * 2u, &full[t & 1]);
-    };
-    if (tid == 0) issue(0);
-    for (int t = 0; t < ntiles; ++t) {
-      if (tid == 0 && t + 1 < ntiles) issue(t + 1);  // buffer (t+1)&1 was released by the barrier ending tile t-1
-      mbar_wait(&full[t & 1], (uint32_t)((t >> 1) & 1));
-      bwd_process_tile<CC>(acc, n, stage[t & 1], min(kBwdTile, per - t * kBwdTile), contk, contv);
-      __syncthreads();
-    }
-  } else {
-    for (int t = 0; t < ntiles; ++t) {
-      const int e0 = t * kBwdTile, tc = min(kBwdTile, per - e0);
-      BwdStage<CC> &st = stage[0];
-      __syncthreads();
-      for (int cc = 0; cc < nch; ++cc)
-        for (int i = tid; i < tc; i += kBwdThreads) st.gt[cc][i] = __ldg(g + (size_t)cc * per + e0 + i);
-      for (int i = tid; i < tc; i += kBwdThreads) st.sk[i] = __ldg(skey + sbase + e0 + i), st.tp[i] = __ldg(tperm + sbase + e0 + i);
-      __syncthreads();
-      bwd_process_tile<CC>(acc, n, st, tc, contk, contv);
-    }
-  }
-  __syncthreads();
-  for (int cc = 0; cc < nch; ++cc) {
-    float *dst = grad_points + ((size_t)scene * c + ch0 + cc) * n;
-    for (int i = tid; i < n; i += kBwdThreads) dst[i] += acc[(size_t)cc * n + i];  // "+=": the entry point accumulates
-  }
-}
-
 __global__ void group_bwd_generic_kernel(const float *__restrict__ grad_out, const int *__restrict__ idx, float *__restrict__ grad_points,
                                          int c, int n, size_t per, size_t total) {
   for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
@@ -485,78 +256,19 @@ extern "C" int gb_group_fwd(const float *points, const int *idx, float *out, int
   return finish_launch();
 }
 
-// stream-ordered scratch from the device's default pool; the pool is told once to keep freed memory instead of
-// returning it to the driver at every synchronisation (the default), which would make every call pay a fresh allocation
-static cudaError_t scratch_alloc(void **p, size_t bytes, cudaStream_t s) {
-  static bool configured = false;
-  if (!configured) {
-    int dev = 0;
-    cudaMemPool_t pool;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-      unsigned long long keep = ~0ull;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    }
-    configured = true;
-  }
-  return cudaMallocAsync(p, bytes, s);
-}
-
-template <int CC>
-static int launch_group_bwd_sorted(const float *grad_out, const int *skey, const unsigned short *tperm, float *grad_points, int b, int c,
-                                   int n, size_t per, size_t smem, int vec_ok, cudaStream_t s) {
-  auto kern = group_bwd_accum_kernel<CC>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return (int)e;
-  const int chunks = (c + CC - 1) / CC;
-  kern<<<(unsigned)(b * chunks), kBwdThreads, smem, s>>>(grad_out, skey, tperm, grad_points, c, n, (int)per, chunks, vec_ok);
-  count_launch();
-  return finish_launch();
-}
-
-static size_t bwd_accum_smem(int CC, int n) {
-  const size_t stage = (size_t)CC * kBwdTile * sizeof(float) + kBwdTile * (sizeof(int) + sizeof(unsigned short));
-  return 2 * stage + (kBwdTile / 32) * (sizeof(int) + CC * sizeof(float)) + (size_t)CC * n * sizeof(float);
-}
-
-extern "C" int gb_group_bwd(const float *grad_out, const int *idx, float *grad_points, int b, int c, int n, int npoints,
-                            int nsample, gb_stream_t stream) {
+static int group_bwd_impl(const float *grad_out, const int *idx, float *grad_points, int b, int c, int n, int npoints, int nsample,
+                          int overwrite, gb_stream_t stream) {
   if (b < 0 || c < 0 || n <= 0 || npoints < 0 || nsample < 0 || !grad_out || !idx || !grad_points) return (int)cudaErrorInvalidValue;
   const size_t per = (size_t)npoints * nsample;
-  if (b == 0 || c == 0 || per == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
+  if (b == 0 || c == 0) return 0;
+  if (per == 0) return overwrite ? (int)cudaMemsetAsync(grad_points, 0, (size_t)b * c * n * sizeof(float), s) : 0;
 
-  // ---- sorted, atomic-free path: worth the one-off sort when there are enough channels to amortise it ----
-  const size_t sort_smem = ((size_t)n + 32) * sizeof(int);
-  if (!(g_tuning.group_mode & 4) && c >= 4 && sort_smem <= 200u * 1024u && bwd_accum_smem(1, n) <= 200u * 1024u && b <= 65535 &&
-      per < (1u << 30) && (size_t)b * per < (1u << 31)) {
-    // channels per CTA: as many as keep two CTAs on an SM, but enough CTAs to fill the chip
-    int CC = 8;
-    while (CC > 1 && (bwd_accum_smem(CC, n) > 110u * 1024u || (long)b * ((c + CC - 1) / CC) < (long)num_sms())) CC >>= 1;
-    const size_t tiles = (per + kBwdTile - 1) / kBwdTile;
-    int *skey = nullptr;
-    const size_t key_bytes = ((size_t)b * per * sizeof(int) + 255) & ~(size_t)255;
-    cudaError_t e = scratch_alloc((void **)&skey, key_bytes + (size_t)b * per * sizeof(unsigned short), s);
+  // ---- sorted, atomic-free path (scatter.cu): worth the one-off sort when there are enough channels to amortise it ----
+  if (!(g_tuning.group_mode & 4) && seg_scatter_supported(b, c, n, per, 1)) return seg_scatter_add(grad_out, idx, nullptr, grad_points, b, c, n, per, 1, overwrite, s);
+  if (overwrite) {
+    cudaError_t e = cudaMemsetAsync(grad_points, 0, (size_t)b * c * n * sizeof(float), s);
     if (e != cudaSuccess) return (int)e;
-    unsigned short *tperm = reinterpret_cast<unsigned short *>(reinterpret_cast<unsigned char *>(skey) + key_bytes);
-    e = cudaFuncSetAttribute(group_bwd_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem);
-    int rc = (int)e;
-    if (!rc) {
-      group_bwd_sort_kernel<<<dim3((unsigned)tiles, b), kBwdSortThreads, sort_smem, s>>>(idx, (int)per, n, skey, tperm);
-      count_launch();
-      rc = finish_launch();
-    }
-    const int vec_ok = (per % 8 == 0) && (((uintptr_t)grad_out & 15u) == 0);  // bulk (TMA) tile loads possible
-    if (!rc) {
-      const size_t smem = bwd_accum_smem(CC, n);
-      switch (CC) {
-        case 8: rc = launch_group_bwd_sorted<8>(grad_out, skey, tperm, grad_points, b, c, n, per, smem, vec_ok, s); break;
-        case 4: rc = launch_group_bwd_sorted<4>(grad_out, skey, tperm, grad_points, b, c, n, per, smem, vec_ok, s); break;
-        case 2: rc = launch_group_bwd_sorted<2>(grad_out, skey, tperm, grad_points, b, c, n, per, smem, vec_ok, s); break;
-        default: rc = launch_group_bwd_sorted<1>(grad_out, skey, tperm, grad_points, b, c, n, per, smem, vec_ok, s); break;
-      }
-    }
-    cudaFreeAsync(skey, s);
-    return rc;
   }
 
   const bool aligned = (per % 4 == 0) && (((uintptr_t)idx | (uintptr_t)grad_out) & 15u) == 0 && (size_t)b * c <= 65535 && per / 4 < (1u << 30);
@@ -570,6 +282,16 @@ extern "C" int gb_group_bwd(const float *grad_out, const int *idx, float *grad_p
   }
   count_launch();
   return finish_launch();
+}
+
+extern "C" int gb_group_bwd(const float *grad_out, const int *idx, float *grad_points, int b, int c, int n, int npoints,
+                            int nsample, gb_stream_t stream) {
+  return group_bwd_impl(grad_out, idx, grad_points, b, c, n, npoints, nsample, 0, stream);
+}
+
+extern "C" int gb_group_bwd_set(const float *grad_out, const int *idx, float *grad_points, int b, int c, int n, int npoints,
+                                int nsample, gb_stream_t stream) {
+  return group_bwd_impl(grad_out, idx, grad_points, b, c, n, npoints, nsample, 1, stream);
 }
 
 extern "C" int gb_gather_fwd(const float *points, const int *idx, float *out, int b, int c, int n, int m, gb_stream_t stream) {

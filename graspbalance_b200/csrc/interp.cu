@@ -9,7 +9,8 @@
 // four channels; a thread owns four consecutive points (three 128-bit loads each for idx and weight, read once per channel
 // CHUNK) and writes one coalesced 128-bit streaming store per channel.  Value = fmaf(p3,w3, fmaf(p1,w1, p2*w2)), the
 // contraction nvcc applies to the reference expression (SASS-checked), so the forward is bit-exact.
-// Backward: red.global.add.f32 of g*w_t into the [C,m] gradient rows (which stay in L2).
+// Backward: the atomic-free sorted segmented sum of scatter.cu; fallback red.global.add.f32 of g*w_t into the [C,m]
+// gradient rows (which stay in L2).
 #include "common.cuh"
 
 namespace gb {
@@ -166,14 +167,32 @@ extern "C" int gb_three_interp_fwd(const float *points, const int *idx, const fl
   return finish_launch();
 }
 
-extern "C" int gb_three_interp_bwd(const float *grad_out, const int *idx, const float *weight, float *grad_points, int b, int c, int n,
-                                   int m, gb_stream_t stream) {
+static int interp_bwd_impl(const float *grad_out, const int *idx, const float *weight, float *grad_points, int b, int c, int n, int m,
+                           int overwrite, gb_stream_t stream) {
   if (b < 0 || c < 0 || m <= 0 || n < 0 || !grad_out || !idx || !weight || !grad_points) return (int)cudaErrorInvalidValue;
-  if (b == 0 || c == 0 || n == 0) return 0;
+  if (b == 0 || c == 0) return 0;
+  if (n == 0) return overwrite ? (int)cudaMemsetAsync(grad_points, 0, (size_t)b * c * m * sizeof(float), (cudaStream_t)stream) : 0;
+  // atomic-free sorted segmented sum (scatter.cu): entries e = 3*j + t, source g[c][e / 3], weight w[e]
+  if (!(g_tuning.interp_mode & 4) && seg_scatter_supported(b, c, m, (size_t)n * 3, 3))
+    return seg_scatter_add(grad_out, idx, weight, grad_points, b, c, m, (size_t)n * 3, 3, overwrite, (cudaStream_t)stream);
+  if (overwrite) {
+    cudaError_t e = cudaMemsetAsync(grad_points, 0, (size_t)b * c * m * sizeof(float), (cudaStream_t)stream);
+    if (e != cudaSuccess) return (int)e;
+  }
   const size_t total = (size_t)b * c * n;
   size_t grid = (total + 255) / 256;
   if (grid > (size_t)num_sms() * 32) grid = (size_t)num_sms() * 32;
   interp_bwd_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(grad_out, idx, weight, grad_points, c, m, (size_t)n, total);
   count_launch();
   return finish_launch();
+}
+
+extern "C" int gb_three_interp_bwd(const float *grad_out, const int *idx, const float *weight, float *grad_points, int b, int c, int n,
+                                   int m, gb_stream_t stream) {
+  return interp_bwd_impl(grad_out, idx, weight, grad_points, b, c, n, m, 0, stream);
+}
+
+extern "C" int gb_three_interp_bwd_set(const float *grad_out, const int *idx, const float *weight, float *grad_points, int b, int c,
+                                       int n, int m, gb_stream_t stream) {
+  return interp_bwd_impl(grad_out, idx, weight, grad_points, b, c, n, m, 1, stream);
 }

@@ -11,9 +11,302 @@
 // Semantics kept bit for bit: candidates in ascending index; hit iff d2 < radius*radius (fp32, strict),
 // for the cylinder additionally hmin < x_rot < hmax with (x_rot,y_rot,z_rot) = (p - q)^T R; the first hit pre-fills all
 // nsample slots; no hit leaves zeros.  Floating-point contraction is the one nvcc applies to the reference source.
+//
+// Large clouds (n >= 4096) first go through a UNIFORM CELL GRID built per call (grid_build_kernel: bounding box,
+// counting sort of the points by cell, all in one CTA's shared memory per scene).  A query then tests only the points of
+// the cells its search region can reach (a conservative box, see grid_query_kernel) -- in any order -- and marks hits in
+// a per-warp n-bit BITMAP in shared memory; reading the bitmap back in word order yields the first nsample hits in
+// ascending index, exactly the reference's sequential scan.  The per-candidate arithmetic is the same instruction
+// sequence as the full scan, and culling only removes points that cannot pass it, so results stay bit-exact.  When the
+// grid would not cull (radius comparable to the scene) the build kernel says so and the full-scan kernel runs instead.
+#include <float.h>
+
 #include "common.cuh"
 
 namespace gb {
+
+__device__ __forceinline__ bool ball_hit(float qx, float qy, float qz, float x, float y, float z, float radius2) {
+  return sqdist3(qx - x, qy - y, qz - z) < radius2;
+}
+// (x_rot, y_rot, z_rot) = (p - q)^T R with the reference's contraction (cylinder_query_gpu.cu:58-66, SASS-checked)
+__device__ __forceinline__ bool cyl_hit(const float (&r)[9], float qx, float qy, float qz, float x, float y, float z, float radius2,
+                                        float hmin, float hmax) {
+  const float dx = x - qx, dy = y - qy, dz = z - qz;
+  const float xr = __fmaf_rn(r[6], dz, __fmaf_rn(r[0], dx, __fmul_rn(r[3], dy)));
+  const float yr = __fmaf_rn(r[7], dz, __fmaf_rn(r[1], dx, __fmul_rn(r[4], dy)));
+  const float zr = __fmaf_rn(r[8], dz, __fmaf_rn(r[2], dx, __fmul_rn(r[5], dy)));
+  const float d2 = __fmaf_rn(yr, yr, __fmul_rn(zr, zr));
+  return (d2 < radius2) && (xr > hmin) && (xr < hmax);
+}
+
+// ---- uniform cell grid ------------------------------------------------------------------------------------------------
+constexpr int kGridMaxCells = 4096;
+constexpr int kGridMaxDim = 32;
+constexpr int kGridThreads = 1024;
+constexpr int kGridQueryWarps = 8;
+
+struct __align__(16) GridHeader {
+  float ox, oy, oz, inv;      // cell = clamp(floor((p - o) * inv))
+  int gx, gy, gz, use_grid;   // use_grid = 0: the grid would not cull, run the full scan instead
+  float maxabs, pad0, pad1, pad2;
+};
+
+// Monotone in x (fp32 subtract, multiply by a non-negative constant, floor, clamp), so every point with
+// lo <= x <= hi lands in a cell between cell(lo) and cell(hi).  NaN -> cell 0, +-inf -> the border cells.
+__device__ __forceinline__ int grid_cell(float x, float o, float inv, int g) {
+  return min(g - 1, max(0, __float2int_rd(__fmul_rn(__fsub_rn(x, o), inv))));
+}
+
+// grid b, kGridThreads threads.  xyz [b,n,3] -> sorted [b,n] (x, y, z, original index as int bits) grouped by cell,
+// cell_start [b, kGridMaxCells + 1], hdr [b].  reach = radius of a sphere around the query that contains the search region.
+__global__ void __launch_bounds__(kGridThreads) grid_build_kernel(const float *__restrict__ xyz, int n, float reach, int force,
+                                                                  float cell_frac,
+                                                                  float4 *__restrict__ sorted, int *__restrict__ cell_start,
+                                                                  GridHeader *__restrict__ hdr) {
+  __shared__ int s_cnt[kGridMaxCells];
+  __shared__ float s_red[32][6];
+  __shared__ int s_wsum[32];
+  __shared__ GridHeader s_h;
+  const int scene = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  xyz += (size_t)scene * n * 3;
+  sorted += (size_t)scene * n;
+  cell_start += (size_t)scene * (kGridMaxCells + 1);
+
+  // 1. bounding box of the finite coordinates
+  float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  for (int i = tid; i < n; i += kGridThreads) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const float v = __ldg(xyz + 3 * (size_t)i + d);
+      if (fabsf(v) <= FLT_MAX) lo[d] = fminf(lo[d], v), hi[d] = fmaxf(hi[d], v);
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[d] = fminf(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
+      hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
+    }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) s_red[warp][d] = lo[d], s_red[warp][3 + d] = hi[d];
+  }
+  for (int i = tid; i < kGridMaxCells; i += kGridThreads) s_cnt[i] = 0;
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < kGridThreads / 32; ++w) {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) lo[d] = fminf(lo[d], s_red[w][d]), hi[d] = fmaxf(hi[d], s_red[w][3 + d]);
+    }
+    float ext[3], maxabs = 0.f, emax = 0.f;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      if (lo[d] > hi[d]) lo[d] = hi[d] = 0.f;  // no finite coordinate at all
+      ext[d] = hi[d] - lo[d];
+      emax = fmaxf(emax, ext[d]);
+      maxabs = fmaxf(maxabs, fmaxf(fabsf(lo[d]), fabsf(hi[d])));
+    }
+    GridHeader h;
+    h.ox = lo[0], h.oy = lo[1], h.oz = lo[2];
+    h.maxabs = maxabs, h.pad0 = h.pad1 = h.pad2 = 0.f;
+    // cell edge = cell_frac x the reach of a query (its box then spans <= 2 / cell_frac + 1 cells per axis), >= extent / 32,
+    // <= 4096 cells in total
+    const float E = __fmaf_rn(reach, 1.0001f, 1e-5f * maxabs);
+    float s = fmaxf(E * cell_frac, emax / kGridMaxDim);
+    h.gx = h.gy = h.gz = 1, h.inv = 0.f;
+    if (s > 0.f && s <= FLT_MAX) {
+      for (;;) {
+        h.gx = min(kGridMaxDim, (int)(ext[0] / s) + 1), h.gy = min(kGridMaxDim, (int)(ext[1] / s) + 1);
+        h.gz = min(kGridMaxDim, (int)(ext[2] / s) + 1);
+        if (h.gx * h.gy * h.gz <= kGridMaxCells) break;
+        s *= 1.25f;
+      }
+      h.inv = 1.0f / s;
+    }
+    // share of the cloud's cells one query box touches; the grid pays off when that is small
+    const float span = s > 0.f && s <= FLT_MAX ? 2.f * E / s + 1.f : 1.f;
+    const float frac = fminf(1.f, span / h.gx) * fminf(1.f, span / h.gy) * fminf(1.f, span / h.gz);
+    h.use_grid = (force || frac <= 0.3f) ? 1 : 0;
+    s_h = h;
+    hdr[scene] = h;
+  }
+  __syncthreads();
+  const GridHeader h = s_h;
+  if (!h.use_grid) return;
+  const int ncells = h.gx * h.gy * h.gz;
+
+  // 2. histogram
+  for (int i = tid; i < n; i += kGridThreads) {
+    const float x = __ldg(xyz + 3 * (size_t)i), y = __ldg(xyz + 3 * (size_t)i + 1), z = __ldg(xyz + 3 * (size_t)i + 2);
+    const int c = (grid_cell(z, h.oz, h.inv, h.gz) * h.gy + grid_cell(y, h.oy, h.inv, h.gy)) * h.gx + grid_cell(x, h.ox, h.inv, h.gx);
+    atomicAdd(&s_cnt[c], 1);
+  }
+  __syncthreads();
+  // 3. exclusive scan over the cells (4 consecutive cells per thread)
+  constexpr int kPer = kGridMaxCells / kGridThreads;
+  int cnt[kPer], local = 0;
+#pragma unroll
+  for (int e = 0; e < kPer; ++e) {
+    const int c = tid * kPer + e;
+    cnt[e] = c < ncells ? s_cnt[c] : 0;
+    local += cnt[e];
+  }
+  int incl = local;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int o = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += o;
+  }
+  if (lane == 31) s_wsum[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    const int w = s_wsum[lane];
+    int wi = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int o = __shfl_up_sync(0xffffffffu, wi, d);
+      if (lane >= d) wi += o;
+    }
+    s_wsum[lane] = wi - w;
+  }
+  __syncthreads();
+  int run = s_wsum[warp] + incl - local;
+#pragma unroll
+  for (int e = 0; e < kPer; ++e) {
+    const int c = tid * kPer + e;
+    if (c < ncells) {
+      s_cnt[c] = run;  // becomes the scatter cursor
+      cell_start[c] = run;
+    }
+    run += cnt[e];
+  }
+  if (tid == 0) cell_start[ncells] = n;
+  __syncthreads();
+  // 4. scatter (order inside a cell is irrelevant: the bitmap restores index order)
+  for (int i = tid; i < n; i += kGridThreads) {
+    const float x = __ldg(xyz + 3 * (size_t)i), y = __ldg(xyz + 3 * (size_t)i + 1), z = __ldg(xyz + 3 * (size_t)i + 2);
+    const int c = (grid_cell(z, h.oz, h.inv, h.gz) * h.gy + grid_cell(y, h.oy, h.inv, h.gy)) * h.gx + grid_cell(x, h.ox, h.inv, h.gx);
+    const int pos = atomicAdd(&s_cnt[c], 1);
+    sorted[pos] = make_float4(x, y, z, __int_as_float(i));
+  }
+}
+
+// grid (ceil(m / 8), b), 8 warps, one WARP per query; dynamic smem 8 * words uint32 (words = ceil(n / 32)).
+// Search region -> conservative box.  Ball: the cube of half-edge r around q.  Cylinder with R orthonormal to within err:
+// p - q = R u with u = (x_rot, y_rot, z_rot), hmin < u0 < hmax, |(u1, u2)| < r, so along world axis i the offset lies in
+// [min(R_i0 hmin, R_i0 hmax) - r |(R_i1, R_i2)|, max(R_i0 hmin, R_i0 hmax) + r |(R_i1, R_i2)|] (the cylinder's own
+// bounding box, much tighter than its bounding sphere); a rotation further than 1e-3 from orthonormal searches the
+// whole grid.  Every bound is widened by reach * (1e-4 + 4 err) + 1e-5 * (largest coordinate magnitude), orders of
+// magnitude above the fp32 rounding of the test (a few ulp of the coordinates), so no point that passes it is culled.
+template <bool CYL>
+__global__ void __launch_bounds__(kGridQueryWarps * 32, 5) grid_query_kernel(const float *__restrict__ new_xyz, const float4 *__restrict__ sorted,
+                                                                         const int *__restrict__ cell_start,
+                                                                         const GridHeader *__restrict__ hdr, const float *__restrict__ rot,
+                                                                         int *__restrict__ idx, int n, int m, float radius, float radius2,
+                                                                         float reach, float hmin, float hmax, int nsample, int words) {
+  extern __shared__ unsigned s_bm[];
+  const int scene = blockIdx.y;
+  const GridHeader h = hdr[scene];
+  if (!h.use_grid) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned *bm = s_bm + (size_t)warp * words;
+  for (int i = lane; i < words; i += 32) bm[i] = 0u;
+  const int j = blockIdx.x * kGridQueryWarps + warp;
+  if (j >= m) return;
+  __syncwarp();
+  sorted += (size_t)scene * n;
+  cell_start += (size_t)scene * (kGridMaxCells + 1);
+  const size_t qi = (size_t)scene * m + j;
+  const float qx = __ldg(new_xyz + qi * 3), qy = __ldg(new_xyz + qi * 3 + 1), qz = __ldg(new_xyz + qi * 3 + 2);
+  float r[9];
+  float grow = 1e-4f;
+  bool full = false;
+  if (CYL) {
+#pragma unroll
+    for (int e = 0; e < 9; ++e) r[e] = __ldg(rot + qi * 9 + e);
+    // columns of R are the axes the offsets are projected on
+    const float c00 = r[0] * r[0] + r[3] * r[3] + r[6] * r[6], c11 = r[1] * r[1] + r[4] * r[4] + r[7] * r[7];
+    const float c22 = r[2] * r[2] + r[5] * r[5] + r[8] * r[8], c01 = r[0] * r[1] + r[3] * r[4] + r[6] * r[7];
+    const float c02 = r[0] * r[2] + r[3] * r[5] + r[6] * r[8], c12 = r[1] * r[2] + r[4] * r[5] + r[7] * r[8];
+    const float err = fmaxf(fmaxf(fmaxf(fabsf(c00 - 1.f), fabsf(c11 - 1.f)), fmaxf(fabsf(c22 - 1.f), fabsf(c01))), fmaxf(fabsf(c02), fabsf(c12)));
+    full = !(err < 1e-3f);  // also catches NaN
+    grow += 4.f * err;
+  }
+  const float pad = __fmaf_rn(reach, grow, 1e-5f * fmaxf(fmaxf(h.maxabs, fabsf(qx)), fmaxf(fabsf(qy), fabsf(qz))));
+  float blo[3], bhi[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    if (CYL) {
+      const float a0 = r[3 * i] * hmin, a1 = r[3 * i] * hmax;
+      const float rr = radius * sqrtf(r[3 * i + 1] * r[3 * i + 1] + r[3 * i + 2] * r[3 * i + 2]);
+      blo[i] = fminf(a0, a1) - rr - pad, bhi[i] = fmaxf(a0, a1) + rr + pad;
+    } else {
+      blo[i] = -radius - pad, bhi[i] = radius + pad;
+    }
+  }
+  int x0 = 0, x1 = h.gx - 1, y0 = 0, y1 = h.gy - 1, z0 = 0, z1 = h.gz - 1;
+  if (!full && pad <= FLT_MAX) {
+    x0 = grid_cell(qx + blo[0], h.ox, h.inv, h.gx), x1 = grid_cell(qx + bhi[0], h.ox, h.inv, h.gx);
+    y0 = grid_cell(qy + blo[1], h.oy, h.inv, h.gy), y1 = grid_cell(qy + bhi[1], h.oy, h.inv, h.gy);
+    z0 = grid_cell(qz + blo[2], h.oz, h.inv, h.gz), z1 = grid_cell(qz + bhi[2], h.oz, h.inv, h.gz);
+  }
+
+  // ---- candidates: the cells of a (z, y) row are contiguous in the sorted array ----
+  for (int cz = z0; cz <= z1; ++cz) {
+    for (int cy = y0; cy <= y1; ++cy) {
+      const int row = (cz * h.gy + cy) * h.gx;
+      const int s0 = __ldg(cell_start + row + x0), s1 = __ldg(cell_start + row + x1 + 1);
+      for (int i = s0 + lane; i < s1; i += 64) {
+        const float4 p0 = __ldg(sorted + i);
+        const bool two = i + 32 < s1;
+        const float4 p1 = two ? __ldg(sorted + i + 32) : p0;
+        const bool h0 = CYL ? cyl_hit(r, qx, qy, qz, p0.x, p0.y, p0.z, radius2, hmin, hmax) : ball_hit(qx, qy, qz, p0.x, p0.y, p0.z, radius2);
+        const bool h1 = two && (CYL ? cyl_hit(r, qx, qy, qz, p1.x, p1.y, p1.z, radius2, hmin, hmax) : ball_hit(qx, qy, qz, p1.x, p1.y, p1.z, radius2));
+        if (h0) {
+          const int k = __float_as_int(p0.w);
+          atomicOr(&bm[k >> 5], 1u << (k & 31));
+        }
+        if (h1) {
+          const int k = __float_as_int(p1.w);
+          atomicOr(&bm[k >> 5], 1u << (k & 31));
+        }
+      }
+    }
+  }
+  __syncwarp();
+
+  // ---- read the bitmap back in index order: first nsample hits, the rest padded with the first hit ----
+  int *out = idx + qi * (size_t)nsample;
+  int cnt = 0, first = 0;
+  for (int wb = 0; wb < words && cnt < nsample; wb += 32) {
+    unsigned w = wb + lane < words ? bm[wb + lane] : 0u;
+    const unsigned any = __ballot_sync(0xffffffffu, w != 0u);
+    if (!any) continue;
+    const int pc = __popc(w);
+    int incl = pc;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int o = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += o;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (cnt == 0) {
+      const int l0 = __ffs(any) - 1;
+      const unsigned w0 = __shfl_sync(0xffffffffu, w, l0);
+      first = (wb + l0) * 32 + __ffs(w0) - 1;
+    }
+    int pos = cnt + incl - pc;
+    while (w && pos < nsample) {
+      const int bit = __ffs(w) - 1;
+      out[pos++] = (wb + lane) * 32 + bit;
+      w &= w - 1;
+    }
+    cnt += total;
+  }
+  for (int sl = min(cnt, nsample) + lane; sl < nsample; sl += 32) out[sl] = first;
+}
 
 constexpr int kQueryWarps = 8;
 constexpr int kQueryTile = 2016;  // points per shared-memory tile (23.6 KB, multiple of 32), two buffers fit the 48 KB static limit
@@ -22,11 +315,12 @@ template <bool CYL, int QPW>
 __global__ void __launch_bounds__(kQueryWarps * 32) query_kernel(const float *__restrict__ new_xyz, const float *__restrict__ xyz,
                                                                  const float *__restrict__ rot, int *__restrict__ idx, int n,
                                                                  int m, float radius2, float hmin, float hmax, int nsample,
-                                                                 int use_bulk) {
+                                                                 int use_bulk, const GridHeader *__restrict__ hdr) {
   __shared__ __align__(128) float tile[2][kQueryTile * 3];
   __shared__ uint64_t full[2];
 
   const int scene = blockIdx.y;
+  if (hdr && hdr[scene].use_grid) return;  // this scene was answered by grid_query_kernel
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   xyz += (size_t)scene * n * 3;
   const int q0 = (blockIdx.x * kQueryWarps + warp) * QPW;  // first query of this warp
@@ -96,18 +390,8 @@ __global__ void __launch_bounds__(kQueryWarps * 32) query_kernel(const float *__
 #pragma unroll
         for (int q = 0; q < QPW; ++q) {
           if (cnt[q] < nsample) {  // warp uniform
-            bool hit;
-            if (CYL) {
-              const float dx = x - qx[q], dy = y - qy[q], dz = z - qz[q];
-              const float xr = __fmaf_rn(r[q][6], dz, __fmaf_rn(r[q][0], dx, __fmul_rn(r[q][3], dy)));
-              const float yr = __fmaf_rn(r[q][7], dz, __fmaf_rn(r[q][1], dx, __fmul_rn(r[q][4], dy)));
-              const float zr = __fmaf_rn(r[q][8], dz, __fmaf_rn(r[q][2], dx, __fmul_rn(r[q][5], dy)));
-              const float d2 = __fmaf_rn(yr, yr, __fmul_rn(zr, zr));
-              hit = valid && (d2 < radius2) && (xr > hmin) && (xr < hmax);
-            } else {
-              const float d2 = sqdist3(qx[q] - x, qy[q] - y, qz[q] - z);
-              hit = valid && (d2 < radius2);
-            }
+            const bool hit = valid && (CYL ? cyl_hit(r[q], qx[q], qy[q], qz[q], x, y, z, radius2, hmin, hmax)
+                                           : ball_hit(qx[q], qy[q], qz[q], x, y, z, radius2));
             const unsigned mask = __ballot_sync(0xffffffffu, hit);
             if (mask) {
               if (cnt[q] == 0) first[q] = base_k + base + __ffs(mask) - 1;
@@ -149,6 +433,42 @@ static int launch_query(const float *new_xyz, const float *xyz, const float *rot
   if (b == 0 || m == 0) return 0;
   const float radius2 = radius * radius;  // fp32 product, as ball_query_gpu.cu:22
   const int use_bulk = (n % 4 == 0) && (((uintptr_t)xyz & 15u) == 0);
+  if (b > 65535) return (int)cudaErrorInvalidValue;
+
+  // ---- cell-grid path for large clouds; the build kernel decides per scene whether the grid culls enough ----
+  GridHeader *hdr = nullptr;
+  void *scratch = nullptr;
+  const int words = (n + 31) / 32;
+  if (g_tuning.query_mode != 1 && (n >= 4096 || g_tuning.query_mode == 2) && (size_t)words * kGridQueryWarps * 4 <= 96u * 1024u) {
+    const size_t sorted_bytes = (size_t)b * n * sizeof(float4);
+    const size_t cells_bytes = (((size_t)b * (kGridMaxCells + 1) * sizeof(int)) + 15) & ~(size_t)15;
+    cudaError_t e = scratch_alloc(&scratch, sorted_bytes + cells_bytes + (size_t)b * sizeof(GridHeader), s);
+    if (e != cudaSuccess) return (int)e;
+    float4 *sorted = reinterpret_cast<float4 *>(scratch);
+    int *cell_start = reinterpret_cast<int *>(reinterpret_cast<unsigned char *>(scratch) + sorted_bytes);
+    hdr = reinterpret_cast<GridHeader *>(reinterpret_cast<unsigned char *>(scratch) + sorted_bytes + cells_bytes);
+    // radius of a sphere around the query that contains the search region (rounded up)
+    double reach = fabs((double)radius);
+    if (CYL) {
+      const double hm = fmax(fabs((double)hmin), fabs((double)hmax));
+      reach = sqrt(reach * reach + hm * hm);
+    }
+    const float reachf = (float)(reach * (1.0 + 1e-6));
+    const float cell_frac = g_tuning.grid_cell_pct > 0 ? 0.01f * g_tuning.grid_cell_pct : 0.5f;
+    grid_build_kernel<<<b, kGridThreads, 0, s>>>(xyz, n, reachf, g_tuning.query_mode == 2 ? 1 : 0, cell_frac, sorted, cell_start, hdr);
+    count_launch();
+    const size_t smem = (size_t)words * kGridQueryWarps * sizeof(unsigned);
+    auto kern = grid_query_kernel<CYL>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      cudaFreeAsync(scratch, s);
+      return (int)e;
+    }
+    kern<<<dim3((m + kGridQueryWarps - 1) / kGridQueryWarps, b), kGridQueryWarps * 32, smem, s>>>(new_xyz, sorted, cell_start, hdr, rot, idx, n, m,
+                                                                                                 fabsf(radius), radius2, reachf, hmin, hmax, nsample,
+                                                                                                 words);
+    count_launch();
+  }
   int qpw = g_tuning.query_qpw;
   if (qpw != 1 && qpw != 2 && qpw != 4) {
     const long warps = (long)b * m;
@@ -156,14 +476,15 @@ static int launch_query(const float *new_xyz, const float *xyz, const float *rot
   }
   const int per_cta = kQueryWarps * qpw;
   dim3 grid((m + per_cta - 1) / per_cta, b);
-  if (grid.y > 65535) return (int)cudaErrorInvalidValue;
   switch (qpw) {
-    case 4: query_kernel<CYL, 4><<<grid, kQueryWarps * 32, 0, s>>>(new_xyz, xyz, rot, idx, n, m, radius2, hmin, hmax, nsample, use_bulk); break;
-    case 2: query_kernel<CYL, 2><<<grid, kQueryWarps * 32, 0, s>>>(new_xyz, xyz, rot, idx, n, m, radius2, hmin, hmax, nsample, use_bulk); break;
-    default: query_kernel<CYL, 1><<<grid, kQueryWarps * 32, 0, s>>>(new_xyz, xyz, rot, idx, n, m, radius2, hmin, hmax, nsample, use_bulk); break;
+    case 4: query_kernel<CYL, 4><<<grid, kQueryWarps * 32, 0, s>>>(new_xyz, xyz, rot, idx, n, m, radius2, hmin, hmax, nsample, use_bulk, hdr); break;
+    case 2: query_kernel<CYL, 2><<<grid, kQueryWarps * 32, 0, s>>>(new_xyz, xyz, rot, idx, n, m, radius2, hmin, hmax, nsample, use_bulk, hdr); break;
+    default: query_kernel<CYL, 1><<<grid, kQueryWarps * 32, 0, s>>>(new_xyz, xyz, rot, idx, n, m, radius2, hmin, hmax, nsample, use_bulk, hdr); break;
   }
   count_launch();
-  return finish_launch();
+  const int rc = finish_launch();
+  if (scratch) cudaFreeAsync(scratch, s);
+  return rc;
 }
 
 }  // namespace gb

@@ -1,0 +1,444 @@
+// scatter.cu -- atomic-free segmented scatter-add, the backward of grouping_operation and of three_interpolate.
+//
+// Replaces group_points_grad_kernel (PointNet/_ext_src/src/group_points_gpu.cu:69-90), group_points_grad_kernel_fast
+// (pointnet2_batch/src/group_points_gpu.cu:9-22), three_interpolate_grad_kernel (interpolate_gpu.cu:121-148) and
+// three_interpolate_grad_kernel_fast (pointnet2_batch/src/interpolate_gpu.cu:127-149): one float atomicAdd per element
+// (group) or three (interpolate) into global memory -- the L2 atomic units retire about one lane per SM per cycle, which
+// is what bounds the reference.
+//
+// Both ops are   grad[b,c,key[b,e]] += src[b,c,e / DIV] * (w[b,e])   with DIV = 1 (group) or 3 (interpolate): the
+// targets depend on e only, not on the channel.  So:
+//   pass 1 (once per call, shared by all channels): every tile of T consecutive entries is counting-sorted by target in
+//     shared memory; the output is one packed word per entry, (tile-local entry << 16) | target, in target order
+//     (+ the weights in the same order for the interpolate backward);
+//   pass 2: a CTA owns CC channels of one scene with a [n][CC] fp32 accumulator in shared memory.  Tiles of the CC source
+//     rows stream in through the TMA engine (cp.async.bulk + mbarrier, up to 4 stages); each warp owns 64 consecutive
+//     sorted entries of the tile, one per lane per step: runs of equal targets are summed with a segmented warp
+//     reduction whose depth adapts to the longest run in the step (none when all 32 targets differ), and the head of
+//     each run does a PLAIN vector read-modify-write of the accumulator -- inside a tile a target belongs to one warp,
+//     except for the run that crosses a warp's boundary, whose two owners use shared-memory atomics (<= 2 targets per
+//     warp per tile).  Tiles are separated by one __syncthreads.  Rows are written once, coalesced.
+// HBM traffic is the algorithmic minimum (src read once, grad written once); the sort output (4-8 B per entry) is re-read
+// from L2 once per channel chunk.
+#include "common.cuh"
+
+namespace gb {
+
+constexpr int kSegTileStride = 2048;  // words of sort output per tile (tiles are padded to this)
+constexpr int kSegSortThreads = 512;
+constexpr int kSegThreads = 1024;  // 32 warps x 64 entries = one tile
+constexpr int kSegMaxStages = 4;
+constexpr unsigned kSegInvalid = 0xFFFFFFFFu;  // target 0xFFFF: dropped
+
+// entries per tile: DIV = 3 keeps tiles on point boundaries and the TMA row pieces 16-byte multiples (680 * 4 B)
+__host__ __device__ constexpr int seg_tile(int div) { return div == 3 ? 2040 : 2048; }
+
+// grid (tiles, b); dynamic smem (n + 32) ints + 2048 u16.  idx [b, per] -> packed [b, tiles, 2048] (+ wsorted, same
+// layout, one spare tile per scene) and bnd [b, tiles + 1, 64]
+template <bool WEIGHTED>
+__global__ void __launch_bounds__(kSegSortThreads) seg_sort_kernel(const int *__restrict__ idx, const float *__restrict__ weight,
+                                                                   int per, int n, int T, unsigned *__restrict__ packed,
+                                                                   float *__restrict__ wsorted, unsigned char *__restrict__ bnd) {
+  extern __shared__ int s_bins[];  // [n] counts -> running cursors, then [32] warp partials, then [2048] sorted keys (u16)
+  int *wsum = s_bins + n;
+  unsigned short *skeys = reinterpret_cast<unsigned short *>(wsum + 32);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const size_t ibase = (size_t)blockIdx.y * per + (size_t)blockIdx.x * T;
+  const size_t obase = ((size_t)blockIdx.y * (gridDim.x + 1) + blockIdx.x) * kSegTileStride;  // one spare tile per scene
+  const int tc = min(T, per - (int)blockIdx.x * T);
+  for (int i = tid; i < n; i += kSegSortThreads) s_bins[i] = 0;
+  __syncthreads();
+  constexpr int R = kSegTileStride / kSegSortThreads;
+  int key[R];
+  float wv[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int e = r * kSegSortThreads + tid;
+    int k = -1;
+    wv[r] = 0.f;
+    if (e < tc) {
+      k = __ldg(idx + ibase + e);
+      if (WEIGHTED) wv[r] = __ldg(weight + ibase + e);
+      if ((unsigned)k >= (unsigned)n) k = -1;  // out-of-range targets are dropped (undefined behaviour in the reference)
+      else atomicAdd(&s_bins[k], 1);
+    }
+    key[r] = k;
+  }
+  __syncthreads();
+  // exclusive scan of s_bins[0..n): each thread owns a contiguous chunk
+  const int chunk = (n + kSegSortThreads - 1) / kSegSortThreads;
+  const int c0 = min(n, tid * chunk), c1 = min(n, c0 + chunk);
+  int local = 0;
+  for (int i = c0; i < c1; ++i) local += s_bins[i];
+  int incl = local;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int o = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += o;
+  }
+  if (lane == 31) wsum[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    const int w = lane < kSegSortThreads / 32 ? wsum[lane] : 0;
+    int wi = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int o = __shfl_up_sync(0xffffffffu, wi, d);
+      if (lane >= d) wi += o;
+    }
+    wsum[lane] = wi - w;  // exclusive prefix of the warp totals (16 warps)
+    if (lane == kSegSortThreads / 32 - 1) wsum[31] = wi;  // number of valid entries
+  }
+  __syncthreads();
+  int run = wsum[warp] + incl - local;
+  const int total = wsum[31];
+  for (int i = c0; i < c1; ++i) {
+    const int cnt = s_bins[i];
+    s_bins[i] = run;
+    run += cnt;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int e = r * kSegSortThreads + tid;
+    if (key[r] >= 0) {
+      const int pos = atomicAdd(&s_bins[key[r]], 1);
+      packed[obase + pos] = ((unsigned)e << 16) | (unsigned)key[r];
+      skeys[pos] = (unsigned short)key[r];
+      if (WEIGHTED) wsorted[obase + pos] = wv[r];
+    }
+  }
+  for (int e = total + tid; e < kSegTileStride; e += kSegSortThreads) {
+    packed[obase + e] = kSegInvalid;
+    skeys[e] = 0xFFFFu;
+    if (WEIGHTED) wsorted[obase + e] = 0.f;
+  }
+  __syncthreads();
+  // boundary bytes for the accumulate kernel: boundary w (between its warps w-1 and w) moves from entry 64 w to the next
+  // run head within 32 entries (low 6 bits = shift); bit 7 = there is none, the run stays split (shared target)
+  if (tid <= 32) {  // boundaries 0 and 32 are the tile's ends: always 0
+    unsigned char code = 0;
+    const int p = tid * 64;
+    if (tid > 0 && tid < 32 && skeys[p] != 0xFFFFu && skeys[p] == skeys[p - 1]) {
+      int sh = 1;
+      while (sh <= 32 && skeys[p + sh] == skeys[p]) ++sh;  // p + 32 < 2048
+      code = sh <= 32 ? (unsigned char)sh : (unsigned char)0x80u;
+    }
+    bnd[((size_t)blockIdx.y * (gridDim.x + 1) + blockIdx.x) * 64 + tid] = code;
+  }
+}
+
+template <int CC>
+__device__ __forceinline__ void seg_rmw(float *a, const float (&v)[CC]) {
+  if (CC % 4 == 0) {
+    float4 x[CC / 4 > 0 ? CC / 4 : 1];
+#pragma unroll
+    for (int q = 0; q < CC / 4; ++q) x[q] = reinterpret_cast<float4 *>(a)[q];
+#pragma unroll
+    for (int q = 0; q < CC / 4; ++q) {
+      x[q].x += v[4 * q], x[q].y += v[4 * q + 1], x[q].z += v[4 * q + 2], x[q].w += v[4 * q + 3];
+      reinterpret_cast<float4 *>(a)[q] = x[q];
+    }
+  } else if (CC == 2) {
+    float2 x = *reinterpret_cast<float2 *>(a);
+    x.x += v[0], x.y += v[1];
+    *reinterpret_cast<float2 *>(a) = x;
+  } else {
+#pragma unroll
+    for (int cc = 0; cc < CC; ++cc) a[cc] += v[cc];
+  }
+}
+
+// One step = 32 sorted entries at fixed positions, one per lane.  `mine`: the entry belongs to this warp (see the boundary
+// bytes below); entries of other warps count as invalid.
+//   * all 32 targets differ (the common case for large n): every lane does a plain vector read-modify-write;
+//   * short runs of equal targets (rank of a lane inside its run <= 3): rank-by-rank passes, each conflict free;
+//   * longer runs (a padded neighbourhood: up to nsample copies of one index): segmented warp reduction whose depth
+//     adapts to the longest run, then the run heads update.
+// Only when a run longer than 32 entries straddles this warp's boundary (`shared` targets) do its two owners fall back
+// to shared-memory atomics for that one target.
+template <int CC, int DIV, bool WEIGHTED>
+__device__ __forceinline__ void seg_step(float *acc, const float *gt, int TP, unsigned pk, float w, bool mine, int lane, unsigned lemask,
+                                         bool any_shared, unsigned kshare0, unsigned kshare1) {
+  const unsigned k = mine ? (pk & 0xFFFFu) : 0xFFFFu;
+  const unsigned tp = pk >> 16;
+  const bool valid = k != 0xFFFFu;
+  const unsigned sp = DIV == 3 ? (tp * 43691u) >> 17 : tp;  // tp / 3, exact for tp < 2^16
+  float v[CC];
+#pragma unroll
+  for (int cc = 0; cc < CC; ++cc) {
+    v[cc] = valid ? gt[cc * TP + sp] : 0.f;
+    if (WEIGHTED) v[cc] = __fmul_rn(v[cc], w);  // the reference adds g * w_t (interpolate_gpu.cu:144-146)
+  }
+  float *a = acc + (size_t)k * CC;
+  const unsigned prev = __shfl_up_sync(0xffffffffu, k, 1);
+  const bool head = (lane == 0) || (prev != k);
+  const unsigned heads = __ballot_sync(0xffffffffu, head);
+  if (any_shared) {  // rare: reduce fully, heads of shared targets use atomics
+    const unsigned after = lane == 31 ? 0u : (heads >> (lane + 1));
+    const int run = after ? (__ffs(after) - 1) : (31 - lane);
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+#pragma unroll
+      for (int cc = 0; cc < CC; ++cc) {
+        const float other = __shfl_down_sync(0xffffffffu, v[cc], d);
+        if (d <= run) v[cc] += other;
+      }
+    }
+    if (head && valid) {
+      if (k == kshare0 || k == kshare1) {
+#pragma unroll
+        for (int cc = 0; cc < CC; ++cc) atomicAdd(a + cc, v[cc]);
+      } else {
+        seg_rmw<CC>(a, v);
+      }
+    }
+    return;
+  }
+  if (heads == 0xffffffffu) {
+    if (valid) seg_rmw<CC>(a, v);
+    return;
+  }
+  const int rank = lane - (31 - __clz(heads & lemask));  // position of this lane inside its run
+  const int maxrank = __reduce_max_sync(0xffffffffu, valid ? rank : 0);  // runs of masked / padding entries do not count
+  if (maxrank <= 3) {
+    for (int p = 0; p <= maxrank; ++p) {
+      if (rank == p && valid) seg_rmw<CC>(a, v);
+      __syncwarp();
+    }
+    return;
+  }
+  const unsigned after = lane == 31 ? 0u : (heads >> (lane + 1));
+  const int run = after ? (__ffs(after) - 1) : (31 - lane);  // followers of this lane inside its run
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    if (d > maxrank) break;
+#pragma unroll
+    for (int cc = 0; cc < CC; ++cc) {
+      const float other = __shfl_down_sync(0xffffffffu, v[cc], d);
+      if (d <= run) v[cc] += other;
+    }
+  }
+  if (head && valid) seg_rmw<CC>(a, v);
+}
+
+// grid b * chunks, kSegThreads threads.  src [b,c,per_src] (per_src = entries / DIV); packed/wsorted [b,tiles+1,2048]
+// (+32 words); bnd [b,tiles+1,64] boundary bytes; grad [b,c,n] (+= or =).  dynamic smem: stage[stages][CC][TP] | acc[n][CC].
+//
+// Warp w of the CTA owns the sorted entries [64 w + shift_w, 64 (w+1) + shift_{w+1}) of a tile: the sort kernel moved
+// every 64-entry boundary right to the next run head (shift <= 32), so no run of equal targets is split between two
+// warps and the accumulator needs no atomics.  Lanes sit on FIXED positions (three steps of 32 from 64 w; the third only
+// when shift_{w+1} > 0) and mask the entries they do not own.
+template <int CC, int DIV, bool WEIGHTED>
+__global__ void __launch_bounds__(kSegThreads, 1) seg_accum_kernel(const float *__restrict__ src, const unsigned *__restrict__ packed,
+                                                                   const float *__restrict__ wsorted,
+                                                                   const unsigned char *__restrict__ bnd, float *__restrict__ grad,
+                                                                   int c, int n, int per_src, int tiles, int chunks, int stages,
+                                                                   int bulk_ok, int overwrite) {
+  constexpr int T = seg_tile(DIV), TP = T / DIV;
+  extern __shared__ __align__(128) unsigned char s_raw[];
+  __shared__ uint64_t full[kSegMaxStages];
+  float *stage = reinterpret_cast<float *>(s_raw);
+  float *acc = stage + (size_t)stages * CC * TP;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned lemask = (2u << lane) - 1u;
+  const int scene = blockIdx.x / chunks, chunk = blockIdx.x - scene * chunks;
+  const int ch0 = chunk * CC;
+  const int nch = min(CC, c - ch0);
+  for (int i = tid; i < CC * n; i += kSegThreads) acc[i] = 0.f;
+  if (nch < CC)  // rows of missing channels stay zero
+    for (int i = tid; i < stages * CC * TP; i += kSegThreads) stage[i] = 0.f;
+  const float *g = src + ((size_t)scene * c + ch0) * per_src;
+  // sort output of this scene; one spare tile behind the last one keeps the prefetch below unconditional
+  const unsigned *pp = packed + (size_t)scene * (tiles + 1) * kSegTileStride + warp * 64 + lane;
+  const float *wp = WEIGHTED ? wsorted + (size_t)scene * (tiles + 1) * kSegTileStride + warp * 64 + lane : nullptr;
+  const unsigned char *bp = bnd + (size_t)scene * (tiles + 1) * 64 + warp;
+
+  auto issue = [&](int t, int sidx) {  // thread 0: bulk copies of tile t's CC row pieces into stage sidx
+    const int p0 = t * TP, pc = min(TP, per_src - p0);
+    float *dst = stage + (size_t)sidx * CC * TP;
+    mbar_arrive_expect_tx(&full[sidx], (uint32_t)pc * 4u * (uint32_t)nch);
+    for (int cc = 0; cc < nch; ++cc) bulk_g2s(dst + cc * TP, g + (size_t)cc * per_src + p0, (uint32_t)pc * 4u, &full[sidx]);
+  };
+  if (bulk_ok) {
+    if (tid == 0) {
+      for (int s = 0; s < stages; ++s) mbar_init(&full[s], 1);
+      fence_mbar_init();
+    }
+    fence_proxy_async();  // the zero fill above (generic proxy) is ordered before the bulk writes (async proxy)
+    __syncthreads();
+    if (tid == 0)
+      for (int t = 0; t < stages - 1 && t < tiles; ++t) issue(t, t);
+  } else {
+    __syncthreads();
+  }
+
+  // sort output of tile 0 (registers); the next tile's is fetched from L2 while the current one is processed
+  unsigned pk0 = pp[0], pk1 = pp[32], pk2 = pp[64];
+  float w0 = 0.f, w1 = 0.f, w2 = 0.f;
+  if (WEIGHTED) w0 = wp[0], w1 = wp[32], w2 = wp[64];
+  unsigned b0 = bp[0], b1 = bp[1];
+  int sidx = 0, issue_sidx = stages - 1;  // stage of tile t / of tile t + stages - 1
+  uint32_t parity = 0;
+  for (int t = 0; t < tiles; ++t) {
+    const unsigned c0 = pk0, c1 = pk1, c2 = pk2, cb0 = b0, cb1 = b1;
+    const float cw0 = w0, cw1 = w1, cw2 = w2;
+    pp += kSegTileStride, bp += 64;
+    pk0 = pp[0], pk1 = pp[32], pk2 = pp[64];
+    if (WEIGHTED) wp += kSegTileStride, w0 = wp[0], w1 = wp[32], w2 = wp[64];
+    b0 = bp[0], b1 = bp[1];
+    const float *gt = stage + (size_t)sidx * CC * TP;
+    if (bulk_ok) {
+      // the stage of tile t + stages - 1 was consumed by tile t - 1, which every thread has left (barrier below)
+      if (tid == 0 && t + stages - 1 < tiles) issue(t + stages - 1, issue_sidx);
+      mbar_wait(&full[sidx], parity);
+    } else {
+      const int p0 = t * TP, pc = min(TP, per_src - p0);
+      float *dst = stage + (size_t)sidx * CC * TP;
+      for (int cc = 0; cc < nch; ++cc)
+        for (int i = tid; i < pc; i += kSegThreads) dst[cc * TP + i] = __ldg(g + (size_t)cc * per_src + p0 + i);
+      __syncthreads();
+    }
+    // ownership: [64 w + shift0, 64 (w+1) + shift1)
+    const int shift0 = cb0 & 63u, shift1 = cb1 & 63u;
+    const bool any_shared = ((cb0 | cb1) & 0x80u) != 0u;
+    unsigned kshare0 = 0xFFFFu, kshare1 = 0xFFFFu;
+    if (any_shared) {  // a run of more than 32 entries straddles a boundary of this warp: its target is shared
+      const unsigned kf = __shfl_sync(0xffffffffu, c0 & 0xFFFFu, 0), kl = __shfl_sync(0xffffffffu, c1 & 0xFFFFu, 31);
+      if (cb0 & 0x80u) kshare0 = kf;
+      if (cb1 & 0x80u) kshare1 = kl;
+    }
+    seg_step<CC, DIV, WEIGHTED>(acc, gt, TP, c0, cw0, lane >= shift0, lane, lemask, any_shared, kshare0, kshare1);
+    __syncwarp();  // a run continuing into the next step updates the same accumulator
+    seg_step<CC, DIV, WEIGHTED>(acc, gt, TP, c1, cw1, true, lane, lemask, any_shared, kshare0, kshare1);
+    if (shift1) {
+      __syncwarp();
+      seg_step<CC, DIV, WEIGHTED>(acc, gt, TP, c2, cw2, lane < shift1, lane, lemask, any_shared, kshare0, kshare1);
+    }
+    __syncthreads();  // targets change owner between tiles; also releases the stage
+    if (++sidx == stages) sidx = 0, parity ^= 1u;
+    if (++issue_sidx == stages) issue_sidx = 0;
+  }
+  for (int cc = 0; cc < nch; ++cc) {
+    float *dst = grad + ((size_t)scene * c + ch0 + cc) * n;
+    if (overwrite) {
+      for (int i = tid; i < n; i += kSegThreads) dst[i] = acc[(size_t)i * CC + cc];
+    } else {  // the reference entry points accumulate into the caller's (zero-filled) tensor
+      int i = tid;
+      for (; i + 3 * kSegThreads < n; i += 4 * kSegThreads) {
+        const float d0 = dst[i], d1 = dst[i + kSegThreads], d2 = dst[i + 2 * kSegThreads], d3 = dst[i + 3 * kSegThreads];
+        dst[i] = d0 + acc[(size_t)i * CC + cc];
+        dst[i + kSegThreads] = d1 + acc[(size_t)(i + kSegThreads) * CC + cc];
+        dst[i + 2 * kSegThreads] = d2 + acc[(size_t)(i + 2 * kSegThreads) * CC + cc];
+        dst[i + 3 * kSegThreads] = d3 + acc[(size_t)(i + 3 * kSegThreads) * CC + cc];
+      }
+      for (; i < n; i += kSegThreads) dst[i] += acc[(size_t)i * CC + cc];
+    }
+  }
+}
+
+// stream-ordered scratch from the device's default pool; the pool is told once to keep freed memory instead of
+// returning it to the driver at every synchronisation (the default), which would make every call pay a fresh allocation
+cudaError_t scratch_alloc(void **p, size_t bytes, cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    int dev = 0;
+    cudaMemPool_t pool;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    configured = true;
+  }
+  return cudaMallocAsync(p, bytes, s);
+}
+
+constexpr size_t kSegSmemBudget = 227u * 1024u - 1024u;  // dynamic; the mbarriers are static
+
+template <int CC, int DIV, bool WEIGHTED>
+static int launch_seg_accum(const float *src, const unsigned *packed, const float *wsorted, const unsigned char *bnd, float *grad,
+                            int b, int c, int n, int per_src, int tiles, int bulk_ok, int overwrite, cudaStream_t s) {
+  constexpr int TP = seg_tile(DIV) / DIV;
+  const size_t acc_bytes = (size_t)CC * n * sizeof(float), stage_bytes = (size_t)CC * TP * sizeof(float);
+  int stages = (int)((kSegSmemBudget - acc_bytes) / stage_bytes);
+  stages = stages > kSegMaxStages ? kSegMaxStages : stages;
+  if (stages > tiles) stages = tiles < 1 ? 1 : tiles;
+  if (!bulk_ok) stages = 1;
+  const size_t smem = acc_bytes + stages * stage_bytes;
+  auto kern = seg_accum_kernel<CC, DIV, WEIGHTED>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  const int chunks = (c + CC - 1) / CC;
+  kern<<<(unsigned)(b * chunks), kSegThreads, smem, s>>>(src, packed, wsorted, bnd, grad, c, n, per_src, tiles, chunks, stages, bulk_ok,
+                                                         overwrite);
+  count_launch();
+  return finish_launch();
+}
+
+bool seg_scatter_supported(int b, int c, int n, size_t entries, int div) {
+  const int TP = seg_tile(div) / div;
+  return c >= 4 && n < 0xFFFF && ((size_t)n + 32) * sizeof(int) + 4096 <= 200u * 1024u &&
+         (size_t)n * sizeof(float) + 2 * (size_t)TP * sizeof(float) <= kSegSmemBudget && b <= 65535 && entries < (1u << 30) &&
+         (size_t)b * entries < (1u << 31);
+}
+
+// grad[b,c,key[b,e]] += src[b,c,e/div] * (weight ? weight[b,e] : 1); key/weight [b,entries]; src [b,c,entries/div].
+// Two shapes are instantiated: div = 1 without weights (group) and div = 3 with weights (interpolate).
+// overwrite != 0: grad is fully written (no zero fill needed) instead of accumulated into.
+int seg_scatter_add(const float *src, const int *key, const float *weight, float *grad, int b, int c, int n, size_t entries, int div,
+                    int overwrite, cudaStream_t s) {
+  if ((div != 1 && div != 3) || (div == 3) != (weight != nullptr)) return (int)cudaErrorInvalidValue;
+  const int T = seg_tile(div), TP = T / div;
+  const int per_src = (int)(entries / div);
+  const int tiles = (int)((entries + T - 1) / T);
+  // per scene one spare (never processed, only prefetched) tile, plus 32 words behind each array for the third-step read
+  const size_t words = (size_t)b * (tiles + 1) * kSegTileStride + 32;
+  unsigned *packed = nullptr;
+  cudaError_t e = scratch_alloc((void **)&packed, words * sizeof(unsigned) * (weight ? 2 : 1) + (size_t)b * (tiles + 1) * 64, s);
+  if (e != cudaSuccess) return (int)e;
+  float *wsorted = weight ? reinterpret_cast<float *>(packed + words) : nullptr;
+  unsigned char *bnd = reinterpret_cast<unsigned char *>(packed + words * (weight ? 2 : 1));
+  const size_t sort_smem = ((size_t)n + 32) * sizeof(int) + kSegTileStride * sizeof(unsigned short);
+  int rc;
+  if (weight) {
+    rc = (int)cudaFuncSetAttribute(seg_sort_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem);
+    if (!rc) seg_sort_kernel<true><<<dim3((unsigned)tiles, b), kSegSortThreads, sort_smem, s>>>(key, weight, (int)entries, n, T, packed, wsorted, bnd);
+  } else {
+    rc = (int)cudaFuncSetAttribute(seg_sort_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem);
+    if (!rc) seg_sort_kernel<false><<<dim3((unsigned)tiles, b), kSegSortThreads, sort_smem, s>>>(key, nullptr, (int)entries, n, T, packed, nullptr, bnd);
+  }
+  if (!rc) {
+    count_launch();
+    rc = finish_launch();
+  }
+  if (!rc) {
+    // channels per CTA: as many as fit beside two stages, but keep at least one CTA per SM
+    int CC = 8;
+    while (CC > 1 && ((size_t)CC * n * sizeof(float) + 2 * (size_t)CC * TP * sizeof(float) > kSegSmemBudget ||
+                      (long)b * ((c + CC - 1) / CC) < (long)num_sms()))
+      CC >>= 1;
+    if (g_tuning.scatter_cc == 1 || g_tuning.scatter_cc == 2 || g_tuning.scatter_cc == 4 || g_tuning.scatter_cc == 8) {
+      CC = g_tuning.scatter_cc;
+      while (CC > 1 && (size_t)CC * n * sizeof(float) + 2 * (size_t)CC * TP * sizeof(float) > kSegSmemBudget) CC >>= 1;
+    }
+    // bulk (TMA) row pieces need 16-byte aligned global addresses and sizes
+    const int bulk_ok = (per_src % 4 == 0) && (((uintptr_t)src & 15u) == 0);
+#define GB_SEG_CASE(CCV)                                                                                            \
+  case CCV:                                                                                                         \
+    rc = div == 3 ? launch_seg_accum<CCV, 3, true>(src, packed, wsorted, bnd, grad, b, c, n, per_src, tiles, bulk_ok, overwrite, s)  \
+                  : launch_seg_accum<CCV, 1, false>(src, packed, wsorted, bnd, grad, b, c, n, per_src, tiles, bulk_ok, overwrite, s); \
+    break;
+    switch (CC) {
+      GB_SEG_CASE(8)
+      GB_SEG_CASE(4)
+      GB_SEG_CASE(2)
+      default:
+        GB_SEG_CASE(1)
+    }
+#undef GB_SEG_CASE
+  }
+  cudaFreeAsync(packed, s);
+  return rc;
+}
+
+}  // namespace gb

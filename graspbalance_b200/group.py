@@ -70,8 +70,9 @@ class GroupingOperation(Function):
     def backward(ctx, grad_out):
         idx, N = ctx.for_backwards
         B, C, npoint, nsample = grad_out.size()
-        grad_features = torch.zeros([B, C, N], dtype=torch.float, device=grad_out.device)
-        pointnet2_cuda.group_points_grad_wrapper(B, C, N, npoint, nsample, grad_out.detach().contiguous(), idx, grad_features)
+        # group.py:83-85 zero-fills and accumulates; the _set entry writes every element, same values
+        grad_features = torch.empty([B, C, N], dtype=torch.float, device=grad_out.device)
+        pointnet2_cuda.group_points_grad_set(B, C, N, npoint, nsample, grad_out.detach().contiguous(), idx, grad_features)
         return grad_features, None
 
 

@@ -44,6 +44,14 @@ def group_points_grad_wrapper(b, c, n, npoints, nsample, grad_out, idx, grad_poi
     return 1
 
 
+def group_points_grad_set(b, c, n, npoints, nsample, grad_out, idx, grad_points):
+    """Not in the reference module: group_points_grad_wrapper into an UNINITIALISED grad_points (fully overwritten), used by
+    graspbalance_b200.group.GroupingOperation.backward to skip the zero fill of group.py:83 and its read-back."""
+    _chk(grad_out, "grad_out_tensor", _f32); _chk(idx, "idx_tensor", _i32); _chk(grad_points, "grad_points_tensor", _f32)
+    _lib.call("gb_group_bwd_set", grad_out, grad_out.data_ptr(), idx.data_ptr(), grad_points.data_ptr(), b, c, n, npoints, nsample)
+    return 1
+
+
 def gather_points_wrapper(b, c, n, npoints, points, idx, out):
     """sampling.cpp:9-18."""
     _chk(points, "points_tensor", _f32); _chk(idx, "idx_tensor", _i32); _chk(out, "out_tensor", _f32)
@@ -85,3 +93,10 @@ def three_interpolate_grad_wrapper(b, c, n, m, grad_out, idx, weight, grad_point
     _chk(grad_out, "grad_out_tensor", _f32); _chk(idx, "idx_tensor", _i32)
     _chk(weight, "weight_tensor", _f32); _chk(grad_points, "grad_points_tensor", _f32)
     _lib.call("gb_three_interp_bwd", grad_out, grad_out.data_ptr(), idx.data_ptr(), weight.data_ptr(), grad_points.data_ptr(), b, c, n, m)
+
+
+def three_interpolate_grad_set(b, c, n, m, grad_out, idx, weight, grad_points):
+    """Not in the reference module: three_interpolate_grad_wrapper into an UNINITIALISED grad_points (fully overwritten)."""
+    _chk(grad_out, "grad_out_tensor", _f32); _chk(idx, "idx_tensor", _i32)
+    _chk(weight, "weight_tensor", _f32); _chk(grad_points, "grad_points_tensor", _f32)
+    _lib.call("gb_three_interp_bwd_set", grad_out, grad_out.data_ptr(), idx.data_ptr(), weight.data_ptr(), grad_points.data_ptr(), b, c, n, m)

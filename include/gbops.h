@@ -78,6 +78,10 @@ GB_API int gb_group_fwd(const float *points, const int *idx, float *out, int b, 
  * ACCUMULATES into grad_points [b,c,n]. */
 GB_API int gb_group_bwd(const float *grad_out, const int *idx, float *grad_points, int b, int c, int n, int npoints,
                  int nsample, gb_stream_t stream);
+/* Same sum, but grad_points is fully OVERWRITTEN: what module A's group_points_grad (group_points.cpp:50-75) returns from
+ * its own torch::zeros output, without the zero fill and the read-back of an accumulating launch. */
+GB_API int gb_group_bwd_set(const float *grad_out, const int *idx, float *grad_points, int b, int c, int n, int npoints,
+                     int nsample, gb_stream_t stream);
 
 /* A: three_nn_kernel_wrapper (interpolate_gpu.cu:66-73); B: three_nn_kernel_launcher_fast (:62-81).
  * unknown [b,n,3], known [b,m,3] -> dist2 [b,n,3] f32 (SQUARED), idx [b,n,3] i32. */
@@ -93,6 +97,10 @@ GB_API int gb_three_interp_fwd(const float *points, const int *idx, const float 
  * ACCUMULATES into grad_points [b,c,m]. */
 GB_API int gb_three_interp_bwd(const float *grad_out, const int *idx, const float *weight, float *grad_points, int b, int c,
                         int n, int m, gb_stream_t stream);
+/* Same sum, grad_points fully OVERWRITTEN (module A's three_interpolate_grad, interpolate.cpp:76-104, zero-fills its own
+ * output). */
+GB_API int gb_three_interp_bwd_set(const float *grad_out, const int *idx, const float *weight, float *grad_points, int b, int c,
+                            int n, int m, gb_stream_t stream);
 
 /* C: knn_device (knn.cu:217-263) looped over the batch as knn.h:31-38 does.
  * ref [b,dim,nref], query [b,dim,nquery] (channel first) -> idx [b,k,nquery] int64, 1-BASED, ascending (dist, index).
@@ -118,6 +126,11 @@ GB_API int gb_collision_counts_host(const double *points, int np, const double *
  *   "fps_cluster"  0 = auto, else 1/2/4/8/16 CTAs per scene
  *   "fps_threads"  0 = auto, else 256/512/1024
  *   "group_split"  0 = auto, else output splits per (scene, channel chunk)
+ *   "group_mode"   bit 0: plain (not streaming) stores in group fwd; bit 1: generic fwd kernel; bit 2: atomic backward
+ *   "interp_mode"  bit 0: plain stores; bit 1: generic fwd kernel; bit 2: atomic backward
+ *   "query_qpw"    0 = auto, else 1/2/4 queries per warp in the full-scan query kernel
+ *   "query_mode"   0 = auto, 1 = full scan only, 2 = always build the cell grid
+ *   "scatter_cc"   0 = auto, else 1/2/4 channels per CTA in the sorted backward
  */
 GB_API int gb_set_tuning(const char *key, int value);
 GB_API int gb_get_tuning(const char *key, int *value);

@@ -56,13 +56,25 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "perf_vs_ref.json"))
     ap.add_argument("--sweep", action="store_true")
+    ap.add_argument("--sweep2", action="store_true", help="cell-grid edge and sorted-backward channel sweeps")
     ap.add_argument("--B", type=int, default=4)
+    ap.add_argument("--only", default="", help="regex: time only the ops whose name matches")
+    ap.add_argument("--iters", type=int, default=0, help="override the number of timed launches per op")
+    ap.add_argument("--no-ref", action="store_true", help="do not time the reference extensions")
     args = ap.parse_args()
+    import re
+    only = re.compile(args.only) if args.only else None
     rA, rB, rC = _load_ref("gbref_pointnet2_ext"), _load_ref("gbref_pointnet2_batch"), _load_ref("gbref_knn")
+    if args.no_ref:
+        rA = rB = rC = None
     B, N, m, ns = args.B, 20000, 1024, 64
     rows = []
 
     def add(name, mine, ref_a=None, ref_b=None, bytes_per_scene=None, scenes_n=B, **kw):
+        if only is not None and not only.search(name):
+            return
+        if args.iters:
+            kw["iters"] = args.iters
         t = timeit(mine, **kw)
         row = {"op": name, "us": round(t, 2), "us_per_scene": round(t / scenes_n, 2)}
         if bytes_per_scene:
@@ -172,7 +184,7 @@ def main():
         want = torch.empty((B, k, m), dtype=torch.int64, device=dev)
         rows_before = len(rows)
         add(f"knn R=20000 Q=1024 k={k}", lambda: knn_modules.knn_k(ref3, q3, k), None, None, bytes_per_scene=12 * (N + m) + 8 * k * m)
-        if rC is not None:
+        if rC is not None and len(rows) > rows_before:
             t = timeit(lambda: rC.knn(ref3, q3, want))
             rows[rows_before]["ref_c_us"] = round(t, 2)
             rows[rows_before]["speedup_vs_c"] = round(t / rows[rows_before]["us"], 2)
@@ -196,7 +208,7 @@ def main():
 
     if args.sweep:
         for C in (1, 2, 4, 8, 16):
-            for Tn in (512, 1024):
+            for Tn in (256, 512, 1024):
                 _lib.set_tuning("fps_cluster", C)
                 _lib.set_tuning("fps_threads", Tn)
                 try:
@@ -233,6 +245,33 @@ def main():
             rows.append({"op": f"sweep ball uniform qpw={q}", "us": round(t, 1)})
             print(json.dumps(rows[-1]), flush=True)
         _lib.set_tuning("query_qpw", 0)
+
+    if args.sweep2:
+        for pct in (100, 67, 50, 33, 25):
+            _lib.set_tuning("grid_cell_pct", pct)
+            for name, fn in (("ball r=.05", lambda: A.ball_query(new_xyz, xyz, 0.05, ns)),
+                             ("cyl hmax=.04", lambda: A.cylinder_query(new_xyz, xyz, rot, 0.05, -0.02, 0.04, ns)),
+                             ("cyl r=.02 hmax=.01", lambda: A.cylinder_query(new_xyz, xyz, rot, 0.02, -0.02, 0.01, ns))):
+                t = timeit(fn, iters=5)
+                rows.append({"op": f"sweep2 {name} B={B} grid_cell_pct={pct}", "us": round(t, 1)})
+                print(json.dumps(rows[-1]), flush=True)
+        _lib.set_tuning("grid_cell_pct", 0)
+        _lib.set_tuning("query_mode", 1)
+        for name, fn in (("ball r=.05", lambda: A.ball_query(new_xyz, xyz, 0.05, ns)),
+                         ("cyl hmax=.04", lambda: A.cylinder_query(new_xyz, xyz, rot, 0.05, -0.02, 0.04, ns))):
+            t = timeit(fn, iters=5)
+            rows.append({"op": f"sweep2 {name} B={B} full scan", "us": round(t, 1)})
+            print(json.dumps(rows[-1]), flush=True)
+        _lib.set_tuning("query_mode", 0)
+        for cc in (1, 2, 4, 8):
+            _lib.set_tuning("scatter_cc", cc)
+            for name, fn in (("group bwd C=128 N=20000", lambda: A.group_points_grad(gout, idx, N)),
+                             ("group bwd C=128 N=2048", lambda: A.group_points_grad(g2, idx2, 2048)),
+                             ("interp bwd C=256", lambda: A.three_interpolate_grad(go, i3, w, m))):
+                t = timeit(fn, iters=5)
+                rows.append({"op": f"sweep2 {name} B={B} scatter_cc={cc}", "us": round(t, 1)})
+                print(json.dumps(rows[-1]), flush=True)
+        _lib.set_tuning("scatter_cc", 0)
 
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     with open(args.out, "w") as f:

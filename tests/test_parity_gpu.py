@@ -187,6 +187,72 @@ def test_queries_full_size_vs_reference(dev, ref_a, ref_b):
             assert torch.equal(pu.cylinder_query(0.05, -0.02, hmax, 64, xyz, new_xyz, rot), want)
 
 
+def _special_cloud(kind, N, seed):
+    rng = np.random.default_rng(seed)
+    xyz = scenes.scene_batch([seed, seed + 1], N, "tabletop" if kind != "uniform" else "uniform")
+    if kind == "nan_inf":  # non-finite points never hit and must not disturb the others
+        xyz[0, rng.choice(N, 40, replace=False)] = np.nan
+        xyz[1, rng.choice(N, 40, replace=False), 1] = np.inf
+        xyz[1, rng.choice(N, 10, replace=False), 2] = -np.inf
+    elif kind == "planar":  # zero extent along z: a one-cell-thick grid
+        xyz[..., 2] = 0.25
+    elif kind == "dups":  # one heavily duplicated point: a cell holding a third of the cloud
+        xyz[:, N // 3: 2 * N // 3] = xyz[:, :1]
+    elif kind == "outlier":  # one far point stretches the bounding box
+        xyz[0, 7] = (40.0, -30.0, 25.0)
+    return xyz
+
+
+@pytest.mark.parametrize("mode", [1, 2])  # 1 = full scan only, 2 = cell grid forced
+@pytest.mark.parametrize("kind,N,m,r,ns", [("tabletop", 6000, 200, 0.05, 64), ("nan_inf", 5000, 150, 0.06, 32),
+                                           ("planar", 4100, 100, 0.04, 16), ("dups", 3000, 64, 0.03, 64),
+                                           ("outlier", 5000, 100, 0.05, 32), ("uniform", 4096, 100, 0.3, 24),
+                                           ("tabletop", 2500, 64, -0.05, 16), ("tabletop", 2500, 64, 0.0, 16),
+                                           ("tabletop", 2500, 64, 1e30, 40), ("uniform", 70, 9, 0.4, 5)])
+def test_ball_query_grid_and_scan_paths(dev, mode, kind, N, m, r, ns):
+    xyz = _special_cloud(kind, N, 11)
+    new_xyz = _queries(xyz, m, 4)
+    new_xyz[:, :3] += 5.0  # queries far outside the cloud
+    if kind == "nan_inf":
+        new_xyz[0, 5] = np.nan
+    want = oracle.ball_query(r, ns, xyz, new_xyz)
+    _lib.set_tuning("query_mode", mode)
+    try:
+        got = pu.ball_query(r, ns, T(xyz, dev), T(new_xyz, dev)).cpu().numpy()
+    finally:
+        _lib.set_tuning("query_mode", 0)
+    np.testing.assert_array_equal(got, want)
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("kind,N,m,ns,hmin,hmax,rotkind", [("tabletop", 6000, 200, 64, -0.02, 0.04, "ortho"),
+                                                         ("nan_inf", 5000, 100, 32, -0.02, 0.02, "ortho"),
+                                                         ("planar", 4100, 100, 16, -0.02, 0.01, "ortho"),
+                                                         ("tabletop", 5000, 120, 32, -0.02, 0.04, "scaled"),
+                                                         ("tabletop", 5000, 120, 32, -0.02, 0.04, "random"),
+                                                         ("tabletop", 3000, 60, 16, 0.03, -0.01, "ortho"),
+                                                         ("outlier", 5000, 100, 32, -0.5, 0.5, "ortho")])
+def test_cylinder_query_grid_and_scan_paths(dev, mode, kind, N, m, ns, hmin, hmax, rotkind):
+    xyz = _special_cloud(kind, N, 13)
+    new_xyz = _queries(xyz, m, 6)
+    rng = np.random.default_rng(17)
+    v = rng.normal(size=(2, m, 3)).astype(np.float32)
+    rot = scenes.viewpoint_rotations(-v, rng.uniform(0, np.pi, (2, m)).astype(np.float32)).reshape(2, m, 9)
+    if rotkind == "scaled":  # not orthonormal: the search region is no longer inside the bounding sphere
+        rot = rot * rng.uniform(0.2, 3.0, (2, m, 1)).astype(np.float32)
+    elif rotkind == "random":
+        rot = rng.normal(size=(2, m, 9)).astype(np.float32)
+        rot[0, 3] = np.nan
+    rot = np.ascontiguousarray(rot.astype(np.float32))
+    want = oracle.cylinder_query(0.05, hmin, hmax, ns, xyz, new_xyz, rot)
+    _lib.set_tuning("query_mode", mode)
+    try:
+        got = pu.cylinder_query(0.05, hmin, hmax, ns, T(xyz, dev), T(new_xyz, dev), T(rot, dev)).cpu().numpy()
+    finally:
+        _lib.set_tuning("query_mode", 0)
+    np.testing.assert_array_equal(got, want)
+
+
 # ------------------------------------------------------------------------------------------------- group / gather
 @pytest.mark.parametrize("B,C,N,m,ns", [(2, 3, 20000, 256, 64), (2, 128, 20000, 64, 64), (1, 131, 2048, 128, 32),
                                         (2, 5, 100, 7, 3), (1, 259, 1024, 512, 16), (1, 1, 50, 4, 4), (2, 16, 60000, 16, 8)])
@@ -203,6 +269,37 @@ def test_group_forward_backward_vs_oracle(dev, B, C, N, m, ns):
         out.backward(T(gout, dev))
         assert_grad_close(f.grad.cpu().numpy(), oracle.grouping_operation_grad(gout, idx, N))
     assert torch.equal(gb_group.torch_grouping_operation(T(feats, dev), T(idx, dev)), out.detach())
+
+
+@pytest.mark.parametrize("B,C,N,m,ns,pattern", [(2, 8, 20000, 64, 64, "zeros"), (2, 12, 3000, 128, 64, "one_per_query"),
+                                                (1, 16, 50, 256, 32, "random"), (2, 6, 7, 100, 48, "random"),
+                                                (1, 9, 2048, 2048, 8, "identity_runs"), (2, 4, 1, 77, 16, "zeros"),
+                                                (1, 5, 40000, 300, 64, "two_values")])
+def test_group_backward_long_runs(dev, B, C, N, m, ns, pattern):
+    """Index patterns whose sorted tiles are dominated by long runs of equal targets (what ball_query returns for empty
+    and sparse neighbourhoods): every boundary-shift / shared-target case of the sorted backward."""
+    rng = np.random.default_rng(N + m)
+    if pattern == "zeros":
+        idx = np.zeros((B, m, ns), np.int32)
+    elif pattern == "one_per_query":
+        idx = np.repeat(rng.integers(0, N, (B, m, 1)), ns, axis=2).astype(np.int32)
+    elif pattern == "identity_runs":
+        idx = np.repeat((np.arange(m) % N)[None, :, None], ns, axis=2).astype(np.int32) * np.ones((B, 1, 1), np.int32)
+    elif pattern == "two_values":
+        idx = np.where(rng.random((B, m, ns)) < 0.5, 3, N - 1).astype(np.int32)
+    else:
+        idx = rng.integers(0, N, (B, m, ns)).astype(np.int32)
+    gout = rng.normal(size=(B, C, m, ns)).astype(np.float32)
+    want = oracle.grouping_operation_grad(gout, idx, N)
+    for mod in (pu, gb_group):
+        f = torch.zeros((B, C, N), device=dev, requires_grad=True)
+        mod.grouping_operation(f, T(idx, dev)).backward(T(gout, dev))
+        assert_grad_close(f.grad.cpu().numpy(), want, scale=max(np.abs(want).max(), 1.0))
+    # module B's accumulate-into-caller-tensor entry adds to what is already there
+    base = rng.normal(size=(B, C, N)).astype(np.float32)
+    acc = T(base, dev)
+    gb_b.group_points_grad_wrapper(B, C, N, m, ns, T(gout, dev), T(idx, dev), acc)
+    assert_grad_close(acc.cpu().numpy(), base + want, scale=max(np.abs(want).max(), 1.0))
 
 
 def test_gather_forward_backward_vs_oracle(dev):
@@ -257,7 +354,8 @@ def test_three_nn_vs_oracle(dev, B, n, m):
         np.testing.assert_array_equal(dist.cpu().numpy(), np.sqrt(want_d2))
 
 
-@pytest.mark.parametrize("B,C,m,n", [(2, 256, 1024, 20000), (1, 7, 50, 333), (2, 64, 256, 512), (1, 130, 512, 1024)])
+@pytest.mark.parametrize("B,C,m,n", [(2, 256, 1024, 20000), (1, 7, 50, 333), (2, 64, 256, 512), (1, 130, 512, 1024),
+                                     (1, 8, 4, 5000), (2, 16, 1, 999), (1, 5, 30000, 4096), (2, 4, 3, 2)])
 def test_three_interpolate_vs_oracle(dev, B, C, m, n):
     rng = np.random.default_rng(C)
     feats = rng.normal(size=(B, C, m)).astype(np.float32)
