@@ -14,7 +14,7 @@ ABI_VERSION = 1
 
 _lib = None
 
-_vp, _i, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+_vp, _i, _f, _ll = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_longlong
 
 # name -> argtypes (restype is int unless listed in _RESTYPES); must match include/gbops.h
 SIGNATURES = {
@@ -28,6 +28,9 @@ SIGNATURES = {
     "gb_group_fwd": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "gb_group_bwd": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "gb_group_bwd_set": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "gb_group_fwd_strided": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _ll, _vp],
+    "gb_group_bwd_strided": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _ll, _i, _vp],
+    "gb_group_xyz": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _ll, _vp],
     "gb_three_nn": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp],
     "gb_three_interp_fwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "gb_three_interp_bwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
@@ -101,6 +104,9 @@ ALGO_BYTES = {
     "gb_three_interp_bwd": lambda a: a[4] * (4 * a[5] * a[7] + 24 * a[6] + 4 * a[5] * a[6]),   # args (b,c,n,m)
     "gb_group_bwd_set": lambda a: a[3] * (4 * a[4] * a[5] + 4 * a[6] * a[7] + 4 * a[4] * a[6] * a[7]),
     "gb_three_interp_bwd_set": lambda a: a[4] * (4 * a[5] * a[7] + 24 * a[6] + 4 * a[5] * a[6]),
+    "gb_group_fwd_strided": lambda a: a[3] * (4 * a[4] * a[5] + 4 * a[6] * a[7] + 4 * a[4] * a[6] * a[7]),
+    "gb_group_bwd_strided": lambda a: a[3] * (4 * a[4] * a[5] + 4 * a[6] * a[7] + 4 * a[4] * a[6] * a[7]),
+    "gb_group_xyz": lambda a: a[5] * (12 * a[6] + 12 * a[7] + (36 * a[7] if a[3] else 0) + 16 * a[7] * a[8]),  # b*(12n+12m(+36m)+(4+12) m ns)
     "gb_knn": lambda a: a[3] * (4 * a[4] * (a[5] + a[6]) + 8 * a[7] * a[6]),              # b*(4d(R+Q) + 8kQ)
     "gb_collision_counts": lambda a: 24 * a[1] + 176 * a[5] + 48 * a[5],
 }

@@ -42,6 +42,7 @@ struct Tuning {
   int interp_mode = 0;
   int query_qpw = 0;
   int scatter_cc = 0;
+  int scatter_mode = 0;  // bit 0: never use the dense (thread-owned targets) backward
   int query_mode = 0;  // 1: never use the cell grid, 2: always use it (when the shape allows)
   int grid_cell_pct = 0;  // cell edge as a percentage of the query reach (0 = default 50)
 };
@@ -52,8 +53,8 @@ cudaError_t scratch_alloc(void **p, size_t bytes, cudaStream_t s);
 
 // scatter.cu: atomic-free segmented scatter-add shared by the group and interpolate backward passes
 bool seg_scatter_supported(int b, int c, int n, size_t entries, int div);
-int seg_scatter_add(const float *src, const int *key, const float *weight, float *grad, int b, int c, int n, size_t entries, int div,
-                    int overwrite, cudaStream_t s);
+int seg_scatter_add(const float *src, size_t src_stride, const int *key, const float *weight, float *grad, int b, int c, int n,
+                    size_t entries, int div, int overwrite, cudaStream_t s);
 
 // squared distance exactly as nvcc contracts the reference's (a-b)*(a-b)+(c-d)*(c-d)+(e-f)*(e-f):
 // FMUL on the y term, then FFMA x, then FFMA z (SASS of ball_query_gpu.cu / sampling_gpu.cu / interpolate_gpu.cu).

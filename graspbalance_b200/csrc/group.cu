@@ -44,7 +44,7 @@ template <> __device__ __forceinline__ float vget<4>(const float4 &a, int v) { r
 template <int V>
 __global__ void __launch_bounds__(kGroupThreads) group_fwd_kernel(const float *__restrict__ points, const int *__restrict__ idx,
                                                                  float *__restrict__ out, int c, int n, int per4, int CH, int chunks,
-                                                                 long long total, long long wpc, int streaming) {
+                                                                 long long total, long long wpc, int streaming, size_t out_stride) {
   extern __shared__ __align__(16) float s_rows[];  // [CH/V][n][V]
   using Vec = typename VecT<V>::type;
   Vec *srow = reinterpret_cast<Vec *>(s_rows);
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(kGroupThreads) group_fwd_kernel(const float *_
 #pragma unroll
         for (int e = 0; e < V; ++e) {
           if (ch0 + e < c) {
-            float *dst = out + ((size_t)scene * c + ch0 + e) * per + (size_t)q * 4;
+            float *dst = out + (size_t)scene * out_stride + (size_t)(ch0 + e) * per + (size_t)q * 4;
             const float4 o = make_float4(vget<V>(a0, e), vget<V>(a1, e), vget<V>(a2, e), vget<V>(a3, e));
             if (streaming) st_cs_f4(dst, o);
             else *reinterpret_cast<float4 *>(dst) = o;
@@ -101,11 +101,11 @@ __global__ void __launch_bounds__(kGroupThreads) group_fwd_kernel(const float *_
 
 // generic fallback (any shape / alignment): one thread per output element, gathers straight from global/L2
 __global__ void group_fwd_generic_kernel(const float *__restrict__ points, const int *__restrict__ idx, float *__restrict__ out, int c,
-                                         int n, size_t per, size_t total) {
+                                         int n, size_t per, size_t total, size_t out_stride) {
   for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
     const size_t row = e / per, pos = e - row * per;
-    const size_t scene = row / c;
-    out[e] = __ldg(points + row * n + __ldg(idx + scene * per + pos));
+    const size_t scene = row / c, ch = row - scene * c;
+    out[scene * out_stride + ch * per + pos] = __ldg(points + row * n + __ldg(idx + scene * per + pos));
   }
 }
 
@@ -131,11 +131,11 @@ __device__ __forceinline__ bool warp_run_reduce(int key, float &val) {
 
 // grad_out [b,c,per]; idx [b,per]; grad_points [b,c,n] (+=).  One thread per 4 consecutive positions; grid.y = rows (b*c).
 __global__ void __launch_bounds__(256) group_bwd_kernel(const float *__restrict__ grad_out, const int *__restrict__ idx,
-                                                        float *__restrict__ grad_points, int c, int n, int per4) {
+                                                        float *__restrict__ grad_points, int c, int n, int per4, size_t go_stride) {
   const size_t row = blockIdx.y;
   const size_t scene = row / c;
   const size_t per = (size_t)per4 * 4;
-  const float *g = grad_out + row * per;
+  const float *g = grad_out + scene * go_stride + (row - scene * c) * per;
   const int *ip = idx + scene * per;
   float *dst = grad_points + row * n;
   const int qbase = blockIdx.x * (256 * 4);
@@ -170,11 +170,64 @@ __global__ void __launch_bounds__(256) group_bwd_kernel(const float *__restrict_
 }
 
 __global__ void group_bwd_generic_kernel(const float *__restrict__ grad_out, const int *__restrict__ idx, float *__restrict__ grad_points,
-                                         int c, int n, size_t per, size_t total) {
+                                         int c, int n, size_t per, size_t total, size_t go_stride) {
   for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
     const size_t row = e / per, pos = e - row * per;
     const size_t scene = row / c;
-    atomicAdd(grad_points + row * n + __ldg(idx + scene * per + pos), __ldg(grad_out + e));
+    atomicAdd(grad_points + row * n + __ldg(idx + scene * per + pos), __ldg(grad_out + scene * go_stride + (row - scene * c) * per + pos));
+  }
+}
+
+// ---- grouped coordinates of QueryAndGroup / CylinderQueryAndGroup in one pass ------------------------------------------
+// out[b, :, j, k] = ((xyz[b, idx[b,j,k]] - new_xyz[b,j]) * scale) . R[b,j]: what pointnet2_utils.py:178-190,281-291 build
+// from transpose + grouping_operation + subtract + divide + permute + matmul + permute (seven passes over [B,3,m,ns] and a
+// batched 3x3 sgemm).  Each op rounds as the torch op it replaces: fp32 subtract, multiply by the fp32 reciprocal of the
+// radius (ATen divides by a CPU scalar that way), dot product accumulated over k = 0, 1, 2 with fma.
+// VEC = 4: one thread per 4 consecutive samples of a query (nsample % 4 == 0), 128-bit idx load and stores.
+template <bool ROT, int VEC>
+__global__ void __launch_bounds__(256) group_xyz_kernel(const float *__restrict__ xyz, const float *__restrict__ new_xyz,
+                                                        const int *__restrict__ idx, const float *__restrict__ rot,
+                                                        float *__restrict__ out, int n, int m, int ns, float scale, int use_scale,
+                                                        size_t out_stride, size_t total) {
+  const size_t per = (size_t)m * ns;
+  const int nsv = ns / VEC;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const size_t qrow = t / nsv;  // scene * m + j
+    const int kq = (int)(t - qrow * nsv);
+    const size_t scene = qrow / m;
+    const float qx = __ldg(new_xyz + qrow * 3), qy = __ldg(new_xyz + qrow * 3 + 1), qz = __ldg(new_xyz + qrow * 3 + 2);
+    float r[9];
+    if (ROT) {
+#pragma unroll
+      for (int e = 0; e < 9; ++e) r[e] = __ldg(rot + qrow * 9 + e);
+    }
+    int id[VEC];
+    if (VEC == 4) {
+      const int4 v = ld_nc_i4(idx + qrow * ns + (size_t)kq * 4);
+      id[0] = v.x, id[VEC > 1 ? 1 : 0] = v.y, id[VEC > 2 ? 2 : 0] = v.z, id[VEC > 3 ? 3 : 0] = v.w;
+    } else {
+      id[0] = __ldg(idx + qrow * ns + kq);
+    }
+    float o[3][VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      const float *p = xyz + (scene * n + (size_t)id[e]) * 3;
+      float dx = __fsub_rn(__ldg(p), qx), dy = __fsub_rn(__ldg(p + 1), qy), dz = __fsub_rn(__ldg(p + 2), qz);
+      if (use_scale) dx = __fmul_rn(dx, scale), dy = __fmul_rn(dy, scale), dz = __fmul_rn(dz, scale);
+      if (ROT) {
+        o[0][e] = __fmaf_rn(dz, r[6], __fmaf_rn(dy, r[3], __fmul_rn(dx, r[0])));
+        o[1][e] = __fmaf_rn(dz, r[7], __fmaf_rn(dy, r[4], __fmul_rn(dx, r[1])));
+        o[2][e] = __fmaf_rn(dz, r[8], __fmaf_rn(dy, r[5], __fmul_rn(dx, r[2])));
+      } else {
+        o[0][e] = dx, o[1][e] = dy, o[2][e] = dz;
+      }
+    }
+    float *dst = out + scene * out_stride + (qrow - scene * m) * ns + (size_t)kq * VEC;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      if (VEC == 4) st_cs_f4(dst + ch * per, make_float4(o[ch][0], o[ch][VEC > 1 ? 1 : 0], o[ch][VEC > 2 ? 2 : 0], o[ch][VEC > 3 ? 3 : 0]));
+      else dst[ch * per] = o[ch][0];
+    }
   }
 }
 
@@ -203,7 +256,8 @@ static inline unsigned grid_for(size_t total, int threads) {
 }
 
 template <int V>
-static int launch_group_fwd(const float *points, const int *idx, float *out, int b, int c, int n, size_t per, int CH, cudaStream_t s) {
+static int launch_group_fwd(const float *points, const int *idx, float *out, int b, int c, int n, size_t per, int CH, size_t out_stride,
+                            cudaStream_t s) {
   auto kern = group_fwd_kernel<V>;
   const size_t smem = (size_t)CH * n * sizeof(float);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -220,7 +274,8 @@ static int launch_group_fwd(const float *points, const int *idx, float *out, int
   if (ctas < 1) ctas = 1;
   const long long wpc = (total + ctas - 1) / ctas;
   ctas = (total + wpc - 1) / wpc;
-  kern<<<(unsigned)ctas, kGroupThreads, smem, s>>>(points, idx, out, c, n, per4, CH, chunks, total, wpc, (g_tuning.group_mode & 1) ? 0 : 1);
+  kern<<<(unsigned)ctas, kGroupThreads, smem, s>>>(points, idx, out, c, n, per4, CH, chunks, total, wpc, (g_tuning.group_mode & 1) ? 0 : 1,
+                                                   out_stride);
   count_launch();
   return finish_launch();
 }
@@ -229,13 +284,15 @@ static int launch_group_fwd(const float *points, const int *idx, float *out, int
 
 using namespace gb;
 
-extern "C" int gb_group_fwd(const float *points, const int *idx, float *out, int b, int c, int n, int npoints, int nsample,
-                            gb_stream_t stream) {
+static int group_fwd_impl(const float *points, const int *idx, float *out, int b, int c, int n, int npoints, int nsample,
+                          long long out_scene_stride, gb_stream_t stream) {
   if (b < 0 || c < 0 || n <= 0 || npoints < 0 || nsample < 0 || !points || !idx || !out) return (int)cudaErrorInvalidValue;
   const size_t per = (size_t)npoints * nsample;
   if (b == 0 || c == 0 || per == 0) return 0;
+  if (out_scene_stride < (long long)((size_t)c * per)) return (int)cudaErrorInvalidValue;
+  const size_t ostride = (size_t)out_scene_stride;
   cudaStream_t s = (cudaStream_t)stream;
-  const bool aligned = (per % 4 == 0) && (((uintptr_t)idx | (uintptr_t)out) & 15u) == 0 && per / 4 < (1u << 30);
+  const bool aligned = (per % 4 == 0) && (ostride % 4 == 0) && (((uintptr_t)idx | (uintptr_t)out) & 15u) == 0 && per / 4 < (1u << 30);
   const size_t row_bytes = (size_t)n * sizeof(float);
   const size_t big = 200u * 1024u;
   if (aligned && row_bytes <= big && !(g_tuning.group_mode & 2)) {
@@ -246,39 +303,53 @@ extern "C" int gb_group_fwd(const float *points, const int *idx, float *out, int
     CH -= CH % V;
     if (CH > ((c + V - 1) / V) * V) CH = ((c + V - 1) / V) * V;
     if (CH > 64) CH = 64;
-    if (V == 4) return launch_group_fwd<4>(points, idx, out, b, c, n, per, CH, s);
-    if (V == 2) return launch_group_fwd<2>(points, idx, out, b, c, n, per, CH, s);
-    return launch_group_fwd<1>(points, idx, out, b, c, n, per, CH, s);
+    if (V == 4) return launch_group_fwd<4>(points, idx, out, b, c, n, per, CH, ostride, s);
+    if (V == 2) return launch_group_fwd<2>(points, idx, out, b, c, n, per, CH, ostride, s);
+    return launch_group_fwd<1>(points, idx, out, b, c, n, per, CH, ostride, s);
   }
   const size_t total = (size_t)b * c * per;
-  group_fwd_generic_kernel<<<grid_for(total, 256), 256, 0, s>>>(points, idx, out, c, n, per, total);
+  group_fwd_generic_kernel<<<grid_for(total, 256), 256, 0, s>>>(points, idx, out, c, n, per, total, ostride);
   count_launch();
   return finish_launch();
 }
 
+extern "C" int gb_group_fwd(const float *points, const int *idx, float *out, int b, int c, int n, int npoints, int nsample,
+                            gb_stream_t stream) {
+  return group_fwd_impl(points, idx, out, b, c, n, npoints, nsample, (long long)c * npoints * nsample, stream);
+}
+
+extern "C" int gb_group_fwd_strided(const float *points, const int *idx, float *out, int b, int c, int n, int npoints, int nsample,
+                                    long long out_scene_stride, gb_stream_t stream) {
+  return group_fwd_impl(points, idx, out, b, c, n, npoints, nsample, out_scene_stride, stream);
+}
+
 static int group_bwd_impl(const float *grad_out, const int *idx, float *grad_points, int b, int c, int n, int npoints, int nsample,
-                          int overwrite, gb_stream_t stream) {
+                          long long go_scene_stride, int overwrite, gb_stream_t stream) {
   if (b < 0 || c < 0 || n <= 0 || npoints < 0 || nsample < 0 || !grad_out || !idx || !grad_points) return (int)cudaErrorInvalidValue;
   const size_t per = (size_t)npoints * nsample;
+  if (go_scene_stride < (long long)((size_t)c * per)) return (int)cudaErrorInvalidValue;
+  const size_t gstride = (size_t)go_scene_stride;
   cudaStream_t s = (cudaStream_t)stream;
   if (b == 0 || c == 0) return 0;
   if (per == 0) return overwrite ? (int)cudaMemsetAsync(grad_points, 0, (size_t)b * c * n * sizeof(float), s) : 0;
 
   // ---- sorted, atomic-free path (scatter.cu): worth the one-off sort when there are enough channels to amortise it ----
-  if (!(g_tuning.group_mode & 4) && seg_scatter_supported(b, c, n, per, 1)) return seg_scatter_add(grad_out, idx, nullptr, grad_points, b, c, n, per, 1, overwrite, s);
+  if (!(g_tuning.group_mode & 4) && gstride % 4 == 0 && seg_scatter_supported(b, c, n, per, 1))
+    return seg_scatter_add(grad_out, gstride, idx, nullptr, grad_points, b, c, n, per, 1, overwrite, s);
   if (overwrite) {
     cudaError_t e = cudaMemsetAsync(grad_points, 0, (size_t)b * c * n * sizeof(float), s);
     if (e != cudaSuccess) return (int)e;
   }
 
-  const bool aligned = (per % 4 == 0) && (((uintptr_t)idx | (uintptr_t)grad_out) & 15u) == 0 && (size_t)b * c <= 65535 && per / 4 < (1u << 30);
+  const bool aligned = (per % 4 == 0) && (gstride % 4 == 0) && (((uintptr_t)idx | (uintptr_t)grad_out) & 15u) == 0 && (size_t)b * c <= 65535 &&
+                       per / 4 < (1u << 30);
   if (aligned) {
     const int per4 = (int)(per / 4);
     dim3 grid((per4 + 1023) / 1024, b * c);
-    group_bwd_kernel<<<grid, 256, 0, s>>>(grad_out, idx, grad_points, c, n, per4);
+    group_bwd_kernel<<<grid, 256, 0, s>>>(grad_out, idx, grad_points, c, n, per4, gstride);
   } else {
     const size_t total = (size_t)b * c * per;
-    group_bwd_generic_kernel<<<grid_for(total, 256), 256, 0, s>>>(grad_out, idx, grad_points, c, n, per, total);
+    group_bwd_generic_kernel<<<grid_for(total, 256), 256, 0, s>>>(grad_out, idx, grad_points, c, n, per, total, gstride);
   }
   count_launch();
   return finish_launch();
@@ -286,12 +357,17 @@ static int group_bwd_impl(const float *grad_out, const int *idx, float *grad_poi
 
 extern "C" int gb_group_bwd(const float *grad_out, const int *idx, float *grad_points, int b, int c, int n, int npoints,
                             int nsample, gb_stream_t stream) {
-  return group_bwd_impl(grad_out, idx, grad_points, b, c, n, npoints, nsample, 0, stream);
+  return group_bwd_impl(grad_out, idx, grad_points, b, c, n, npoints, nsample, (long long)c * npoints * nsample, 0, stream);
 }
 
 extern "C" int gb_group_bwd_set(const float *grad_out, const int *idx, float *grad_points, int b, int c, int n, int npoints,
                                 int nsample, gb_stream_t stream) {
-  return group_bwd_impl(grad_out, idx, grad_points, b, c, n, npoints, nsample, 1, stream);
+  return group_bwd_impl(grad_out, idx, grad_points, b, c, n, npoints, nsample, (long long)c * npoints * nsample, 1, stream);
+}
+
+extern "C" int gb_group_bwd_strided(const float *grad_out, const int *idx, float *grad_points, int b, int c, int n, int npoints,
+                                    int nsample, long long grad_out_scene_stride, int overwrite, gb_stream_t stream) {
+  return group_bwd_impl(grad_out, idx, grad_points, b, c, n, npoints, nsample, grad_out_scene_stride, overwrite ? 1 : 0, stream);
 }
 
 extern "C" int gb_gather_fwd(const float *points, const int *idx, float *out, int b, int c, int n, int m, gb_stream_t stream) {
@@ -309,6 +385,28 @@ extern "C" int gb_gather_bwd(const float *grad_out, const int *idx, float *grad_
   const size_t total = (size_t)b * c * m;
   if (total == 0) return 0;
   gather_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(grad_out, idx, grad_points, c, n, m, total);
+  count_launch();
+  return finish_launch();
+}
+
+extern "C" int gb_group_xyz(const float *xyz, const float *new_xyz, const int *idx, const float *rot, float *out, int b, int n, int m,
+                            int nsample, float scale, int use_scale, long long out_scene_stride, gb_stream_t stream) {
+  if (b < 0 || n <= 0 || m < 0 || nsample < 0 || !xyz || !new_xyz || !idx || !out) return (int)cudaErrorInvalidValue;
+  const size_t per = (size_t)m * nsample;
+  if (b == 0 || per == 0) return 0;
+  if (out_scene_stride < (long long)(3 * per)) return (int)cudaErrorInvalidValue;
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool vec = (nsample % 4 == 0) && (out_scene_stride % 4 == 0) && ((((uintptr_t)idx | (uintptr_t)out) & 15u) == 0);
+  const size_t total = vec ? (size_t)b * m * (nsample / 4) : (size_t)b * per;
+  const unsigned grid = grid_for(total, 256);
+  const size_t os = (size_t)out_scene_stride;
+  if (vec) {
+    if (rot) group_xyz_kernel<true, 4><<<grid, 256, 0, s>>>(xyz, new_xyz, idx, rot, out, n, m, nsample, scale, use_scale, os, total);
+    else group_xyz_kernel<false, 4><<<grid, 256, 0, s>>>(xyz, new_xyz, idx, rot, out, n, m, nsample, scale, use_scale, os, total);
+  } else {
+    if (rot) group_xyz_kernel<true, 1><<<grid, 256, 0, s>>>(xyz, new_xyz, idx, rot, out, n, m, nsample, scale, use_scale, os, total);
+    else group_xyz_kernel<false, 1><<<grid, 256, 0, s>>>(xyz, new_xyz, idx, rot, out, n, m, nsample, scale, use_scale, os, total);
+  }
   count_launch();
   return finish_launch();
 }

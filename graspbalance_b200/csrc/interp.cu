@@ -174,7 +174,7 @@ static int interp_bwd_impl(const float *grad_out, const int *idx, const float *w
   if (n == 0) return overwrite ? (int)cudaMemsetAsync(grad_points, 0, (size_t)b * c * m * sizeof(float), (cudaStream_t)stream) : 0;
   // atomic-free sorted segmented sum (scatter.cu): entries e = 3*j + t, source g[c][e / 3], weight w[e]
   if (!(g_tuning.interp_mode & 4) && seg_scatter_supported(b, c, m, (size_t)n * 3, 3))
-    return seg_scatter_add(grad_out, idx, weight, grad_points, b, c, m, (size_t)n * 3, 3, overwrite, (cudaStream_t)stream);
+    return seg_scatter_add(grad_out, (size_t)c * n, idx, weight, grad_points, b, c, m, (size_t)n * 3, 3, overwrite, (cudaStream_t)stream);
   if (overwrite) {
     cudaError_t e = cudaMemsetAsync(grad_points, 0, (size_t)b * c * m * sizeof(float), (cudaStream_t)stream);
     if (e != cudaSuccess) return (int)e;

@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(kSegThreads, 1) seg_accum_kernel(const float *
                                                                    const float *__restrict__ wsorted,
                                                                    const unsigned char *__restrict__ bnd, float *__restrict__ grad,
                                                                    int c, int n, int per_src, int tiles, int chunks, int stages,
-                                                                   int bulk_ok, int overwrite) {
+                                                                   int bulk_ok, int overwrite, size_t src_stride) {
   constexpr int T = seg_tile(DIV), TP = T / DIV;
   extern __shared__ __align__(128) unsigned char s_raw[];
   __shared__ uint64_t full[kSegMaxStages];
@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(kSegThreads, 1) seg_accum_kernel(const float *
   for (int i = tid; i < CC * n; i += kSegThreads) acc[i] = 0.f;
   if (nch < CC)  // rows of missing channels stay zero
     for (int i = tid; i < stages * CC * TP; i += kSegThreads) stage[i] = 0.f;
-  const float *g = src + ((size_t)scene * c + ch0) * per_src;
+  const float *g = src + (size_t)scene * src_stride + (size_t)ch0 * per_src;
   // sort output of this scene; one spare tile behind the last one keeps the prefetch below unconditional
   const unsigned *pp = packed + (size_t)scene * (tiles + 1) * kSegTileStride + warp * 64 + lane;
   const float *wp = WEIGHTED ? wsorted + (size_t)scene * (tiles + 1) * kSegTileStride + warp * 64 + lane : nullptr;
@@ -337,6 +337,197 @@ __global__ void __launch_bounds__(kSegThreads, 1) seg_accum_kernel(const float *
   }
 }
 
+// ---- dense mode: few targets (n <= 4096) -------------------------------------------------------------------------------
+// When a tile of ~2048 entries hits every target about once or more (InvResMLP groupings with n = m <= 2048, the
+// interpolation backward with <= 1024 known points), entry-parallel processing spends its time merging runs.  Here the
+// roles flip: a THREAD owns a target (TPT targets when n > 1024) and CT channels for the whole kernel and keeps their sums
+// in REGISTERS; per tile it walks its targets' slices of the sorted entry list and adds the staged source values.  No
+// accumulator in shared memory, no atomics, no run merging; the only barrier releases the stage.
+//
+// Sort output per tile ("blob", one bulk copy): tp[2048] u16 (tile-local entry of each sorted position) | start[NS] u16
+// (first sorted position of every target, start[n] = number of valid entries; NS = n + 1 rounded up to 8).
+__host__ __device__ inline int seg_dense_ns(int n) { return (n + 1 + 7) & ~7; }
+__host__ __device__ inline size_t seg_dense_blob(int n) { return (size_t)kSegTileStride * 2 + (size_t)seg_dense_ns(n) * 2; }
+
+// grid (tiles, b); dynamic smem (n + 32) ints
+__global__ void __launch_bounds__(kSegSortThreads) seg_sort_dense_kernel(const int *__restrict__ idx, int per, int n, int T,
+                                                                         unsigned char *__restrict__ blobs) {
+  extern __shared__ int s_bins[];
+  int *wsum = s_bins + n;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const size_t ibase = (size_t)blockIdx.y * per + (size_t)blockIdx.x * T;
+  unsigned short *tp = reinterpret_cast<unsigned short *>(blobs + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * seg_dense_blob(n));
+  unsigned short *start = tp + kSegTileStride;
+  const int tc = min(T, per - (int)blockIdx.x * T);
+  for (int i = tid; i < n; i += kSegSortThreads) s_bins[i] = 0;
+  __syncthreads();
+  constexpr int R = kSegTileStride / kSegSortThreads;
+  int key[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int e = r * kSegSortThreads + tid;
+    int k = -1;
+    if (e < tc) {
+      k = __ldg(idx + ibase + e);
+      if ((unsigned)k >= (unsigned)n) k = -1;  // out-of-range targets are dropped
+      else atomicAdd(&s_bins[k], 1);
+    }
+    key[r] = k;
+  }
+  __syncthreads();
+  const int chunk = (n + kSegSortThreads - 1) / kSegSortThreads;
+  const int c0 = min(n, tid * chunk), c1 = min(n, c0 + chunk);
+  int local = 0;
+  for (int i = c0; i < c1; ++i) local += s_bins[i];
+  int incl = local;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int o = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += o;
+  }
+  if (lane == 31) wsum[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    const int w = lane < kSegSortThreads / 32 ? wsum[lane] : 0;
+    int wi = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int o = __shfl_up_sync(0xffffffffu, wi, d);
+      if (lane >= d) wi += o;
+    }
+    wsum[lane] = wi - w;
+    if (lane == kSegSortThreads / 32 - 1) wsum[31] = wi;
+  }
+  __syncthreads();
+  int run = wsum[warp] + incl - local;
+  const int total = wsum[31];
+  for (int i = c0; i < c1; ++i) {
+    const int cnt = s_bins[i];
+    s_bins[i] = run;
+    start[i] = (unsigned short)run;
+    run += cnt;
+  }
+  for (int i = n + tid; i < seg_dense_ns(n); i += kSegSortThreads) start[i] = (unsigned short)total;
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int e = r * kSegSortThreads + tid;
+    if (key[r] >= 0) tp[atomicAdd(&s_bins[key[r]], 1)] = (unsigned short)e;
+  }
+  for (int e = total + tid; e < kSegTileStride; e += kSegSortThreads) tp[e] = 0;
+}
+
+// grid b * chunks, kSegThreads threads.  Thread -> target slot ts = tid % NT and channel group cg = tid / NT
+// (NT = 2^nt_log2 >= n when n <= 1024, else 1024 with TPT targets ts, ts + 1024, ...); CC = CT * (1024 / NT) channels per
+// CTA.  dynamic smem per stage: gt[CC][TP] f32 | wt[T] f32 (weighted) | blob.
+template <int CT, int TPT, int DIV, bool WEIGHTED>
+__global__ void __launch_bounds__(kSegThreads, 1) seg_dense_kernel(const float *__restrict__ src, const unsigned char *__restrict__ blobs,
+                                                                   const float *__restrict__ weight, float *__restrict__ grad, int c,
+                                                                   int n, int per_src, int tiles, int chunks, int nt_log2, int stages,
+                                                                   int stage_bytes, int bulk_ok, int overwrite, size_t src_stride) {
+  constexpr int T = seg_tile(DIV), TP = T / DIV;
+  extern __shared__ __align__(128) unsigned char s_raw[];
+  __shared__ uint64_t full[kSegMaxStages];
+  const int tid = threadIdx.x;
+  const int NT = 1 << nt_log2, G = kSegThreads >> nt_log2, CC = CT * G;
+  const int ts = tid & (NT - 1), cg = tid >> nt_log2;
+  const int scene = blockIdx.x / chunks, chunk = blockIdx.x - scene * chunks;
+  const int ch0 = chunk * CC;
+  const int nch = min(CC, c - ch0);
+  const float *g = src + (size_t)scene * src_stride + (size_t)ch0 * per_src;
+  const size_t blob = seg_dense_blob(n);
+  const unsigned char *bsrc = blobs + (size_t)scene * tiles * blob;
+  const float *wsrc = WEIGHTED ? weight + (size_t)scene * per_src * DIV : nullptr;
+  const int wt_off = CC * TP * 4, blob_off = wt_off + (WEIGHTED ? T * 4 : 0);
+
+  if (nch < CC)  // rows of missing channels stay zero
+    for (int i = tid; i < stages * stage_bytes / 4; i += kSegThreads) reinterpret_cast<float *>(s_raw)[i] = 0.f;
+  auto issue = [&](int t, int sidx) {
+    const int p0 = t * TP, pc = min(TP, per_src - p0);
+    unsigned char *dst = s_raw + (size_t)sidx * stage_bytes;
+    mbar_arrive_expect_tx(&full[sidx], (uint32_t)pc * 4u * (uint32_t)nch + (WEIGHTED ? (uint32_t)pc * DIV * 4u : 0u) + (uint32_t)blob);
+    for (int cc = 0; cc < nch; ++cc)
+      bulk_g2s(dst + (size_t)cc * TP * 4, g + (size_t)cc * per_src + p0, (uint32_t)pc * 4u, &full[sidx]);
+    if (WEIGHTED) bulk_g2s(dst + wt_off, wsrc + (size_t)p0 * DIV, (uint32_t)pc * DIV * 4u, &full[sidx]);
+    bulk_g2s(dst + blob_off, bsrc + (size_t)t * blob, (uint32_t)blob, &full[sidx]);
+  };
+  if (bulk_ok) {
+    if (tid == 0) {
+      for (int s = 0; s < stages; ++s) mbar_init(&full[s], 1);
+      fence_mbar_init();
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0)
+      for (int t = 0; t < stages - 1 && t < tiles; ++t) issue(t, t);
+  } else {
+    __syncthreads();
+  }
+
+  float a[TPT][CT];
+#pragma unroll
+  for (int j = 0; j < TPT; ++j)
+#pragma unroll
+    for (int cc = 0; cc < CT; ++cc) a[j][cc] = 0.f;
+
+  int sidx = 0, issue_sidx = stages - 1;
+  uint32_t parity = 0;
+  for (int t = 0; t < tiles; ++t) {
+    unsigned char *st = s_raw + (size_t)sidx * stage_bytes;
+    if (bulk_ok) {
+      if (tid == 0 && t + stages - 1 < tiles) issue(t + stages - 1, issue_sidx);
+      mbar_wait(&full[sidx], parity);
+    } else {
+      const int p0 = t * TP, pc = min(TP, per_src - p0);
+      for (int cc = 0; cc < nch; ++cc)
+        for (int i = tid; i < pc; i += kSegThreads) reinterpret_cast<float *>(st)[cc * TP + i] = __ldg(g + (size_t)cc * per_src + p0 + i);
+      if (WEIGHTED)
+        for (int i = tid; i < pc * DIV; i += kSegThreads) reinterpret_cast<float *>(st + wt_off)[i] = __ldg(wsrc + (size_t)p0 * DIV + i);
+      for (int i = tid; i < (int)(blob / 4); i += kSegThreads)
+        reinterpret_cast<unsigned *>(st + blob_off)[i] = __ldg(reinterpret_cast<const unsigned *>(bsrc + (size_t)t * blob) + i);
+      __syncthreads();
+    }
+    const float *gt = reinterpret_cast<const float *>(st) + (size_t)cg * CT * TP;
+    const float *wt = reinterpret_cast<const float *>(st + wt_off);
+    const unsigned short *tp = reinterpret_cast<const unsigned short *>(st + blob_off);
+    const unsigned short *start = tp + kSegTileStride;
+#pragma unroll
+    for (int j = 0; j < TPT; ++j) {
+      const int k = ts + j * NT;
+      if (k < n) {
+        const int e1 = start[k + 1];
+        for (int i = start[k]; i < e1; ++i) {
+          const unsigned p = tp[i];
+          const unsigned sp = DIV == 3 ? (p * 43691u) >> 17 : p;
+          const float wv = WEIGHTED ? wt[p] : 1.f;
+#pragma unroll
+          for (int cc = 0; cc < CT; ++cc) {
+            const float v = gt[cc * TP + sp];
+            a[j][cc] += WEIGHTED ? __fmul_rn(v, wv) : v;  // the reference adds g * w_t (interpolate_gpu.cu:144-146)
+          }
+        }
+      }
+    }
+    __syncthreads();  // releases the stage
+    if (++sidx == stages) sidx = 0, parity ^= 1u;
+    if (++issue_sidx == stages) issue_sidx = 0;
+  }
+#pragma unroll
+  for (int j = 0; j < TPT; ++j) {
+    const int k = ts + j * NT;
+    if (k < n) {
+#pragma unroll
+      for (int cc = 0; cc < CT; ++cc) {
+        const int ch = cg * CT + cc;
+        if (ch < nch) {
+          float *dst = grad + ((size_t)scene * c + ch0 + ch) * n + k;
+          *dst = overwrite ? a[j][cc] : *dst + a[j][cc];
+        }
+      }
+    }
+  }
+}
+
 // stream-ordered scratch from the device's default pool; the pool is told once to keep freed memory instead of
 // returning it to the driver at every synchronisation (the default), which would make every call pay a fresh allocation
 cudaError_t scratch_alloc(void **p, size_t bytes, cudaStream_t s) {
@@ -356,8 +547,8 @@ cudaError_t scratch_alloc(void **p, size_t bytes, cudaStream_t s) {
 constexpr size_t kSegSmemBudget = 227u * 1024u - 1024u;  // dynamic; the mbarriers are static
 
 template <int CC, int DIV, bool WEIGHTED>
-static int launch_seg_accum(const float *src, const unsigned *packed, const float *wsorted, const unsigned char *bnd, float *grad,
-                            int b, int c, int n, int per_src, int tiles, int bulk_ok, int overwrite, cudaStream_t s) {
+static int launch_seg_accum(const float *src, size_t src_stride, const unsigned *packed, const float *wsorted, const unsigned char *bnd,
+                            float *grad, int b, int c, int n, int per_src, int tiles, int bulk_ok, int overwrite, cudaStream_t s) {
   constexpr int TP = seg_tile(DIV) / DIV;
   const size_t acc_bytes = (size_t)CC * n * sizeof(float), stage_bytes = (size_t)CC * TP * sizeof(float);
   int stages = (int)((kSegSmemBudget - acc_bytes) / stage_bytes);
@@ -370,9 +561,94 @@ static int launch_seg_accum(const float *src, const unsigned *packed, const floa
   if (e != cudaSuccess) return (int)e;
   const int chunks = (c + CC - 1) / CC;
   kern<<<(unsigned)(b * chunks), kSegThreads, smem, s>>>(src, packed, wsorted, bnd, grad, c, n, per_src, tiles, chunks, stages, bulk_ok,
-                                                         overwrite);
+                                                         overwrite, src_stride);
   count_launch();
   return finish_launch();
+}
+
+template <int CT, int TPT, int DIV, bool WEIGHTED>
+static int launch_seg_dense(const float *src, size_t src_stride, const unsigned char *blobs, const float *weight, float *grad, int b, int c,
+                            int n, int per_src, int tiles, int nt_log2, int bulk_ok, int overwrite, cudaStream_t s) {
+  constexpr int T = seg_tile(DIV), TP = T / DIV;
+  const int G = kSegThreads >> nt_log2, CC = CT * G;
+  const size_t stage_bytes = ((size_t)CC * TP * 4 + (WEIGHTED ? (size_t)T * 4 : 0) + seg_dense_blob(n) + 127) & ~(size_t)127;
+  int stages = (int)(kSegSmemBudget / stage_bytes);
+  stages = stages > kSegMaxStages ? kSegMaxStages : stages;
+  if (stages > tiles) stages = tiles;
+  if (!bulk_ok || stages < 1) stages = 1;
+  const size_t smem = stages * stage_bytes;
+  auto kern = seg_dense_kernel<CT, TPT, DIV, WEIGHTED>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  const int chunks = (c + CC - 1) / CC;
+  kern<<<(unsigned)(b * chunks), kSegThreads, smem, s>>>(src, blobs, weight, grad, c, n, per_src, tiles, chunks, nt_log2, stages,
+                                                         (int)stage_bytes, bulk_ok, overwrite, src_stride);
+  count_launch();
+  return finish_launch();
+}
+
+constexpr int kSegDenseMaxN = 4096;
+
+// dense mode (thread-owned targets, register accumulators) for n <= 4096
+static int seg_scatter_dense(const float *src, size_t src_stride, const int *key, const float *weight, float *grad, int b, int c, int n,
+                             size_t entries, int div, int overwrite, cudaStream_t s) {
+  const int T = seg_tile(div), TP = T / div;
+  const int per_src = (int)(entries / div);
+  const int tiles = (int)((entries + T - 1) / T);
+  const size_t blob = seg_dense_blob(n);
+  unsigned char *blobs = nullptr;
+  cudaError_t e = scratch_alloc((void **)&blobs, (size_t)b * tiles * blob, s);
+  if (e != cudaSuccess) return (int)e;
+  const size_t sort_smem = ((size_t)n + 32) * sizeof(int);
+  seg_sort_dense_kernel<<<dim3((unsigned)tiles, b), kSegSortThreads, sort_smem, s>>>(key, (int)entries, n, T, blobs);
+  count_launch();
+  int rc = finish_launch();
+  if (!rc) {
+    int nt_log2 = 8;  // >= 256 target slots: at most 4 channel groups per CTA, so one channel per thread always fits
+    while ((1 << nt_log2) < n && nt_log2 < 10) ++nt_log2;
+    const int NT = 1 << nt_log2, G = kSegThreads / NT;
+    const int tpt = (n + NT - 1) / NT;  // 1 when n <= 1024, else 2..4
+    // channels per thread: as many as registers (CT * TPT <= 16), two stages of shared memory and the grid allow
+    int CT = 8;
+    auto stage_of = [&](int ct) { return (size_t)ct * G * TP * 4 + (weight ? (size_t)T * 4 : 0) + blob + 128; };
+    while (CT > 1 && (CT * (tpt > 2 ? 4 : tpt) > 16 || CT * G > ((c + 3) & ~3) * 2 || 2 * stage_of(CT) > kSegSmemBudget ||
+                      (long)b * ((c + CT * G - 1) / (CT * G)) < (long)num_sms()))
+      CT >>= 1;
+    if (g_tuning.scatter_cc == 1 || g_tuning.scatter_cc == 2 || g_tuning.scatter_cc == 4 || g_tuning.scatter_cc == 8) {
+      CT = g_tuning.scatter_cc;
+      while (CT > 1 && (CT * (tpt > 2 ? 4 : tpt) > 16 || 2 * stage_of(CT) > kSegSmemBudget)) CT >>= 1;
+    }
+    // bulk copies: 16-byte aligned row pieces (and weight pieces: per_src * div * 4 bytes per scene)
+    const int bulk_ok = (per_src % 4 == 0) && (((uintptr_t)src & 15u) == 0) && (!weight || ((uintptr_t)weight & 15u) == 0) &&
+                        2 * stage_of(CT) <= kSegSmemBudget;
+#define GB_DENSE_CASE(CTV, TPTV)                                                                                                   \
+  rc = div == 3 ? launch_seg_dense<CTV, TPTV, 3, true>(src, src_stride, blobs, weight, grad, b, c, n, per_src, tiles, nt_log2, bulk_ok, overwrite, s) \
+                : launch_seg_dense<CTV, TPTV, 1, false>(src, src_stride, blobs, weight, grad, b, c, n, per_src, tiles, nt_log2, bulk_ok, overwrite, s)
+    if (tpt <= 1) {
+      switch (CT) {
+        case 8: GB_DENSE_CASE(8, 1); break;
+        case 4: GB_DENSE_CASE(4, 1); break;
+        case 2: GB_DENSE_CASE(2, 1); break;
+        default: GB_DENSE_CASE(1, 1); break;
+      }
+    } else if (tpt <= 2) {
+      switch (CT) {
+        case 8: GB_DENSE_CASE(8, 2); break;
+        case 4: GB_DENSE_CASE(4, 2); break;
+        case 2: GB_DENSE_CASE(2, 2); break;
+        default: GB_DENSE_CASE(1, 2); break;
+      }
+    } else {
+      switch (CT) {
+        case 4: GB_DENSE_CASE(4, 4); break;
+        case 2: GB_DENSE_CASE(2, 4); break;
+        default: GB_DENSE_CASE(1, 4); break;
+      }
+    }
+#undef GB_DENSE_CASE
+  }
+  cudaFreeAsync(blobs, s);
+  return rc;
 }
 
 bool seg_scatter_supported(int b, int c, int n, size_t entries, int div) {
@@ -385,9 +661,10 @@ bool seg_scatter_supported(int b, int c, int n, size_t entries, int div) {
 // grad[b,c,key[b,e]] += src[b,c,e/div] * (weight ? weight[b,e] : 1); key/weight [b,entries]; src [b,c,entries/div].
 // Two shapes are instantiated: div = 1 without weights (group) and div = 3 with weights (interpolate).
 // overwrite != 0: grad is fully written (no zero fill needed) instead of accumulated into.
-int seg_scatter_add(const float *src, const int *key, const float *weight, float *grad, int b, int c, int n, size_t entries, int div,
-                    int overwrite, cudaStream_t s) {
+int seg_scatter_add(const float *src, size_t src_stride, const int *key, const float *weight, float *grad, int b, int c, int n,
+                    size_t entries, int div, int overwrite, cudaStream_t s) {
   if ((div != 1 && div != 3) || (div == 3) != (weight != nullptr)) return (int)cudaErrorInvalidValue;
+  if (n <= kSegDenseMaxN && !(g_tuning.scatter_mode & 1)) return seg_scatter_dense(src, src_stride, key, weight, grad, b, c, n, entries, div, overwrite, s);
   const int T = seg_tile(div), TP = T / div;
   const int per_src = (int)(entries / div);
   const int tiles = (int)((entries + T - 1) / T);
@@ -425,8 +702,8 @@ int seg_scatter_add(const float *src, const int *key, const float *weight, float
     const int bulk_ok = (per_src % 4 == 0) && (((uintptr_t)src & 15u) == 0);
 #define GB_SEG_CASE(CCV)                                                                                            \
   case CCV:                                                                                                         \
-    rc = div == 3 ? launch_seg_accum<CCV, 3, true>(src, packed, wsorted, bnd, grad, b, c, n, per_src, tiles, bulk_ok, overwrite, s)  \
-                  : launch_seg_accum<CCV, 1, false>(src, packed, wsorted, bnd, grad, b, c, n, per_src, tiles, bulk_ok, overwrite, s); \
+    rc = div == 3 ? launch_seg_accum<CCV, 3, true>(src, src_stride, packed, wsorted, bnd, grad, b, c, n, per_src, tiles, bulk_ok, overwrite, s)  \
+                  : launch_seg_accum<CCV, 1, false>(src, src_stride, packed, wsorted, bnd, grad, b, c, n, per_src, tiles, bulk_ok, overwrite, s); \
     break;
     switch (CC) {
       GB_SEG_CASE(8)

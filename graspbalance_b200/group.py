@@ -9,10 +9,12 @@ reference's out-parameter convention (group.py:62-145); KNN / KNNGroup stay torc
 import copy
 import logging
 
+import numpy as np
 import torch
 import torch.nn as nn
 from torch.autograd import Function
 
+from . import _lib
 from . import pointnet2_batch_cuda as pointnet2_cuda
 
 
@@ -150,11 +152,23 @@ class QueryAndGroup(nn.Module):
         idx = ball_query(self.radius, self.nsample, support_xyz, query_xyz)
         if self.return_only_idx:
             return idx
-        grouped_xyz = grouping_operation(support_xyz.transpose(1, 2).contiguous(), idx)
-        if self.relative_xyz:
-            grouped_xyz = grouped_xyz - query_xyz.transpose(1, 2).unsqueeze(-1)
-            if self.normalize_dp:
-                grouped_xyz /= self.radius
+        fusable = all(t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and not t.requires_grad
+                      for t in (query_xyz, support_xyz))
+        if self.relative_xyz and fusable:
+            # gather + centre (+ scale) in one launch instead of transpose, group, subtract, divide (group.py:171-176);
+            # ATen evaluates `/= radius` as a multiply by the fp32 reciprocal
+            B, npoint, nsample = idx.shape
+            grouped_xyz = torch.empty((B, 3, npoint, nsample), dtype=torch.float32, device=idx.device)
+            inv = float(np.float32(1.0) / np.float32(self.radius)) if self.normalize_dp else 0.0
+            _lib.call("gb_group_xyz", support_xyz, support_xyz.data_ptr(), query_xyz.data_ptr(), idx.data_ptr(), None,
+                      grouped_xyz.data_ptr(), B, support_xyz.shape[1], npoint, nsample, inv, 1 if self.normalize_dp else 0,
+                      3 * npoint * nsample)
+        else:
+            grouped_xyz = grouping_operation(support_xyz.transpose(1, 2).contiguous(), idx)
+            if self.relative_xyz:
+                grouped_xyz = grouped_xyz - query_xyz.transpose(1, 2).unsqueeze(-1)
+                if self.normalize_dp:
+                    grouped_xyz /= self.radius
         grouped_features = grouping_operation(features, idx) if features is not None else None
         return grouped_xyz, grouped_features
 

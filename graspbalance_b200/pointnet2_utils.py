@@ -10,11 +10,13 @@ same names, call signatures, dtypes and index layouts, running on graspbalance_b
     cylinder_query(radius, hmin, hmax, nsample, xyz, new_xyz, rot)   :235-244
     QueryAndGroup / GroupAll / CylinderQueryAndGroup / RandomDropout :35-43,152-232,247-308
 """
+import numpy as np
 import torch
 import torch.nn as nn
 from torch.autograd import Function
 
 from . import _ext
+from . import _lib
 
 
 class FurthestPointSampling(Function):
@@ -153,12 +155,66 @@ def _resample_uniformly(idx, nsample):
     return unique_cnt
 
 
+def _fusable(*tensors):
+    """The fused grouper kernels take CUDA fp32 contiguous inputs and do not differentiate w.r.t. coordinates."""
+    return all(t is None or (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and not t.requires_grad) for t in tensors)
+
+
+class _FusedQueryGroup(Function):
+    """(B, 3[+C], npoint, nsample) result of QueryAndGroup / CylinderQueryAndGroup written in place by two launches:
+    gb_group_xyz (gather + centre + scale + rotate) into rows 0..2 and gb_group_fwd_strided into rows 3.. -- instead of
+    transpose, group, subtract, divide, permute, matmul, permute, group, cat (pointnet2_utils.py:178-207, 281-308).
+    Backward reads the feature rows' gradient from the same slice (gb_group_bwd_strided); coordinates get no gradient
+    (callers that need one take the unfused path)."""
+
+    @staticmethod
+    def forward(ctx, xyz, new_xyz, idx, rot, features, inv_radius):
+        B, npoint, nsample = idx.shape
+        N = xyz.shape[1]
+        C = 0 if features is None else features.shape[1]
+        per = npoint * nsample
+        out = torch.empty((B, 3 + C, npoint, nsample), dtype=torch.float32, device=xyz.device)
+        stride = (3 + C) * per
+        _lib.call("gb_group_xyz", xyz, xyz.data_ptr(), new_xyz.data_ptr(), idx.data_ptr(), None if rot is None else rot.data_ptr(),
+                  out.data_ptr(), B, N, npoint, nsample, float(inv_radius or 0.0), 1 if inv_radius is not None else 0, stride)
+        if C:
+            _lib.call("gb_group_fwd_strided", features, features.data_ptr(), idx.data_ptr(), out.data_ptr() + 12 * per, B, C,
+                      features.shape[2], npoint, nsample, stride)
+        ctx.for_backwards = (idx, None if features is None else features.shape[2], C)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        idx, N, C = ctx.for_backwards
+        if not C or not ctx.needs_input_grad[4]:
+            return None, None, None, None, None, None
+        B, npoint, nsample = idx.shape
+        per = npoint * nsample
+        grad_out = grad_out.contiguous()
+        grad = torch.empty((B, C, N), dtype=torch.float32, device=grad_out.device)
+        _lib.call("gb_group_bwd_strided", grad_out, grad_out.data_ptr() + 12 * per, idx.data_ptr(), grad.data_ptr(), B, C, N, npoint,
+                  nsample, (3 + C) * per, 1)
+        return None, None, None, None, grad, None
+
+
 class _GroupBase(nn.Module):
     """Shared tail of QueryAndGroup / CylinderQueryAndGroup: group xyz, centre, optional scale / rotation, group
     features, concatenate, and the ret_* tuple convention (pointnet2_utils.py:178-207,281-308)."""
 
     def _finish(self, idx, xyz, new_xyz, features, rot=None):
         unique_cnt = _resample_uniformly(idx, self.nsample) if self.sample_uniformly else None
+        if self.use_xyz and _fusable(xyz, new_xyz, rot) and (features is None or (features.is_cuda and features.dtype == torch.float32
+                                                                                   and features.is_contiguous())) and idx.is_contiguous():
+            # ATen evaluates `grouped_xyz /= radius` as a multiply by the fp32 reciprocal
+            inv = float(np.float32(1.0) / np.float32(self.radius)) if self.normalize_xyz else None
+            new_features = _FusedQueryGroup.apply(xyz, new_xyz, idx, None if rot is None else rot.reshape(rot.shape[0], rot.shape[1], 9),
+                                                  features, inv)
+            ret = [new_features]
+            if self.ret_grouped_xyz:
+                ret.append(new_features[:, :3])
+            if self.ret_unique_cnt:
+                ret.append(unique_cnt)
+            return ret[0] if len(ret) == 1 else tuple(ret)
         grouped_xyz = grouping_operation(xyz.transpose(1, 2).contiguous(), idx)  # (B, 3, npoint, nsample)
         grouped_xyz -= new_xyz.transpose(1, 2).unsqueeze(-1)
         if self.normalize_xyz:

@@ -83,6 +83,24 @@ GB_API int gb_group_bwd(const float *grad_out, const int *idx, float *grad_point
 GB_API int gb_group_bwd_set(const float *grad_out, const int *idx, float *grad_points, int b, int c, int n, int npoints,
                      int nsample, gb_stream_t stream);
 
+/* Strided variants for fused grouper modules (pointnet2_utils.py:178-207 builds cat([grouped_xyz, grouped_features])):
+ * the C grouped rows of a scene are written to / read from a tensor whose scenes are out_scene_stride floats apart
+ * (>= c*npoints*nsample, multiple of 4 for the vector paths), so features can be grouped straight into channels 3.. of
+ * the [b, 3+c, npoints, nsample] result and their gradient read from that slice without a copy.  `out` / `grad_out` point
+ * at the first of the c rows of scene 0. */
+GB_API int gb_group_fwd_strided(const float *points, const int *idx, float *out, int b, int c, int n, int npoints, int nsample,
+                         long long out_scene_stride, gb_stream_t stream);
+GB_API int gb_group_bwd_strided(const float *grad_out, const int *idx, float *grad_points, int b, int c, int n, int npoints,
+                         int nsample, long long grad_out_scene_stride, int overwrite, gb_stream_t stream);
+
+/* The grouped-coordinate part of QueryAndGroup / CylinderQueryAndGroup (pointnet2_utils.py:178-190, 281-291; group.py:167-176)
+ * in one pass: out[b, :, j, k] = ((xyz[b, idx[b,j,k]] - new_xyz[b,j]) * scale) . R[b,j]   (3 rows per scene, scenes
+ * out_scene_stride floats apart).  xyz [b,n,3] (no transposed copy needed), new_xyz [b,m,3], idx [b,m,nsample],
+ * rot [b,m,9] row-major or NULL (no rotation); use_scale = 0 skips the multiply (scale = fp32 reciprocal of the radius
+ * when normalize_xyz is set, as ATen evaluates `grouped_xyz /= radius`). */
+GB_API int gb_group_xyz(const float *xyz, const float *new_xyz, const int *idx, const float *rot, float *out, int b, int n, int m,
+                 int nsample, float scale, int use_scale, long long out_scene_stride, gb_stream_t stream);
+
 /* A: three_nn_kernel_wrapper (interpolate_gpu.cu:66-73); B: three_nn_kernel_launcher_fast (:62-81).
  * unknown [b,n,3], known [b,m,3] -> dist2 [b,n,3] f32 (SQUARED), idx [b,n,3] i32. */
 GB_API int gb_three_nn(const float *unknown, const float *known, float *dist2, int *idx, int b, int n, int m,

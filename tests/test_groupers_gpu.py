@@ -1,0 +1,162 @@
+"""GPU tests of the grouper modules: QueryAndGroup / CylinderQueryAndGroup of module A
+(PointNet/pointnet2_utils.py:152-308) and QueryAndGroup of module B (ModifiedNetTools/group.py:147-180).
+
+The product runs them as fused launches (gb_group_xyz + gb_group_fwd_strided, backward gb_group_bwd_strided).  They are
+checked against a literal torch restatement of the reference modules' forward (transpose, index gather, subtract, divide,
+permute, matmul, permute, cat -- the op sequence of the cited lines, with torch.gather standing in for
+grouping_operation, the one equivalence the reference itself asserts, group.py:92-96) and against the product's own
+unfused composition of the individual operators.
+  * indices, grouped features and centred / scaled coordinates: BIT-EXACT;
+  * rotated coordinates: |diff| <= 1e-6 (torch.matmul's accumulation order is cuBLAS's business);
+  * feature gradients: 1e-5 relative (float summation order), as for grouping_operation.
+"""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from graspbalance_b200 import group as gb_group
+from graspbalance_b200 import pointnet2_utils as pu
+from graspbalance_b200 import scenes
+
+pytestmark = pytest.mark.gpu
+
+
+def T(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def torch_group(features, idx):
+    """grouping_operation as an index gather (group.py:92-96 torch_grouping_operation)."""
+    B, C, N = features.shape
+    _, m, ns = idx.shape
+    return torch.gather(features, 2, idx.long().reshape(B, 1, m * ns).expand(-1, C, -1)).reshape(B, C, m, ns)
+
+
+def reference_query_and_group(idx, xyz, new_xyz, features, radius, normalize_xyz, use_xyz=True, rot=None):
+    """pointnet2_utils.py:178-207 / 281-308 with the index tensor given."""
+    xyz_trans = xyz.transpose(1, 2).contiguous()
+    grouped_xyz = torch_group(xyz_trans, idx)
+    grouped_xyz = grouped_xyz - new_xyz.transpose(1, 2).unsqueeze(-1)
+    if normalize_xyz:
+        grouped_xyz = grouped_xyz / radius
+    if rot is not None:
+        g = grouped_xyz.permute(0, 2, 3, 1).contiguous()
+        g = torch.matmul(g, rot)
+        grouped_xyz = g.permute(0, 3, 1, 2).contiguous()
+    if features is not None:
+        gf = torch_group(features, idx)
+        new_features = torch.cat([grouped_xyz, gf], dim=1) if use_xyz else gf
+    else:
+        new_features = grouped_xyz
+    return new_features, grouped_xyz
+
+
+def _inputs(dev, B, N, m, C, seed, kind="tabletop"):
+    xyz = scenes.scene_batch(range(seed, seed + B), N, kind)
+    rng = np.random.default_rng(seed)
+    pick = np.stack([rng.choice(N, m, replace=m > N) for _ in range(B)])
+    new_xyz = np.take_along_axis(xyz, pick[..., None], axis=1)
+    feats = rng.normal(size=(B, C, N)).astype(np.float32) if C else None
+    return xyz, new_xyz, feats
+
+
+@pytest.mark.parametrize("B,N,m,C,r,ns,norm", [(2, 20000, 128, 16, 0.05, 64, True), (2, 2048, 96, 5, 0.1, 32, False),
+                                              (1, 777, 33, 0, 0.2, 16, True), (2, 300, 20, 3, 0.3, 6, True),
+                                              (1, 4000, 64, 130, 0.04, 64, True)])
+def test_query_and_group_module_a(dev, B, N, m, C, r, ns, norm):
+    torch.backends.cuda.matmul.allow_tf32 = False
+    xyz, new_xyz, feats = _inputs(dev, B, N, m, C, 31)
+    x, q = T(xyz, dev), T(new_xyz, dev)
+    f = T(feats, dev).requires_grad_(True) if C else None
+    mod = pu.QueryAndGroup(r, ns, use_xyz=True, ret_grouped_xyz=True, normalize_xyz=norm)
+    out, gxyz = mod(x, q, f)
+    idx_want = oracle.ball_query(r, ns, xyz, new_xyz)
+    f_ref = T(feats, dev).requires_grad_(True) if C else None
+    want, want_xyz = reference_query_and_group(T(idx_want, dev), x, q, f_ref, r, norm)
+    assert out.shape == want.shape == (B, 3 + C, m, ns)
+    assert torch.equal(out, want)  # coordinates (subtract, multiply by 1/r) and gathered features: bit-exact
+    assert torch.equal(gxyz, want_xyz)
+    if C:
+        g = torch.randn(out.shape, device=dev, generator=torch.Generator(device=dev).manual_seed(1))
+        out.backward(g)
+        want.backward(g)
+        scale = f_ref.grad.abs().max().item()
+        assert (f.grad - f_ref.grad).abs().max().item() <= 1e-5 * max(scale, 1e-30)
+    # the unfused composition (taken when a coordinate tensor needs a gradient) gives the same result
+    xg = x.clone().requires_grad_(True)
+    out2, _ = mod(xg, q, T(feats, dev) if C else None)
+    assert torch.equal(out2.detach(), out.detach())
+
+
+@pytest.mark.parametrize("B,N,m,C,ns,hmax,rotate", [(2, 20000, 128, 0, 64, 0.04, True), (2, 3000, 50, 8, 16, 0.02, True),
+                                                   (1, 2048, 64, 4, 32, 0.01, False), (2, 500, 9, 0, 5, 0.04, True)])
+def test_cylinder_query_and_group(dev, B, N, m, C, ns, hmax, rotate):
+    torch.backends.cuda.matmul.allow_tf32 = False
+    xyz, new_xyz, feats = _inputs(dev, B, N, m, C, 41)
+    rng = np.random.default_rng(5)
+    v = rng.normal(size=(B, m, 3)).astype(np.float32)
+    rot = scenes.viewpoint_rotations(-v, rng.uniform(0, np.pi, (B, m)).astype(np.float32)).astype(np.float32)  # [B,m,3,3]
+    x, q, R = T(xyz, dev), T(new_xyz, dev), T(rot, dev)
+    f = T(feats, dev).requires_grad_(True) if C else None
+    mod = pu.CylinderQueryAndGroup(0.05, -0.02, hmax, ns, use_xyz=True, ret_grouped_xyz=True, rotate_xyz=rotate)
+    res = mod(x, q, R, f)
+    out, gxyz = res
+    idx_want = oracle.cylinder_query(0.05, -0.02, hmax, ns, xyz, new_xyz, np.ascontiguousarray(rot.reshape(B, m, 9)))
+    f_ref = T(feats, dev).requires_grad_(True) if C else None
+    want, want_xyz = reference_query_and_group(T(idx_want, dev), x, q, f_ref, 0.05, False, rot=R if rotate else None)
+    assert out.shape == want.shape
+    if rotate:
+        assert (out[:, :3] - want[:, :3]).abs().max().item() <= 1e-6
+        assert torch.equal(out[:, 3:], want[:, 3:])
+    else:
+        assert torch.equal(out, want)
+    assert (gxyz - want_xyz).abs().max().item() <= 1e-6
+    if C:
+        g = torch.randn(out.shape, device=dev, generator=torch.Generator(device=dev).manual_seed(2))
+        out.backward(g)
+        want.backward(g)
+        assert (f.grad - f_ref.grad).abs().max().item() <= 1e-5 * max(f_ref.grad.abs().max().item(), 1e-30)
+
+
+@pytest.mark.parametrize("B,N,C,r,ns,norm", [(2, 2048, 32, 0.08, 64, False), (2, 1024, 7, 0.2, 32, True), (1, 333, 4, 0.4, 10, False)])
+def test_query_and_group_module_b(dev, B, N, C, r, ns, norm):
+    xyz, _, feats = _inputs(dev, B, N, 1, C, 51)
+    x = T(xyz, dev)
+    f = T(feats, dev).requires_grad_(True)
+    mod = gb_group.QueryAndGroup(r, ns, normalize_dp=norm)
+    dp, fj = mod(x, x, f)  # InvResMLP: queries are the support points themselves (drp.py:62-67)
+    idx = T(oracle.ball_query(r, ns, xyz, xyz), dev)
+    f_ref = T(feats, dev).requires_grad_(True)
+    want, want_xyz = reference_query_and_group(idx, x, x, f_ref, r, norm, use_xyz=False)
+    assert torch.equal(dp, want_xyz)
+    assert torch.equal(fj, want)
+    g = torch.randn(fj.shape, device=dev, generator=torch.Generator(device=dev).manual_seed(3))
+    fj.backward(g)
+    want.backward(g)
+    assert (f.grad - f_ref.grad).abs().max().item() <= 1e-5 * max(f_ref.grad.abs().max().item(), 1e-30)
+    # unfused composition
+    xg = x.clone().requires_grad_(True)
+    dp2, fj2 = mod(xg, xg, T(feats, dev))
+    assert torch.equal(dp2.detach(), dp) and torch.equal(fj2, fj.detach())
+
+
+def test_strided_group_entries_match_the_contiguous_ones(dev):
+    """gb_group_fwd_strided / gb_group_bwd_strided against gb_group_fwd / gb_group_bwd on odd shapes (generic paths too)."""
+    from graspbalance_b200 import _ext as A, _lib
+    rng = np.random.default_rng(0)
+    for (B, C, N, m, ns, pad) in ((2, 6, 500, 17, 4, 3), (1, 5, 100, 7, 3, 2), (2, 16, 5000, 64, 16, 3), (1, 4, 20000, 32, 64, 5)):
+        feats = T(rng.normal(size=(B, C, N)).astype(np.float32), dev)
+        idx = T(rng.integers(0, N, (B, m, ns)).astype(np.int32), dev)
+        per = m * ns
+        want = A.group_points(feats, idx)
+        big = torch.full((B, pad + C, m, ns), -7.0, device=dev)
+        _lib.call("gb_group_fwd_strided", feats, feats.data_ptr(), idx.data_ptr(), big.data_ptr() + 4 * pad * per, B, C, N, m, ns,
+                  (pad + C) * per)
+        assert torch.equal(big[:, pad:], want) and bool((big[:, :pad] == -7.0).all())
+        gout = torch.randn((B, pad + C, m, ns), device=dev)
+        want_g = A.group_points_grad(gout[:, pad:].contiguous(), idx, N)
+        got = torch.empty((B, C, N), device=dev)
+        _lib.call("gb_group_bwd_strided", gout, gout.data_ptr() + 4 * pad * per, idx.data_ptr(), got.data_ptr(), B, C, N, m, ns,
+                  (pad + C) * per, 1)
+        assert (got - want_g).abs().max().item() <= 1e-5 * max(want_g.abs().max().item(), 1e-30)
