@@ -21,6 +21,12 @@ import sys
 import threading
 import time
 
+if "--impl" in sys.argv and "reference" in sys.argv:
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm is a CPU job that should use every host thread
+    # (numpy's BLAS pool reads the variable when numpy is imported, i.e. below)
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(os.cpu_count() or 1)
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))

@@ -253,23 +253,51 @@ __global__ void __launch_bounds__(kGridQueryWarps * 32, 5) grid_query_kernel(con
     z0 = grid_cell(qz + blo[2], h.oz, h.inv, h.gz), z1 = grid_cell(qz + bhi[2], h.oz, h.inv, h.gz);
   }
 
-  // ---- candidates: the cells of a (z, y) row are contiguous in the sorted array ----
-  for (int cz = z0; cz <= z1; ++cz) {
-    for (int cy = y0; cy <= y1; ++cy) {
-      const int row = (cz * h.gy + cy) * h.gx;
-      const int s0 = __ldg(cell_start + row + x0), s1 = __ldg(cell_start + row + x1 + 1);
-      for (int i = s0 + lane; i < s1; i += 64) {
-        const float4 p0 = __ldg(sorted + i);
-        const bool two = i + 32 < s1;
-        const float4 p1 = two ? __ldg(sorted + i + 32) : p0;
-        const bool h0 = CYL ? cyl_hit(r, qx, qy, qz, p0.x, p0.y, p0.z, radius2, hmin, hmax) : ball_hit(qx, qy, qz, p0.x, p0.y, p0.z, radius2);
-        const bool h1 = two && (CYL ? cyl_hit(r, qx, qy, qz, p1.x, p1.y, p1.z, radius2, hmin, hmax) : ball_hit(qx, qy, qz, p1.x, p1.y, p1.z, radius2));
-        if (h0) {
-          const int k = __float_as_int(p0.w);
-          atomicOr(&bm[k >> 5], 1u << (k & 31));
+  // ---- candidates: the cells of a (z, y) row are contiguous in the sorted array.  The rows of the box (32 at a time, one
+  // per lane: two independent cell_start loads each) are concatenated into one flat candidate range by a warp prefix sum, so
+  // every lane has a candidate in every step whatever the row lengths; a lane finds the row of its flat index with a
+  // cursor that only moves forward. ----
+  const int ny = y1 - y0 + 1, nrows = ny * (z1 - z0 + 1);
+  for (int rb = 0; rb < nrows; rb += 32) {
+    const int rr = rb + lane;
+    int s0 = 0, cnt = 0;
+    if (rr < nrows) {
+      const int dz = rr / ny;
+      const int row = ((z0 + dz) * h.gy + (y0 + rr - dz * ny)) * h.gx;
+      s0 = __ldg(cell_start + row + x0);
+      cnt = __ldg(cell_start + row + x1 + 1) - s0;
+    }
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int o = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += o;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    const int base = s0 - (incl - cnt);  // address of flat index f inside this lane's row = base + f
+    int cur = 0;                         // row of this lane's current flat index
+    for (int f0 = 0; f0 < total; f0 += 64) {
+      float4 p[2];
+      bool ok[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int f = f0 + 32 * u + lane;
+        ok[u] = f < total;
+        for (;;) {  // advance the cursor past the rows that end at or before f (empty rows included)
+          const int inc = __shfl_sync(0xffffffffu, incl, cur);
+          const bool adv = ok[u] && f >= inc;
+          if (!__any_sync(0xffffffffu, adv)) break;
+          cur += adv ? 1 : 0;
         }
-        if (h1) {
-          const int k = __float_as_int(p1.w);
+        const int a = __shfl_sync(0xffffffffu, base, cur) + f;
+        p[u] = ok[u] ? __ldg(sorted + a) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const bool hit = ok[u] && (CYL ? cyl_hit(r, qx, qy, qz, p[u].x, p[u].y, p[u].z, radius2, hmin, hmax)
+                                       : ball_hit(qx, qy, qz, p[u].x, p[u].y, p[u].z, radius2));
+        if (hit) {
+          const int k = __float_as_int(p[u].w);
           atomicOr(&bm[k >> 5], 1u << (k & 31));
         }
       }
