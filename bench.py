@@ -240,6 +240,7 @@ def main():
     ap.add_argument("--no-backward", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="run the sampling chain and the collision tests on the main stream")
     ap.add_argument("--cuda-profiler-range", action="store_true",
                     help="bracket the timed steps with cudaProfilerStart/Stop (for `ncu --profile-from-start off`)")
     args = ap.parse_args()
@@ -267,7 +268,7 @@ def main():
     B = args.batch
     scene_ids = sharding.scene_ids_for_rank(rank, world, B)
     host, offs = make_host_inputs(scene_ids)
-    pipe = pipeline.OpPipeline(B, N_POINTS, dev, seed=rank, backward=not args.no_backward)
+    pipe = pipeline.OpPipeline(B, N_POINTS, dev, seed=rank, backward=not args.no_backward, overlap=not args.no_overlap)
     gather_buf = torch.empty((world * B, pipeline.NUM_SEED + 6 * pipeline.NUM_GRASP), dtype=torch.int64, device=dev) if world > 1 else None
 
     def step(resident, inputs=None):
@@ -314,12 +315,11 @@ def main():
     for _ in range(args.warmup):
         step(True, resident_inputs)
 
-    # ---- device-resident throughput ("value"), with per-launch events for the roofline ----
+    # ---- device-resident throughput ("value") ----
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
-    _lib.PROFILER = {}
     launches0 = _lib.launch_count()
     if args.cuda_profiler_range:
         torch.cuda.synchronize()
@@ -328,9 +328,16 @@ def main():
     if args.cuda_profiler_range:
         torch.cuda.profiler.stop()
     launches = _lib.launch_count() - launches0
-    prof, _lib.PROFILER = _lib.PROFILER, None
     clocks = sampler.stop(tw0, tw1) if rank == 0 else None
     value = world * B * args.steps / (ms * 1e-3)
+
+    # ---- roofline pass: the same K steps again with CUDA events around every libgbops call, on ONE stream (the side
+    # streams of the overlapped schedule would make the bracketed durations overlap each other) ----
+    _lib.PROFILER = {}
+    overlap, pipe.overlap = pipe.overlap, False
+    ms_prof, _, _ = timed(args.steps, True, resident_inputs)
+    pipe.overlap = overlap
+    prof, _lib.PROFILER = _lib.PROFILER, None
 
     # ---- e2e: host buffers in, results out, every step ----
     e2e = None
@@ -353,7 +360,11 @@ def main():
     fam = {}
     for name, evs in prof.items():
         tot_ms = sum(a.elapsed_time(b) for a, b, _ in evs)
-        fam[name] = {"launches": len(evs), "ms": tot_ms, "bytes": sum(x for _, _, x in evs)}
+        base = name.replace("_set", "").replace("_strided", "")  # entry-point variants of one op share its kernels
+        f = fam.setdefault(base, {"launches": 0, "ms": 0.0, "bytes": 0})
+        f["launches"] += len(evs)
+        f["ms"] += tot_ms
+        f["bytes"] += sum(x for _, _, x in evs)
     total_ms = sum(f["ms"] for f in fam.values()) or 1.0
     per_op = []
     for name, f in sorted(fam.items(), key=lambda kv: -kv[1]["ms"]):
@@ -361,14 +372,21 @@ def main():
         per_op.append({"kernel": name, "launches_per_step": f["launches"] / args.steps, "ms_per_step": f["ms"] / args.steps,
                        "share": f["ms"] / total_ms, "achieved_gbs": gbs, "hbm_frac": gbs / peak})
     top = per_op[0]
-    traffic = None
+    # dram__bytes_read + dram__bytes_write per launch of that family, from the committed ncu capture of this same step
+    # (profiles/dram_traffic.json, written by tests/ubench/dram_traffic.py); null when the capture is for another batch size
+    traffic, algo_per_launch = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "dram_traffic.json")) as f:
-            traffic = json.load(f).get(top["kernel"])
+            tj = json.load(f)
+        if tj.get("batch") == B and tj.get("backward") == (not args.no_backward):
+            traffic = tj["families"].get(top["kernel"], {}).get("dram_bytes_per_launch")
     except Exception:
         pass
+    if top["launches_per_step"] > 0:
+        algo_per_launch = fam[top["kernel"]]["bytes"] / fam[top["kernel"]]["launches"]
     roofline = {"kernel": top["kernel"], "bound": "hbm", "achieved": top["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": top["achieved_gbs"] / peak, "traffic": traffic, "peak_source": peak_src,
+                "frac": top["achieved_gbs"] / peak, "traffic": traffic, "algorithmic_bytes_per_launch": algo_per_launch,
+                "peak_source": peak_src,
                 "avg_launch_us": top["ms_per_step"] / max(top["launches_per_step"], 1e-9) * 1e3, "share_of_step": top["share"]}
 
     cpu = None
@@ -386,9 +404,11 @@ def main():
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args), "scenes_per_gpu": B, "n_points": N_POINTS, "parallelism": f"scene-sharded x{world}",
+                       "streams": "sampling chain + collision tests on side streams" if pipe.overlap else "single stream",
                        "l2": "per-step working set (>10 GB of grouped features) exceeds the 126 MB L2; no explicit flush",
                        "algorithmic_bytes_per_scene": int(sum(algo.values()))},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "roofline_pass_ms_per_step": ms_prof / args.steps,
             "pipeline_hbm_frac": (sum(algo.values()) * world * B * args.steps / (ms * 1e-3) / 1e9) / (peak * world),
             "per_op": per_op}
     print(json.dumps(line), flush=True)

@@ -44,8 +44,14 @@ def _randn(shape, gen, device):
 class OpPipeline:
     """Holds the stand-in feature / gradient tensors (allocated once, outside any timed region) and runs the chain."""
 
-    def __init__(self, batch, n_points=20000, device="cuda", seed=0, backward=True):
+    def __init__(self, batch, n_points=20000, device="cuda", seed=0, backward=True, overlap=True):
         self.B, self.N, self.device, self.backward = batch, n_points, torch.device(device), backward
+        # overlap: the sampling chain (4 x FPS + gather: latency-bound, a few warps per SM, depends on xyz only) and the
+        # collision tests (independent of everything else) run on side streams next to the bandwidth-bound grouping work
+        self.overlap = overlap and self.device.type == "cuda"
+        if self.overlap:
+            self._fps_stream = torch.cuda.Stream(self.device)
+            self._col_stream = torch.cuda.Stream(self.device)
         gen = torch.Generator(device=self.device).manual_seed(seed)
         B = batch
         self.sa_groupers = [pu.QueryAndGroup(r, ns, use_xyz=True, ret_grouped_xyz=True, normalize_xyz=True)
@@ -57,7 +63,8 @@ class OpPipeline:
         self.sa_in_feats = [None] + [_randn((B, c, SA_SPECS[i - 1][0]), gen, self.device) for i, (_, _, _, c) in
                                      enumerate(SA_SPECS) if i > 0]
         self.irm_feats = [_randn((B, c, SA_SPECS[i][0]), gen, self.device) for i, (_, c, _, _) in enumerate(IRM_SPECS)]
-        self.sa_grads = [None] + [_randn((B, SA_SPECS[i][3], SA_SPECS[i][0], SA_SPECS[i][2]), gen, self.device)
+        # upstream gradient of the whole (3+C)-channel grouped tensor, as the SharedMLP's backward hands it over
+        self.sa_grads = [None] + [_randn((B, 3 + SA_SPECS[i][3], SA_SPECS[i][0], SA_SPECS[i][2]), gen, self.device)
                                   for i in range(1, 4)]
         self.irm_grads = [_randn((B, c, SA_SPECS[i][0], ns), gen, self.device) for i, (_, c, _, ns) in enumerate(IRM_SPECS)]
         self.fp_feats = [_randn((B, 256, 256), gen, self.device), _randn((B, 256, 512), gen, self.device),
@@ -84,15 +91,50 @@ class OpPipeline:
         Returns a dict of the per-scene outputs a caller would keep."""
         bw = self.backward
         out = {}
+        main = torch.cuda.current_stream(self.device) if self.overlap else None
+
+        def sample(cur, npoint):  # furthest_point_sample + gather_operation of one SA module (pointnet2_modules.py:151-158)
+            inds = pu.furthest_point_sample(cur, npoint)
+            return inds, pu.gather_operation(cur.transpose(1, 2).contiguous(), inds).transpose(1, 2).contiguous()
+
+        def collide():
+            return torch.stack([collision_counts(grasps["scene_points"][b], grasps["T"][b], grasps["R"][b], grasps["thr"][b])
+                                for b in range(len(grasps["scene_points"]))])
+
+        samples, col_done = [], None
+        if self.overlap:
+            start = torch.cuda.Event()
+            start.record(main)
+            self._fps_stream.wait_event(start)
+            with torch.cuda.stream(self._fps_stream):
+                cur = xyz
+                for (npoint, _, _, _) in SA_SPECS:
+                    inds, new_xyz = sample(cur, npoint)
+                    ev = torch.cuda.Event()
+                    ev.record(self._fps_stream)
+                    inds.record_stream(main), new_xyz.record_stream(main)
+                    samples.append((inds, new_xyz, ev))
+                    cur = new_xyz
+            if grasps is not None:
+                self._col_stream.wait_event(start)
+                with torch.cuda.stream(self._col_stream):
+                    out["collision_counts"] = collide()
+                    out["collision_counts"].record_stream(main)
+                    col_done = torch.cuda.Event()
+                    col_done.record(self._col_stream)
+
         cur_xyz, level_xyz = xyz, []
         for lvl, (npoint, radius, nsample, c_in) in enumerate(SA_SPECS):
             # ---- SA module (variant A) ----
-            inds = pu.furthest_point_sample(cur_xyz, npoint)
-            new_xyz = pu.gather_operation(cur_xyz.transpose(1, 2).contiguous(), inds).transpose(1, 2).contiguous()
+            if self.overlap:
+                inds, new_xyz, ev = samples[lvl]
+                main.wait_event(ev)
+            else:
+                inds, new_xyz = sample(cur_xyz, npoint)
             feats = self.sa_in_feats[lvl]
             grouped, _ = self.sa_groupers[lvl](cur_xyz, new_xyz, feats)
             if bw and feats is not None:
-                grouped[:, 3:].backward(self.sa_grads[lvl])
+                grouped.backward(self.sa_grads[lvl])
             if lvl == 0:
                 out["sa1_inds"] = inds
             # ---- InvResMLP blocks (variant B) ----
@@ -109,7 +151,7 @@ class OpPipeline:
         self._interp(sa3_xyz, sa4_xyz, self.fp_feats[0], self.fp_grads[0] if bw else None)
         self._interp(sa2_xyz, sa3_xyz, self.fp_feats[1], self.fp_grads[1] if bw else None)
         up = self._interp(xyz, sa2_xyz, self.fp_feats[2], self.fp_grads[2] if bw else None)
-        out["up_checksum"] = up[:, :, ::997].sum()
+        out["up_checksum"] = up[:, :4, :256].sum()  # small contiguous slices: the checksums only give the step a result to return
         seed_xyz = sa2_xyz  # fp2_xyz: 1024 seeds (drp.py:301-303)
         out["seed_inds"] = out["sa1_inds"][:, :NUM_SEED]
         # ---- grasp crop: 4 radii x 4 depths cylinder query + group ----
@@ -117,16 +159,16 @@ class OpPipeline:
         for groupers in self.crop_groupers:
             for gq in groupers:
                 g = gq(xyz, seed_xyz, view_rot)  # [B,3,1024,64]
-                s = g[:, :, :, 0].sum()
+                s = g[:, :, :4].sum()
                 crop_sum = s if crop_sum is None else crop_sum + s
         out["crop_checksum"] = crop_sum
         # ---- collision test ----
-        if grasps is not None:
-            out["collision_counts"] = torch.stack([
-                collision_counts(grasps["scene_points"][b], grasps["T"][b], grasps["R"][b], grasps["thr"][b])
-                for b in range(len(grasps["scene_points"]))])
+        if col_done is not None:
+            main.wait_event(col_done)
+        elif grasps is not None:
+            out["collision_counts"] = collide()
         if bw:
-            out["grad_checksum"] = sum(t.grad[:, :, ::61].sum() for t in self.sa_in_feats[1:] + self.irm_feats + self.fp_feats)
+            out["grad_checksum"] = sum(t.grad[:, :4, :64].sum() for t in self.sa_in_feats[1:] + self.irm_feats + self.fp_feats)
             for t in self.sa_in_feats[1:] + self.irm_feats + self.fp_feats:
                 t.grad = None
         return out

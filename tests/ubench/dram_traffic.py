@@ -1,0 +1,60 @@
+#!/usr/bin/env python
+"""profiles/dram_traffic.json from an ncu capture of one bench step:
+
+    ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
+        --profile-from-start off --csv --log-file gpurun_out/<tag>_dram.csv python bench.py --steps 1 --warmup 3 ...
+    python tests/ubench/dram_traffic.py gpurun_out/<tag>_dram.csv 32 > profiles/dram_traffic.json
+
+Every launch is attributed to the libgbops entry-point family that issued it (sort / grid-build helper launches go to
+the family of the main kernel that follows them); dram_bytes_per_launch = (read + write bytes of the family) / (number
+of its main launches), i.e. per entry-point call, like bench.py's `achieved`."""
+import csv
+import json
+import re
+import sys
+
+MAIN = [  # (regex on the kernel name, family)
+    (r"group_fwd_kernel|group_fwd_generic", "gb_group_fwd"),
+    (r"seg_dense_kernel<[^>]*, ?\(?int\)?1, ?\(?bool\)?(0|false)>|seg_accum_kernel<[^>]*, ?\(?int\)?1, ?\(?bool\)?(0|false)>|group_bwd_kernel|group_bwd_generic", "gb_group_bwd"),
+    (r"seg_dense_kernel<[^>]*, ?\(?int\)?3, ?\(?bool\)?(1|true)>|seg_accum_kernel<[^>]*, ?\(?int\)?3, ?\(?bool\)?(1|true)>|interp_bwd_kernel", "gb_three_interp_bwd"),
+    (r"interp_fwd", "gb_three_interp_fwd"),
+    (r"grid_query_kernel<\(?bool\)?(1|true)>|query_kernel<\(?bool\)?(1|true)", "gb_cylinder_query"),
+    (r"grid_query_kernel<\(?bool\)?(0|false)>|query_kernel<\(?bool\)?(0|false)", "gb_ball_query"),
+    (r"fps_", "gb_fps"), (r"three_nn", "gb_three_nn"), (r"collision", "gb_collision_counts"), (r"group_xyz", "gb_group_xyz"),
+    (r"gather_", "gb_gather"), (r"knn", "gb_knn"),
+]
+HELPER = r"seg_sort|grid_build"
+
+
+def main():
+    path, batch = sys.argv[1], int(sys.argv[2])
+    launches = {}
+    for r in csv.DictReader(l for l in open(path) if l.startswith('"')):
+        d = launches.setdefault(int(r["ID"]), {"name": r["Kernel Name"]})
+        d[r["Metric Name"]] = float(r["Metric Value"].replace(",", "")) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(r["Metric Unit"], 1)
+    fams, pending = {}, 0.0
+    for i in sorted(launches):
+        d = launches[i]
+        nbytes = d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0)
+        if not d["name"].startswith(("void gb::", "gb::")):
+            continue
+        if re.search(HELPER, d["name"]):
+            pending += nbytes
+            continue
+        for rx, fam in MAIN:
+            if re.search(rx, d["name"]):
+                f = fams.setdefault(fam, {"launches": 0, "dram_bytes": 0.0})
+                # the full-scan query kernel launched behind a grid query is the same entry-point call
+                if not (fam in ("gb_ball_query", "gb_cylinder_query") and "grid_query" not in d["name"] and f.get("_grid_pending")):
+                    f["launches"] += 1
+                f["_grid_pending"] = "grid_query" in d["name"]
+                f["dram_bytes"] += nbytes + pending
+                pending = 0.0
+                break
+    out = {"batch": batch, "backward": True, "source": path, "families": {
+        k: {"launches": v["launches"], "dram_bytes_per_launch": v["dram_bytes"] / max(v["launches"], 1)} for k, v in sorted(fams.items())}}
+    print(json.dumps(out, indent=1))
+
+
+if __name__ == "__main__":
+    main()
