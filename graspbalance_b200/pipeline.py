@@ -52,6 +52,7 @@ class OpPipeline:
         if self.overlap:
             self._fps_stream = torch.cuda.Stream(self.device)
             self._col_stream = torch.cuda.Stream(self.device)
+            self._aux_stream = torch.cuda.Stream(self.device)  # grasp crops + FP/up-sampling chain (compute-bound scans)
         gen = torch.Generator(device=self.device).manual_seed(seed)
         B = batch
         self.sa_groupers = [pu.QueryAndGroup(r, ns, use_xyz=True, ret_grouped_xyz=True, normalize_xyz=True)
@@ -84,6 +85,24 @@ class OpPipeline:
         if grad is not None:
             out.backward(grad)
         return out
+
+    def _crops(self, xyz, view_rot, sa2_xyz, out):
+        # ---- grasp crop: 4 radii x 4 depths cylinder query + group (seeds = fp2_xyz: 1024 points, drp.py:301-303) ----
+        crop_sum = None
+        for groupers in self.crop_groupers:
+            for gq in groupers:
+                g = gq(xyz, sa2_xyz, view_rot)  # [B,3,1024,64]
+                s = g[:, :, :4].sum()  # small contiguous slices: the checksums only give the step a result to return
+                crop_sum = s if crop_sum is None else crop_sum + s
+        out["crop_checksum"] = crop_sum
+
+    def _interpolation(self, xyz, sa2_xyz, sa3_xyz, sa4_xyz, out):
+        bw = self.backward
+        # ---- FP modules + up-sampling of the seed features to the full cloud ----
+        self._interp(sa3_xyz, sa4_xyz, self.fp_feats[0], self.fp_grads[0] if bw else None)
+        self._interp(sa2_xyz, sa3_xyz, self.fp_feats[1], self.fp_grads[1] if bw else None)
+        up = self._interp(xyz, sa2_xyz, self.fp_feats[2], self.fp_grads[2] if bw else None)
+        out["up_checksum"] = up[:, :4, :256].sum()
 
     def run(self, xyz, view_rot, grasps=None):
         """xyz [B,N,3] f32 CUDA; view_rot [B,1024,3,3] f32 CUDA (approach frames of the seeds); grasps = optional dict of
@@ -123,6 +142,20 @@ class OpPipeline:
                     col_done = torch.cuda.Event()
                     col_done.record(self._col_stream)
 
+        aux_done = None
+        if self.overlap:
+            # the 16 cylinder-query crops and the three interpolation chains need only the sampled coordinates: they run on
+            # a third stream next to the SA / InvResMLP grouping work of the main stream
+            self._aux_stream.wait_event(samples[1][2])
+            with torch.cuda.stream(self._aux_stream):
+                self._crops(xyz, view_rot, samples[1][1], out)
+                self._aux_stream.wait_event(samples[3][2])
+                self._interpolation(xyz, samples[1][1], samples[2][1], samples[3][1], out)
+                for k in ("up_checksum", "crop_checksum"):
+                    out[k].record_stream(main)
+                aux_done = torch.cuda.Event()
+                aux_done.record(self._aux_stream)
+
         cur_xyz, level_xyz = xyz, []
         for lvl, (npoint, radius, nsample, c_in) in enumerate(SA_SPECS):
             # ---- SA module (variant A) ----
@@ -147,21 +180,12 @@ class OpPipeline:
             cur_xyz = new_xyz
             level_xyz.append(new_xyz)
         sa1_xyz, sa2_xyz, sa3_xyz, sa4_xyz = level_xyz
-        # ---- FP modules + up-sampling of the seed features to the full cloud ----
-        self._interp(sa3_xyz, sa4_xyz, self.fp_feats[0], self.fp_grads[0] if bw else None)
-        self._interp(sa2_xyz, sa3_xyz, self.fp_feats[1], self.fp_grads[1] if bw else None)
-        up = self._interp(xyz, sa2_xyz, self.fp_feats[2], self.fp_grads[2] if bw else None)
-        out["up_checksum"] = up[:, :4, :256].sum()  # small contiguous slices: the checksums only give the step a result to return
-        seed_xyz = sa2_xyz  # fp2_xyz: 1024 seeds (drp.py:301-303)
         out["seed_inds"] = out["sa1_inds"][:, :NUM_SEED]
-        # ---- grasp crop: 4 radii x 4 depths cylinder query + group ----
-        crop_sum = None
-        for groupers in self.crop_groupers:
-            for gq in groupers:
-                g = gq(xyz, seed_xyz, view_rot)  # [B,3,1024,64]
-                s = g[:, :, :4].sum()
-                crop_sum = s if crop_sum is None else crop_sum + s
-        out["crop_checksum"] = crop_sum
+        if not self.overlap:
+            self._interpolation(xyz, sa2_xyz, sa3_xyz, sa4_xyz, out)
+            self._crops(xyz, view_rot, sa2_xyz, out)
+        if aux_done is not None:
+            main.wait_event(aux_done)
         # ---- collision test ----
         if col_done is not None:
             main.wait_event(col_done)
