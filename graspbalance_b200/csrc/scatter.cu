@@ -346,22 +346,27 @@ __global__ void __launch_bounds__(kSegThreads, 1) seg_accum_kernel(const float *
 //
 // Sort output per tile ("blob", one bulk copy): tp[2048] u16 (tile-local entry of each sorted position) | start[NS] u16
 // (first sorted position of every target, start[n] = number of valid entries; NS = n + 1 rounded up to 8).
+// Entries per tile: 2048 (group) or 3 x 2040 (interpolate: 2040 points, 8160-byte row pieces for the bulk copies).
+__host__ __device__ constexpr int seg_dense_tile(int div) { return div == 3 ? 6120 : 2048; }
+__host__ __device__ constexpr int seg_dense_stride(int div) { return div == 3 ? 6144 : 2048; }  // tp slots per blob
 __host__ __device__ inline int seg_dense_ns(int n) { return (n + 1 + 7) & ~7; }
-__host__ __device__ inline size_t seg_dense_blob(int n) { return (size_t)kSegTileStride * 2 + (size_t)seg_dense_ns(n) * 2; }
+__host__ __device__ inline size_t seg_dense_blob(int n, int div) { return (size_t)seg_dense_stride(div) * 2 + (size_t)seg_dense_ns(n) * 2; }
 
 // grid (tiles, b); dynamic smem (n + 32) ints
-__global__ void __launch_bounds__(kSegSortThreads) seg_sort_dense_kernel(const int *__restrict__ idx, int per, int n, int T,
+template <int DIV>
+__global__ void __launch_bounds__(kSegSortThreads) seg_sort_dense_kernel(const int *__restrict__ idx, int per, int n,
                                                                          unsigned char *__restrict__ blobs) {
+  constexpr int T = seg_dense_tile(DIV), kStride = seg_dense_stride(DIV);
   extern __shared__ int s_bins[];
   int *wsum = s_bins + n;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t ibase = (size_t)blockIdx.y * per + (size_t)blockIdx.x * T;
-  unsigned short *tp = reinterpret_cast<unsigned short *>(blobs + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * seg_dense_blob(n));
-  unsigned short *start = tp + kSegTileStride;
+  unsigned short *tp = reinterpret_cast<unsigned short *>(blobs + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * seg_dense_blob(n, DIV));
+  unsigned short *start = tp + kStride;
   const int tc = min(T, per - (int)blockIdx.x * T);
   for (int i = tid; i < n; i += kSegSortThreads) s_bins[i] = 0;
   __syncthreads();
-  constexpr int R = kSegTileStride / kSegSortThreads;
+  constexpr int R = kStride / kSegSortThreads;
   int key[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) {
@@ -414,7 +419,7 @@ __global__ void __launch_bounds__(kSegSortThreads) seg_sort_dense_kernel(const i
     const int e = r * kSegSortThreads + tid;
     if (key[r] >= 0) tp[atomicAdd(&s_bins[key[r]], 1)] = (unsigned short)e;
   }
-  for (int e = total + tid; e < kSegTileStride; e += kSegSortThreads) tp[e] = 0;
+  for (int e = total + tid; e < kStride; e += kSegSortThreads) tp[e] = 0;
 }
 
 // grid b * chunks, kSegThreads threads.  Thread -> target slot ts = tid % NT and channel group cg = tid / NT
@@ -425,7 +430,7 @@ __global__ void __launch_bounds__(kSegThreads, 1) seg_dense_kernel(const float *
                                                                    const float *__restrict__ weight, float *__restrict__ grad, int c,
                                                                    int n, int per_src, int tiles, int chunks, int nt_log2, int stages,
                                                                    int stage_bytes, int bulk_ok, int overwrite, size_t src_stride) {
-  constexpr int T = seg_tile(DIV), TP = T / DIV;
+  constexpr int T = seg_dense_tile(DIV), TP = T / DIV;
   extern __shared__ __align__(128) unsigned char s_raw[];
   __shared__ uint64_t full[kSegMaxStages];
   const int tid = threadIdx.x;
@@ -435,7 +440,7 @@ __global__ void __launch_bounds__(kSegThreads, 1) seg_dense_kernel(const float *
   const int ch0 = chunk * CC;
   const int nch = min(CC, c - ch0);
   const float *g = src + (size_t)scene * src_stride + (size_t)ch0 * per_src;
-  const size_t blob = seg_dense_blob(n);
+  const size_t blob = seg_dense_blob(n, DIV);
   const unsigned char *bsrc = blobs + (size_t)scene * tiles * blob;
   const float *wsrc = WEIGHTED ? weight + (size_t)scene * per_src * DIV : nullptr;
   const int wt_off = CC * TP * 4, blob_off = wt_off + (WEIGHTED ? T * 4 : 0);
@@ -490,7 +495,7 @@ __global__ void __launch_bounds__(kSegThreads, 1) seg_dense_kernel(const float *
     const float *gt = reinterpret_cast<const float *>(st) + (size_t)cg * CT * TP;
     const float *wt = reinterpret_cast<const float *>(st + wt_off);
     const unsigned short *tp = reinterpret_cast<const unsigned short *>(st + blob_off);
-    const unsigned short *start = tp + kSegTileStride;
+    const unsigned short *start = tp + seg_dense_stride(DIV);
 #pragma unroll
     for (int j = 0; j < TPT; ++j) {
       const int k = ts + j * NT;
@@ -569,9 +574,9 @@ static int launch_seg_accum(const float *src, size_t src_stride, const unsigned 
 template <int CT, int TPT, int DIV, bool WEIGHTED>
 static int launch_seg_dense(const float *src, size_t src_stride, const unsigned char *blobs, const float *weight, float *grad, int b, int c,
                             int n, int per_src, int tiles, int nt_log2, int bulk_ok, int overwrite, cudaStream_t s) {
-  constexpr int T = seg_tile(DIV), TP = T / DIV;
+  constexpr int T = seg_dense_tile(DIV), TP = T / DIV;
   const int G = kSegThreads >> nt_log2, CC = CT * G;
-  const size_t stage_bytes = ((size_t)CC * TP * 4 + (WEIGHTED ? (size_t)T * 4 : 0) + seg_dense_blob(n) + 127) & ~(size_t)127;
+  const size_t stage_bytes = ((size_t)CC * TP * 4 + (WEIGHTED ? (size_t)T * 4 : 0) + seg_dense_blob(n, DIV) + 127) & ~(size_t)127;
   int stages = (int)(kSegSmemBudget / stage_bytes);
   stages = stages > kSegMaxStages ? kSegMaxStages : stages;
   if (stages > tiles) stages = tiles;
@@ -592,15 +597,16 @@ constexpr int kSegDenseMaxN = 4096;
 // dense mode (thread-owned targets, register accumulators) for n <= 4096
 static int seg_scatter_dense(const float *src, size_t src_stride, const int *key, const float *weight, float *grad, int b, int c, int n,
                              size_t entries, int div, int overwrite, cudaStream_t s) {
-  const int T = seg_tile(div), TP = T / div;
+  const int T = seg_dense_tile(div), TP = T / div;
   const int per_src = (int)(entries / div);
   const int tiles = (int)((entries + T - 1) / T);
-  const size_t blob = seg_dense_blob(n);
+  const size_t blob = seg_dense_blob(n, div);
   unsigned char *blobs = nullptr;
   cudaError_t e = scratch_alloc((void **)&blobs, (size_t)b * tiles * blob, s);
   if (e != cudaSuccess) return (int)e;
   const size_t sort_smem = ((size_t)n + 32) * sizeof(int);
-  seg_sort_dense_kernel<<<dim3((unsigned)tiles, b), kSegSortThreads, sort_smem, s>>>(key, (int)entries, n, T, blobs);
+  if (div == 3) seg_sort_dense_kernel<3><<<dim3((unsigned)tiles, b), kSegSortThreads, sort_smem, s>>>(key, (int)entries, n, blobs);
+  else seg_sort_dense_kernel<1><<<dim3((unsigned)tiles, b), kSegSortThreads, sort_smem, s>>>(key, (int)entries, n, blobs);
   count_launch();
   int rc = finish_launch();
   if (!rc) {

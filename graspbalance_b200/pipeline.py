@@ -134,28 +134,8 @@ class OpPipeline:
                     inds.record_stream(main), new_xyz.record_stream(main)
                     samples.append((inds, new_xyz, ev))
                     cur = new_xyz
-            if grasps is not None:
-                self._col_stream.wait_event(start)
-                with torch.cuda.stream(self._col_stream):
-                    out["collision_counts"] = collide()
-                    out["collision_counts"].record_stream(main)
-                    col_done = torch.cuda.Event()
-                    col_done.record(self._col_stream)
 
         aux_done = None
-        if self.overlap:
-            # the 16 cylinder-query crops and the three interpolation chains need only the sampled coordinates: they run on
-            # a third stream next to the SA / InvResMLP grouping work of the main stream
-            self._aux_stream.wait_event(samples[1][2])
-            with torch.cuda.stream(self._aux_stream):
-                self._crops(xyz, view_rot, samples[1][1], out)
-                self._aux_stream.wait_event(samples[3][2])
-                self._interpolation(xyz, samples[1][1], samples[2][1], samples[3][1], out)
-                for k in ("up_checksum", "crop_checksum"):
-                    out[k].record_stream(main)
-                aux_done = torch.cuda.Event()
-                aux_done.record(self._aux_stream)
-
         cur_xyz, level_xyz = xyz, []
         for lvl, (npoint, radius, nsample, c_in) in enumerate(SA_SPECS):
             # ---- SA module (variant A) ----
@@ -179,6 +159,26 @@ class OpPipeline:
                     fj.backward(self.irm_grads[lvl])
             cur_xyz = new_xyz
             level_xyz.append(new_xyz)
+            if self.overlap and lvl == 0:
+                # Host enqueue order = priority: the sampling chain and level 0 of the main stream are on the critical path
+                # and were enqueued first; the independent side work follows.  Collision tests: own stream.  The 16
+                # cylinder-query crops and the three interpolation chains need only the sampled coordinates: aux stream.
+                if grasps is not None:
+                    self._col_stream.wait_event(start)
+                    with torch.cuda.stream(self._col_stream):
+                        out["collision_counts"] = collide()
+                        out["collision_counts"].record_stream(main)
+                        col_done = torch.cuda.Event()
+                        col_done.record(self._col_stream)
+                self._aux_stream.wait_event(samples[1][2])
+                with torch.cuda.stream(self._aux_stream):
+                    self._crops(xyz, view_rot, samples[1][1], out)
+                    self._aux_stream.wait_event(samples[3][2])
+                    self._interpolation(xyz, samples[1][1], samples[2][1], samples[3][1], out)
+                    for k in ("up_checksum", "crop_checksum"):
+                        out[k].record_stream(main)
+                    aux_done = torch.cuda.Event()
+                    aux_done.record(self._aux_stream)
         sa1_xyz, sa2_xyz, sa3_xyz, sa4_xyz = level_xyz
         out["seed_inds"] = out["sa1_inds"][:, :NUM_SEED]
         if not self.overlap:
