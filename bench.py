@@ -361,16 +361,22 @@ def main():
     for name, evs in prof.items():
         tot_ms = sum(a.elapsed_time(b) for a, b, _ in evs)
         base = name.replace("_set", "").replace("_strided", "")  # entry-point variants of one op share its kernels
-        f = fam.setdefault(base, {"launches": 0, "ms": 0.0, "bytes": 0})
+        f = fam.setdefault(base, {"launches": 0, "ms": 0.0, "bytes": 0, "big": None})
         f["launches"] += len(evs)
         f["ms"] += tot_ms
         f["bytes"] += sum(x for _, _, x in evs)
+        for a, b, x in evs:  # the launch that moves the most bytes: small launches of a family are latency-bound
+            if f["big"] is None or x > f["big"][0]:
+                f["big"] = (x, a.elapsed_time(b))
     total_ms = sum(f["ms"] for f in fam.values()) or 1.0
     per_op = []
     for name, f in sorted(fam.items(), key=lambda kv: -kv[1]["ms"]):
         gbs = f["bytes"] / (f["ms"] * 1e-3) / 1e9 if f["ms"] > 0 else 0.0
+        big_gbs = f["big"][0] / (f["big"][1] * 1e-3) / 1e9 if f["big"] and f["big"][1] > 0 else 0.0
         per_op.append({"kernel": name, "launches_per_step": f["launches"] / args.steps, "ms_per_step": f["ms"] / args.steps,
-                       "share": f["ms"] / total_ms, "achieved_gbs": gbs, "hbm_frac": gbs / peak})
+                       "share": f["ms"] / total_ms, "achieved_gbs": gbs, "hbm_frac": gbs / peak,
+                       "largest_launch": {"algorithmic_bytes": int(f["big"][0]) if f["big"] else 0,
+                                          "us": f["big"][1] * 1e3 if f["big"] else 0.0, "hbm_frac": big_gbs / peak}})
     top = per_op[0]
     # dram__bytes_read + dram__bytes_write per launch of that family, from the committed ncu capture of this same step
     # (profiles/dram_traffic.json, written by tests/ubench/dram_traffic.py); null when the capture is for another batch size

@@ -15,11 +15,11 @@ import sys
 
 MAIN = [  # (regex on the kernel name, family)
     (r"group_fwd_kernel|group_fwd_generic", "gb_group_fwd"),
-    (r"seg_dense_kernel<[^>]*, ?\(?int\)?1, ?\(?bool\)?(0|false)>|seg_accum_kernel<[^>]*, ?\(?int\)?1, ?\(?bool\)?(0|false)>|group_bwd_kernel|group_bwd_generic", "gb_group_bwd"),
-    (r"seg_dense_kernel<[^>]*, ?\(?int\)?3, ?\(?bool\)?(1|true)>|seg_accum_kernel<[^>]*, ?\(?int\)?3, ?\(?bool\)?(1|true)>|interp_bwd_kernel", "gb_three_interp_bwd"),
+    (r"seg_dense_kernel<[^>]*, ?(\(int\))?1, ?(\(bool\))?(0|false)>|seg_accum_kernel<[^>]*, ?(\(int\))?1, ?(\(bool\))?(0|false)>|group_bwd_kernel|group_bwd_generic", "gb_group_bwd"),
+    (r"seg_dense_kernel<[^>]*, ?(\(int\))?3, ?(\(bool\))?(1|true)>|seg_accum_kernel<[^>]*, ?(\(int\))?3, ?(\(bool\))?(1|true)>|interp_bwd_kernel", "gb_three_interp_bwd"),
     (r"interp_fwd", "gb_three_interp_fwd"),
-    (r"grid_query_kernel<\(?bool\)?(1|true)>|query_kernel<\(?bool\)?(1|true)", "gb_cylinder_query"),
-    (r"grid_query_kernel<\(?bool\)?(0|false)>|query_kernel<\(?bool\)?(0|false)", "gb_ball_query"),
+    (r"grid_query_kernel<(\(bool\))?(1|true)>|query_kernel<(\(bool\))?(1|true)", "gb_cylinder_query"),
+    (r"grid_query_kernel<(\(bool\))?(0|false)>|query_kernel<(\(bool\))?(0|false)", "gb_ball_query"),
     (r"fps_", "gb_fps"), (r"three_nn", "gb_three_nn"), (r"collision", "gb_collision_counts"), (r"group_xyz", "gb_group_xyz"),
     (r"gather_", "gb_gather"), (r"knn", "gb_knn"),
 ]
