@@ -347,21 +347,25 @@ __global__ void __launch_bounds__(kSegThreads, 1) seg_accum_kernel(const float *
 // Sort output per tile ("blob", one bulk copy): tp[2048] u16 (tile-local entry of each sorted position) | start[NS] u16
 // (first sorted position of every target, start[n] = number of valid entries; NS = n + 1 rounded up to 8).
 // Entries per tile: 2048 (group) or 3 x 2040 (interpolate: 2040 points, 8160-byte row pieces for the bulk copies).
-__host__ __device__ constexpr int seg_dense_tile(int div) { return div == 3 ? 6120 : 2048; }
-__host__ __device__ constexpr int seg_dense_stride(int div) { return div == 3 ? 6144 : 2048; }  // tp slots per blob
+// MUL (1, 2 or 4) widens the tile when a thread holds fewer channels, keeping ~64 KB of source rows per stage: the more
+// entries of a target a tile holds, the better the lanes of a warp are used (slice lengths are Poisson-like).
+__host__ __device__ constexpr int seg_dense_tile(int div, int mul) { return mul * (div == 3 ? 6120 : 2048); }
+__host__ __device__ constexpr int seg_dense_stride(int div, int mul) { return mul * (div == 3 ? 6144 : 2048); }  // tp slots per blob
 __host__ __device__ inline int seg_dense_ns(int n) { return (n + 1 + 7) & ~7; }
-__host__ __device__ inline size_t seg_dense_blob(int n, int div) { return (size_t)seg_dense_stride(div) * 2 + (size_t)seg_dense_ns(n) * 2; }
+__host__ __device__ inline size_t seg_dense_blob(int n, int div, int mul) {
+  return (size_t)seg_dense_stride(div, mul) * 2 + (size_t)seg_dense_ns(n) * 2;
+}
 
 // grid (tiles, b); dynamic smem (n + 32) ints
-template <int DIV>
+template <int DIV, int MUL>
 __global__ void __launch_bounds__(kSegSortThreads) seg_sort_dense_kernel(const int *__restrict__ idx, int per, int n,
                                                                          unsigned char *__restrict__ blobs) {
-  constexpr int T = seg_dense_tile(DIV), kStride = seg_dense_stride(DIV);
+  constexpr int T = seg_dense_tile(DIV, MUL), kStride = seg_dense_stride(DIV, MUL);
   extern __shared__ int s_bins[];
   int *wsum = s_bins + n;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t ibase = (size_t)blockIdx.y * per + (size_t)blockIdx.x * T;
-  unsigned short *tp = reinterpret_cast<unsigned short *>(blobs + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * seg_dense_blob(n, DIV));
+  unsigned short *tp = reinterpret_cast<unsigned short *>(blobs + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * seg_dense_blob(n, DIV, MUL));
   unsigned short *start = tp + kStride;
   const int tc = min(T, per - (int)blockIdx.x * T);
   for (int i = tid; i < n; i += kSegSortThreads) s_bins[i] = 0;
@@ -425,12 +429,12 @@ __global__ void __launch_bounds__(kSegSortThreads) seg_sort_dense_kernel(const i
 // grid b * chunks, kSegThreads threads.  Thread -> target slot ts = tid % NT and channel group cg = tid / NT
 // (NT = 2^nt_log2 >= n when n <= 1024, else 1024 with TPT targets ts, ts + 1024, ...); CC = CT * (1024 / NT) channels per
 // CTA.  dynamic smem per stage: gt[CC][TP] f32 | wt[T] f32 (weighted) | blob.
-template <int CT, int TPT, int DIV, bool WEIGHTED>
+template <int CT, int TPT, int DIV, bool WEIGHTED, int MUL>
 __global__ void __launch_bounds__(kSegThreads, 1) seg_dense_kernel(const float *__restrict__ src, const unsigned char *__restrict__ blobs,
                                                                    const float *__restrict__ weight, float *__restrict__ grad, int c,
                                                                    int n, int per_src, int tiles, int chunks, int nt_log2, int stages,
                                                                    int stage_bytes, int bulk_ok, int overwrite, size_t src_stride) {
-  constexpr int T = seg_dense_tile(DIV), TP = T / DIV;
+  constexpr int T = seg_dense_tile(DIV, MUL), TP = T / DIV;
   extern __shared__ __align__(128) unsigned char s_raw[];
   __shared__ uint64_t full[kSegMaxStages];
   const int tid = threadIdx.x;
@@ -440,7 +444,7 @@ __global__ void __launch_bounds__(kSegThreads, 1) seg_dense_kernel(const float *
   const int ch0 = chunk * CC;
   const int nch = min(CC, c - ch0);
   const float *g = src + (size_t)scene * src_stride + (size_t)ch0 * per_src;
-  const size_t blob = seg_dense_blob(n, DIV);
+  const size_t blob = seg_dense_blob(n, DIV, MUL);
   const unsigned char *bsrc = blobs + (size_t)scene * tiles * blob;
   const float *wsrc = WEIGHTED ? weight + (size_t)scene * per_src * DIV : nullptr;
   const int wt_off = CC * TP * 4, blob_off = wt_off + (WEIGHTED ? T * 4 : 0);
@@ -495,7 +499,7 @@ __global__ void __launch_bounds__(kSegThreads, 1) seg_dense_kernel(const float *
     const float *gt = reinterpret_cast<const float *>(st) + (size_t)cg * CT * TP;
     const float *wt = reinterpret_cast<const float *>(st + wt_off);
     const unsigned short *tp = reinterpret_cast<const unsigned short *>(st + blob_off);
-    const unsigned short *start = tp + seg_dense_stride(DIV);
+    const unsigned short *start = tp + seg_dense_stride(DIV, MUL);
 #pragma unroll
     for (int j = 0; j < TPT; ++j) {
       const int k = ts + j * NT;
@@ -571,18 +575,18 @@ static int launch_seg_accum(const float *src, size_t src_stride, const unsigned 
   return finish_launch();
 }
 
-template <int CT, int TPT, int DIV, bool WEIGHTED>
+template <int CT, int TPT, int DIV, bool WEIGHTED, int MUL>
 static int launch_seg_dense(const float *src, size_t src_stride, const unsigned char *blobs, const float *weight, float *grad, int b, int c,
                             int n, int per_src, int tiles, int nt_log2, int bulk_ok, int overwrite, cudaStream_t s) {
-  constexpr int T = seg_dense_tile(DIV), TP = T / DIV;
+  constexpr int T = seg_dense_tile(DIV, MUL), TP = T / DIV;
   const int G = kSegThreads >> nt_log2, CC = CT * G;
-  const size_t stage_bytes = ((size_t)CC * TP * 4 + (WEIGHTED ? (size_t)T * 4 : 0) + seg_dense_blob(n, DIV) + 127) & ~(size_t)127;
+  const size_t stage_bytes = ((size_t)CC * TP * 4 + (WEIGHTED ? (size_t)T * 4 : 0) + seg_dense_blob(n, DIV, MUL) + 127) & ~(size_t)127;
   int stages = (int)(kSegSmemBudget / stage_bytes);
   stages = stages > kSegMaxStages ? kSegMaxStages : stages;
   if (stages > tiles) stages = tiles;
   if (!bulk_ok || stages < 1) stages = 1;
   const size_t smem = stages * stage_bytes;
-  auto kern = seg_dense_kernel<CT, TPT, DIV, WEIGHTED>;
+  auto kern = seg_dense_kernel<CT, TPT, DIV, WEIGHTED, MUL>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   const int chunks = (c + CC - 1) / CC;
@@ -597,39 +601,54 @@ constexpr int kSegDenseMaxN = 4096;
 // dense mode (thread-owned targets, register accumulators) for n <= 4096
 static int seg_scatter_dense(const float *src, size_t src_stride, const int *key, const float *weight, float *grad, int b, int c, int n,
                              size_t entries, int div, int overwrite, cudaStream_t s) {
-  const int T = seg_dense_tile(div), TP = T / div;
   const int per_src = (int)(entries / div);
+  int nt_log2 = 8;  // >= 256 target slots: at most 4 channel groups per CTA, so one channel per thread always fits
+  while ((1 << nt_log2) < n && nt_log2 < 10) ++nt_log2;
+  const int NT = 1 << nt_log2, G = kSegThreads / NT;
+  const int tpt = (n + NT - 1) / NT;  // 1 when n <= 1024, else 2..4
+  // tile multiplier of a channel count: ~64 KB of source rows per stage (group); the interpolate tile is 2040 points
+  auto mul_of = [&](int ct) { return div == 3 ? 1 : (ct * G >= 8 ? 1 : (ct * G >= 4 ? 2 : 4)); };
+  auto stage_of = [&](int ct) {
+    const int T = seg_dense_tile(div, mul_of(ct)), TP = T / div;
+    return (size_t)ct * G * TP * 4 + (weight ? (size_t)T * 4 : 0) + seg_dense_blob(n, div, mul_of(ct)) + 128;
+  };
+  // channels per thread: as many as registers (CT * TPT <= 16), two stages of shared memory and the grid allow; with two
+  // or more targets per thread, 4 channels x a 4096-entry tile beat 8 x 2048 (B200, n = 2048: 830 vs 893 us)
+  int CT = tpt >= 2 ? 4 : 8;
+  while (CT > 1 && (CT * (tpt > 2 ? 4 : tpt) > 16 || CT * G > ((c + 3) & ~3) * 2 || 2 * stage_of(CT) > kSegSmemBudget ||
+                    (long)b * ((c + CT * G - 1) / (CT * G)) < (long)num_sms()))
+    CT >>= 1;
+  if (g_tuning.scatter_cc == 1 || g_tuning.scatter_cc == 2 || g_tuning.scatter_cc == 4 || g_tuning.scatter_cc == 8) {
+    CT = g_tuning.scatter_cc;
+    while (CT > 1 && (CT * (tpt > 2 ? 4 : tpt) > 16 || 2 * stage_of(CT) > kSegSmemBudget)) CT >>= 1;
+  }
+  const int mul = mul_of(CT);
+  const int T = seg_dense_tile(div, mul);
   const int tiles = (int)((entries + T - 1) / T);
-  const size_t blob = seg_dense_blob(n, div);
+  const size_t blob = seg_dense_blob(n, div, mul);
   unsigned char *blobs = nullptr;
   cudaError_t e = scratch_alloc((void **)&blobs, (size_t)b * tiles * blob, s);
   if (e != cudaSuccess) return (int)e;
   const size_t sort_smem = ((size_t)n + 32) * sizeof(int);
-  if (div == 3) seg_sort_dense_kernel<3><<<dim3((unsigned)tiles, b), kSegSortThreads, sort_smem, s>>>(key, (int)entries, n, blobs);
-  else seg_sort_dense_kernel<1><<<dim3((unsigned)tiles, b), kSegSortThreads, sort_smem, s>>>(key, (int)entries, n, blobs);
+  const dim3 sgrid((unsigned)tiles, b);
+  if (div == 3) seg_sort_dense_kernel<3, 1><<<sgrid, kSegSortThreads, sort_smem, s>>>(key, (int)entries, n, blobs);
+  else if (mul == 1) seg_sort_dense_kernel<1, 1><<<sgrid, kSegSortThreads, sort_smem, s>>>(key, (int)entries, n, blobs);
+  else if (mul == 2) seg_sort_dense_kernel<1, 2><<<sgrid, kSegSortThreads, sort_smem, s>>>(key, (int)entries, n, blobs);
+  else seg_sort_dense_kernel<1, 4><<<sgrid, kSegSortThreads, sort_smem, s>>>(key, (int)entries, n, blobs);
   count_launch();
   int rc = finish_launch();
   if (!rc) {
-    int nt_log2 = 8;  // >= 256 target slots: at most 4 channel groups per CTA, so one channel per thread always fits
-    while ((1 << nt_log2) < n && nt_log2 < 10) ++nt_log2;
-    const int NT = 1 << nt_log2, G = kSegThreads / NT;
-    const int tpt = (n + NT - 1) / NT;  // 1 when n <= 1024, else 2..4
-    // channels per thread: as many as registers (CT * TPT <= 16), two stages of shared memory and the grid allow
-    int CT = 8;
-    auto stage_of = [&](int ct) { return (size_t)ct * G * TP * 4 + (weight ? (size_t)T * 4 : 0) + blob + 128; };
-    while (CT > 1 && (CT * (tpt > 2 ? 4 : tpt) > 16 || CT * G > ((c + 3) & ~3) * 2 || 2 * stage_of(CT) > kSegSmemBudget ||
-                      (long)b * ((c + CT * G - 1) / (CT * G)) < (long)num_sms()))
-      CT >>= 1;
-    if (g_tuning.scatter_cc == 1 || g_tuning.scatter_cc == 2 || g_tuning.scatter_cc == 4 || g_tuning.scatter_cc == 8) {
-      CT = g_tuning.scatter_cc;
-      while (CT > 1 && (CT * (tpt > 2 ? 4 : tpt) > 16 || 2 * stage_of(CT) > kSegSmemBudget)) CT >>= 1;
-    }
     // bulk copies: 16-byte aligned row pieces (and weight pieces: per_src * div * 4 bytes per scene)
     const int bulk_ok = (per_src % 4 == 0) && (((uintptr_t)src & 15u) == 0) && (!weight || ((uintptr_t)weight & 15u) == 0) &&
                         2 * stage_of(CT) <= kSegSmemBudget;
-#define GB_DENSE_CASE(CTV, TPTV)                                                                                                   \
-  rc = div == 3 ? launch_seg_dense<CTV, TPTV, 3, true>(src, src_stride, blobs, weight, grad, b, c, n, per_src, tiles, nt_log2, bulk_ok, overwrite, s) \
-                : launch_seg_dense<CTV, TPTV, 1, false>(src, src_stride, blobs, weight, grad, b, c, n, per_src, tiles, nt_log2, bulk_ok, overwrite, s)
+#define GB_DENSE_ARGS src, src_stride, blobs, weight, grad, b, c, n, per_src, tiles, nt_log2, bulk_ok, overwrite, s
+#define GB_DENSE_CASE(CTV, TPTV)                                                                      \
+  do {                                                                                                \
+    if (div == 3) rc = launch_seg_dense<CTV, TPTV, 3, true, 1>(GB_DENSE_ARGS);                        \
+    else if (mul == 1) rc = launch_seg_dense<CTV, TPTV, 1, false, 1>(GB_DENSE_ARGS);                  \
+    else if (mul == 2) rc = launch_seg_dense<CTV, TPTV, 1, false, 2>(GB_DENSE_ARGS);                  \
+    else rc = launch_seg_dense<CTV, TPTV, 1, false, 4>(GB_DENSE_ARGS);                                \
+  } while (0)
     if (tpt <= 1) {
       switch (CT) {
         case 8: GB_DENSE_CASE(8, 1); break;
@@ -652,6 +671,7 @@ static int seg_scatter_dense(const float *src, size_t src_stride, const int *key
       }
     }
 #undef GB_DENSE_CASE
+#undef GB_DENSE_ARGS
   }
   cudaFreeAsync(blobs, s);
   return rc;

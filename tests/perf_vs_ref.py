@@ -272,6 +272,19 @@ def main():
                 rows.append({"op": f"sweep2 {name} B={B} scatter_cc={cc}", "us": round(t, 1)})
                 print(json.dumps(rows[-1]), flush=True)
         _lib.set_tuning("scatter_cc", 0)
+        # the other InvResMLP grouping shapes of the backbone (drp.py:169-247): N = m, C = 256
+        for (nn, cc_, nsb, rr) in ((1024, 256, 32, 0.2), (512, 256, 16, 0.4), (256, 256, 16, 0.6)):
+            subx = xyz[:, :nn].contiguous()
+            idxn = A.ball_query(subx, subx, rr, nsb)
+            gn = torch.randn((B, cc_, nn, nsb), generator=g).to(dev)
+            nb = 4 * cc_ * nn + 4 * nn * nsb + 4 * cc_ * nn * nsb
+            for cc in (0, 2, 4, 8):
+                _lib.set_tuning("scatter_cc", cc)
+                t = timeit(lambda: A.group_points_grad(gn, idxn, nn), iters=5)
+                rows.append({"op": f"sweep2 group bwd C={cc_} N=m={nn} ns={nsb} B={B} scatter_cc={cc}", "us": round(t, 1),
+                             "hbm_frac": round(nb * B / (t * 1e-6) / 1e9 / HBM, 3)})
+                print(json.dumps(rows[-1]), flush=True)
+        _lib.set_tuning("scatter_cc", 0)
 
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     with open(args.out, "w") as f:
