@@ -276,8 +276,9 @@ static int floor_log2(int v) {
 using namespace gb;
 
 extern "C" int gb_fps(const float *xyz, float *temp, int *idx, int b, int n, int m, int variant, gb_stream_t stream) {
-  if (b < 0 || n <= 0 || m < 0 || (variant != GB_FPS_A && variant != GB_FPS_B) || !xyz || !idx) return (int)cudaErrorInvalidValue;
-  if (b == 0 || m == 0) return 0;
+  if (b < 0 || n <= 0 || m < 0 || (variant != GB_FPS_A && variant != GB_FPS_B)) return (int)cudaErrorInvalidValue;
+  if (b == 0 || m == 0) return 0;  // nothing to do (empty tensors have null data pointers)
+  if (!xyz || !idx) return (int)cudaErrorInvalidValue;
   cudaStream_t s = (cudaStream_t)stream;
   // BS = opt_n_threads(n): cuda_utils.h:21-27 (cap 512) / pointnet2_batch/src/cuda_utils.h:10-14 (cap 1024).
   // floor(log2 n) computed in integers (the reference's double log() agrees for every n < 2^31 that is not within

@@ -286,9 +286,10 @@ using namespace gb;
 
 static int group_fwd_impl(const float *points, const int *idx, float *out, int b, int c, int n, int npoints, int nsample,
                           long long out_scene_stride, gb_stream_t stream) {
-  if (b < 0 || c < 0 || n <= 0 || npoints < 0 || nsample < 0 || !points || !idx || !out) return (int)cudaErrorInvalidValue;
+  if (b < 0 || c < 0 || n <= 0 || npoints < 0 || nsample < 0) return (int)cudaErrorInvalidValue;
   const size_t per = (size_t)npoints * nsample;
-  if (b == 0 || c == 0 || per == 0) return 0;
+  if (b == 0 || c == 0 || per == 0) return 0;  // nothing to do (empty tensors have null data pointers)
+  if (!points || !idx || !out) return (int)cudaErrorInvalidValue;
   if (out_scene_stride < (long long)((size_t)c * per)) return (int)cudaErrorInvalidValue;
   const size_t ostride = (size_t)out_scene_stride;
   cudaStream_t s = (cudaStream_t)stream;
@@ -325,8 +326,9 @@ extern "C" int gb_group_fwd_strided(const float *points, const int *idx, float *
 
 static int group_bwd_impl(const float *grad_out, const int *idx, float *grad_points, int b, int c, int n, int npoints, int nsample,
                           long long go_scene_stride, int overwrite, gb_stream_t stream) {
-  if (b < 0 || c < 0 || n <= 0 || npoints < 0 || nsample < 0 || !grad_out || !idx || !grad_points) return (int)cudaErrorInvalidValue;
+  if (b < 0 || c < 0 || n <= 0 || npoints < 0 || nsample < 0) return (int)cudaErrorInvalidValue;
   const size_t per = (size_t)npoints * nsample;
+  if (b > 0 && c > 0 && (!grad_points || (per > 0 && (!grad_out || !idx)))) return (int)cudaErrorInvalidValue;
   if (go_scene_stride < (long long)((size_t)c * per)) return (int)cudaErrorInvalidValue;
   const size_t gstride = (size_t)go_scene_stride;
   cudaStream_t s = (cudaStream_t)stream;
@@ -371,9 +373,10 @@ extern "C" int gb_group_bwd_strided(const float *grad_out, const int *idx, float
 }
 
 extern "C" int gb_gather_fwd(const float *points, const int *idx, float *out, int b, int c, int n, int m, gb_stream_t stream) {
-  if (b < 0 || c < 0 || n <= 0 || m < 0 || !points || !idx || !out) return (int)cudaErrorInvalidValue;
+  if (b < 0 || c < 0 || n <= 0 || m < 0) return (int)cudaErrorInvalidValue;
   const size_t total = (size_t)b * c * m;
   if (total == 0) return 0;
+  if (!points || !idx || !out) return (int)cudaErrorInvalidValue;
   gather_fwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(points, idx, out, c, n, m, total);
   count_launch();
   return finish_launch();
@@ -381,9 +384,10 @@ extern "C" int gb_gather_fwd(const float *points, const int *idx, float *out, in
 
 extern "C" int gb_gather_bwd(const float *grad_out, const int *idx, float *grad_points, int b, int c, int n, int m,
                              gb_stream_t stream) {
-  if (b < 0 || c < 0 || n <= 0 || m < 0 || !grad_out || !idx || !grad_points) return (int)cudaErrorInvalidValue;
+  if (b < 0 || c < 0 || n <= 0 || m < 0) return (int)cudaErrorInvalidValue;
   const size_t total = (size_t)b * c * m;
   if (total == 0) return 0;
+  if (!grad_out || !idx || !grad_points) return (int)cudaErrorInvalidValue;
   gather_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(grad_out, idx, grad_points, c, n, m, total);
   count_launch();
   return finish_launch();
@@ -391,9 +395,10 @@ extern "C" int gb_gather_bwd(const float *grad_out, const int *idx, float *grad_
 
 extern "C" int gb_group_xyz(const float *xyz, const float *new_xyz, const int *idx, const float *rot, float *out, int b, int n, int m,
                             int nsample, float scale, int use_scale, long long out_scene_stride, gb_stream_t stream) {
-  if (b < 0 || n <= 0 || m < 0 || nsample < 0 || !xyz || !new_xyz || !idx || !out) return (int)cudaErrorInvalidValue;
+  if (b < 0 || n <= 0 || m < 0 || nsample < 0) return (int)cudaErrorInvalidValue;
   const size_t per = (size_t)m * nsample;
   if (b == 0 || per == 0) return 0;
+  if (!xyz || !new_xyz || !idx || !out) return (int)cudaErrorInvalidValue;
   if (out_scene_stride < (long long)(3 * per)) return (int)cudaErrorInvalidValue;
   cudaStream_t s = (cudaStream_t)stream;
   const bool vec = (nsample % 4 == 0) && (out_scene_stride % 4 == 0) && ((((uintptr_t)idx | (uintptr_t)out) & 15u) == 0);

@@ -129,8 +129,9 @@ using namespace gb;
 
 extern "C" int gb_three_interp_fwd(const float *points, const int *idx, const float *weight, float *out, int b, int c, int m, int n,
                                    gb_stream_t stream) {
-  if (b < 0 || c < 0 || m <= 0 || n < 0 || !points || !idx || !weight || !out) return (int)cudaErrorInvalidValue;
+  if (b < 0 || c < 0 || m <= 0 || n < 0) return (int)cudaErrorInvalidValue;
   if (b == 0 || c == 0 || n == 0) return 0;
+  if (!points || !idx || !weight || !out) return (int)cudaErrorInvalidValue;
   cudaStream_t s = (cudaStream_t)stream;
   const bool aligned = (n % 4 == 0) && ((((uintptr_t)idx | (uintptr_t)weight | (uintptr_t)out) & 15u) == 0);
   const size_t row_bytes = (size_t)m * sizeof(float);
@@ -169,8 +170,9 @@ extern "C" int gb_three_interp_fwd(const float *points, const int *idx, const fl
 
 static int interp_bwd_impl(const float *grad_out, const int *idx, const float *weight, float *grad_points, int b, int c, int n, int m,
                            int overwrite, gb_stream_t stream) {
-  if (b < 0 || c < 0 || m <= 0 || n < 0 || !grad_out || !idx || !weight || !grad_points) return (int)cudaErrorInvalidValue;
+  if (b < 0 || c < 0 || m <= 0 || n < 0) return (int)cudaErrorInvalidValue;
   if (b == 0 || c == 0) return 0;
+  if (!grad_points || (n > 0 && (!grad_out || !idx || !weight))) return (int)cudaErrorInvalidValue;
   if (n == 0) return overwrite ? (int)cudaMemsetAsync(grad_points, 0, (size_t)b * c * m * sizeof(float), (cudaStream_t)stream) : 0;
   // atomic-free sorted segmented sum (scatter.cu): entries e = 3*j + t, source g[c][e / 3], weight w[e]
   if (!(g_tuning.interp_mode & 4) && seg_scatter_supported(b, c, m, (size_t)n * 3, 3))

@@ -457,8 +457,9 @@ __global__ void __launch_bounds__(kQueryWarps * 32) query_kernel(const float *__
 template <bool CYL>
 static int launch_query(const float *new_xyz, const float *xyz, const float *rot, int *idx, int b, int n, int m, float radius,
                         float hmin, float hmax, int nsample, cudaStream_t s) {
-  if (b < 0 || n <= 0 || m < 0 || nsample <= 0 || !new_xyz || !xyz || !idx || (CYL && !rot)) return (int)cudaErrorInvalidValue;
-  if (b == 0 || m == 0) return 0;
+  if (b < 0 || n <= 0 || m < 0 || nsample <= 0) return (int)cudaErrorInvalidValue;
+  if (b == 0 || m == 0) return 0;  // nothing to do (empty tensors have null data pointers)
+  if (!new_xyz || !xyz || !idx || (CYL && !rot)) return (int)cudaErrorInvalidValue;
   const float radius2 = radius * radius;  // fp32 product, as ball_query_gpu.cu:22
   const int use_bulk = (n % 4 == 0) && (((uintptr_t)xyz & 15u) == 0);
   if (b > 65535) return (int)cudaErrorInvalidValue;

@@ -61,8 +61,9 @@ __global__ void __launch_bounds__(kNNThreads) three_nn_kernel(const float *__res
 
 extern "C" int gb_three_nn(const float *unknown, const float *known, float *dist2, int *idx, int b, int n, int m,
                            gb_stream_t stream) {
-  if (b < 0 || n < 0 || m < 0 || !unknown || !known || !dist2 || !idx) return (int)cudaErrorInvalidValue;
-  if (b == 0 || n == 0) return 0;
+  if (b < 0 || n < 0 || m < 0) return (int)cudaErrorInvalidValue;
+  if (b == 0 || n == 0) return 0;  // nothing to do (empty tensors have null data pointers)
+  if (!unknown || (m > 0 && !known) || !dist2 || !idx) return (int)cudaErrorInvalidValue;
   if (b > 65535) return (int)cudaErrorInvalidValue;
   dim3 grid((n + gb::kNNThreads - 1) / gb::kNNThreads, b);
   gb::three_nn_kernel<<<grid, gb::kNNThreads, 0, (cudaStream_t)stream>>>(unknown, known, dist2, idx, n, m);

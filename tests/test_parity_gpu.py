@@ -453,3 +453,56 @@ def test_collision_full_size_vs_oracle(dev):
     for a, b in zip(got[2], want[2]):
         np.testing.assert_array_equal(a, b)
     assert 0 < got[0].sum() < 1024
+
+
+# ------------------------------------------------------------------------------------------------- sizes at the edges
+def test_empty_inputs_return_empty_outputs(dev):
+    """Zero queries / samples / scenes: the entry points return without launching (the reference would launch empty grids)."""
+    xyz = T(scenes.scene_batch(range(2), 500, "uniform"), dev)
+    none = xyz[:, :0].contiguous()
+    assert tuple(pu.ball_query(0.1, 8, xyz, none).shape) == (2, 0, 8)
+    assert tuple(pu.furthest_point_sample(xyz, 0).shape) == (2, 0)
+    feats = torch.randn((2, 5, 500), device=dev)
+    assert tuple(pu.gather_operation(feats, torch.zeros((2, 0), dtype=torch.int32, device=dev)).shape) == (2, 5, 0)
+    assert tuple(pu.grouping_operation(feats, torch.zeros((2, 0, 4), dtype=torch.int32, device=dev)).shape) == (2, 5, 0, 4)
+    d, i = pu.three_nn(none, xyz)
+    assert tuple(d.shape) == (2, 0, 3) and tuple(i.shape) == (2, 0, 3)
+    assert tuple(pu.ball_query(0.1, 8, xyz[:0].contiguous(), xyz[:0, :7].contiguous()).shape) == (0, 7, 8)
+    g = gb_a.group_points_grad(torch.zeros((2, 5, 0, 4), device=dev), torch.zeros((2, 0, 4), dtype=torch.int32, device=dev), 500)
+    assert tuple(g.shape) == (2, 5, 500) and float(g.abs().max()) == 0.0
+
+
+def test_dataset_maximum_cloud_size(dev):
+    """50000 points per cloud is the reference loader's cap (graspnet_dataset.py:19): FPS, ball / cylinder query through the
+    cell grid, grouping forward + sorted backward at that size, against the oracle."""
+    B, N, m, ns = 1, 50000, 200, 32
+    xyz = scenes.scene_batch([77], N, "tabletop")
+    x = T(xyz, dev)
+    inds = pu.furthest_point_sample(x, m)
+    np.testing.assert_array_equal(inds.cpu().numpy(), oracle.furthest_point_sample(xyz, m, "A"))
+    new_xyz = np.take_along_axis(xyz, inds.cpu().numpy().astype(np.int64)[..., None], axis=1)
+    q = T(new_xyz, dev)
+    idx = pu.ball_query(0.04, ns, x, q)
+    np.testing.assert_array_equal(idx.cpu().numpy(), oracle.ball_query(0.04, ns, xyz, new_xyz))
+    rng = np.random.default_rng(1)
+    v = rng.normal(size=(B, m, 3)).astype(np.float32)
+    rot = np.ascontiguousarray(scenes.viewpoint_rotations(-v, np.zeros((B, m), np.float32)).reshape(B, m, 9).astype(np.float32))
+    cidx = pu.cylinder_query(0.05, -0.02, 0.04, ns, x, q, T(rot, dev))
+    np.testing.assert_array_equal(cidx.cpu().numpy(), oracle.cylinder_query(0.05, -0.02, 0.04, ns, xyz, new_xyz, rot))
+    feats = rng.normal(size=(B, 6, N)).astype(np.float32)
+    f = T(feats, dev).requires_grad_(True)
+    out = pu.grouping_operation(f, idx)
+    np.testing.assert_array_equal(out.detach().cpu().numpy(), oracle.grouping_operation(feats, idx.cpu().numpy()))
+    gout = rng.normal(size=tuple(out.shape)).astype(np.float32)
+    out.backward(T(gout, dev))
+    assert_grad_close(f.grad.cpu().numpy(), oracle.grouping_operation_grad(gout, idx.cpu().numpy(), N))
+
+
+def test_non_contiguous_and_wrong_dtype_inputs_raise(dev):
+    xyz = T(scenes.scene_batch(range(2), 300, "uniform"), dev)
+    with pytest.raises((RuntimeError, AssertionError)):
+        pu.ball_query(0.1, 4, xyz.transpose(1, 2), xyz)
+    with pytest.raises((RuntimeError, AssertionError)):
+        pu.furthest_point_sample(xyz.double(), 8)
+    with pytest.raises((RuntimeError, AssertionError)):
+        pu.grouping_operation(torch.randn((2, 3, 300), device=dev), torch.zeros((2, 4, 4), dtype=torch.int64, device=dev))
