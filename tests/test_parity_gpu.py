@@ -72,7 +72,7 @@ def test_fps_norm_skip_and_ties(dev):
 
 
 @pytest.mark.parametrize("cluster", [1, 2, 4, 8, 16])
-@pytest.mark.parametrize("threads", [512, 1024])
+@pytest.mark.parametrize("threads", [256, 512, 1024])
 def test_fps_every_decomposition_gives_the_same_picks(dev, cluster, threads):
     xyz = scenes.scene_batch([5, 6], 20000, "tabletop")
     want = oracle.furthest_point_sample(xyz, 300, "A")
