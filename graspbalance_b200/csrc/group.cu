@@ -99,6 +99,65 @@ __global__ void __launch_bounds__(kGroupThreads) group_fwd_kernel(const float *_
   }
 }
 
+// Large clouds (a source row of n floats no longer fits four or two at a time): ONE channel row per buffer, two buffers,
+// filled by the TMA engine (one cp.async.bulk per row: the row is contiguous in global memory) while the previous row is
+// swept -- fill and sweep overlap inside a CTA instead of across co-resident CTAs.  Work unit = (row, position segment);
+// a CTA takes a contiguous run of units, so consecutive units usually share the staged row.
+// points [b,c,n]; idx [b,per]; out rows `per` floats long, scenes out_stride apart.  dynamic smem: 2 * n floats.
+__global__ void __launch_bounds__(kGroupThreads) group_fwd_rows_kernel(const float *__restrict__ points, const int *__restrict__ idx,
+                                                                      float *__restrict__ out, int c, int n, int per4, int segs,
+                                                                      int seg_len4, long long units, long long upc, size_t out_stride) {
+  extern __shared__ __align__(128) float s_row[];  // [2][n]
+  __shared__ uint64_t full[2];
+  const int tid = threadIdx.x;
+  const long long u0 = (long long)blockIdx.x * upc, u1 = min(units, u0 + upc);
+  if (u0 >= u1) return;
+  if (tid == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const size_t per = (size_t)per4 * 4;
+  const long long r_first = u0 / segs, r_last = (u1 - 1) / segs;
+  auto load_row = [&](long long r, int buf) {  // thread 0
+    mbar_arrive_expect_tx(&full[buf], (uint32_t)n * 4u);
+    bulk_g2s(s_row + (size_t)buf * n, points + (size_t)r * n, (uint32_t)n * 4u, &full[buf]);
+  };
+  if (tid == 0) load_row(r_first, 0);
+  long long cur_row = -1;
+  int k = -1;  // index of the current row within this CTA: buffer k & 1, wait parity (k >> 1) & 1
+  for (long long u = u0; u < u1; ++u) {
+    const long long r = u / segs;
+    const int sgm = (int)(u - r * segs);
+    if (r != cur_row) {
+      __syncthreads();  // every thread has left the previous row: its predecessor's buffer may be refilled
+      cur_row = r, ++k;
+      if (tid == 0 && r < r_last) load_row(r + 1, (k + 1) & 1);
+      mbar_wait(&full[k & 1], (uint32_t)((k >> 1) & 1));
+    }
+    const float *row = s_row + (size_t)(k & 1) * n;
+    const size_t scene = (size_t)(r / c), ch = (size_t)(r - (long long)scene * c);
+    const int *ip = idx + scene * per;
+    float *op = out + scene * out_stride + ch * per;
+    const int q1 = min(per4, (sgm + 1) * seg_len4);
+    int q = sgm * seg_len4 + tid;
+    // four index loads (L2 latency) in flight per thread before the first gather
+    for (; q + 3 * kGroupThreads < q1; q += 4 * kGroupThreads) {
+      int4 id[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) id[u] = ld_nc_i4(ip + (size_t)(q + u * kGroupThreads) * 4);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        st_cs_f4(op + (size_t)(q + u * kGroupThreads) * 4, make_float4(row[id[u].x], row[id[u].y], row[id[u].z], row[id[u].w]));
+    }
+    for (; q < q1; q += kGroupThreads) {
+      const int4 id = ld_nc_i4(ip + (size_t)q * 4);
+      st_cs_f4(op + (size_t)q * 4, make_float4(row[id.x], row[id.y], row[id.z], row[id.w]));
+    }
+  }
+}
+
 // generic fallback (any shape / alignment): one thread per output element, gathers straight from global/L2
 __global__ void group_fwd_generic_kernel(const float *__restrict__ points, const int *__restrict__ idx, float *__restrict__ out, int c,
                                          int n, size_t per, size_t total, size_t out_stride) {
@@ -296,6 +355,28 @@ static int group_fwd_impl(const float *points, const int *idx, float *out, int b
   const bool aligned = (per % 4 == 0) && (ostride % 4 == 0) && (((uintptr_t)idx | (uintptr_t)out) & 15u) == 0 && per / 4 < (1u << 30);
   const size_t row_bytes = (size_t)n * sizeof(float);
   const size_t big = 200u * 1024u;
+  // rows too long to stage four channels at a time: TMA double-buffered single rows
+  if (aligned && 4 * row_bytes > big && 2 * row_bytes <= big && n % 4 == 0 && (((uintptr_t)points & 15u) == 0) &&
+      !(g_tuning.group_mode & (2 | 8))) {
+    const int per4 = (int)(per / 4);
+    const long long rows = (long long)b * c;
+    const int grid = num_sms();
+    int segs = (int)((4LL * grid + rows - 1) / rows);  // >= ~4 units per CTA so the contiguous split balances
+    const int max_segs = per4 / (2 * kGroupThreads) > 1 ? per4 / (2 * kGroupThreads) : 1;
+    segs = segs < 1 ? 1 : (segs > max_segs ? max_segs : segs);
+    const int seg_len4 = (per4 + segs - 1) / segs;
+    segs = (per4 + seg_len4 - 1) / seg_len4;
+    const long long units = rows * segs;
+    const long long ctas = units < grid ? units : grid;
+    const long long upc = (units + ctas - 1) / ctas;
+    const size_t smem = 2 * row_bytes;
+    cudaError_t e = cudaFuncSetAttribute(group_fwd_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    group_fwd_rows_kernel<<<(unsigned)((units + upc - 1) / upc), kGroupThreads, smem, s>>>(points, idx, out, c, n, per4, segs, seg_len4, units,
+                                                                                      upc, ostride);
+    count_launch();
+    return finish_launch();
+  }
   if (aligned && row_bytes <= big && !(g_tuning.group_mode & 2)) {
     // channels per fill: as many as fit (V-interleaved), aiming at <= ~100 KB so that two CTAs share an SM when rows are small
     int V = c >= 4 && 4 * row_bytes <= big ? 4 : (c >= 2 && 2 * row_bytes <= big ? 2 : 1);
