@@ -241,6 +241,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="run the sampling chain and the collision tests on the main stream")
+    ap.add_argument("--unfused-crops", action="store_true",
+                    help="grasp crops as the reference's 16 separate CylinderQueryAndGroup calls instead of 4 multi-depth scans")
     ap.add_argument("--cuda-profiler-range", action="store_true",
                     help="bracket the timed steps with cudaProfilerStart/Stop (for `ncu --profile-from-start off`)")
     args = ap.parse_args()
@@ -268,7 +270,8 @@ def main():
     B = args.batch
     scene_ids = sharding.scene_ids_for_rank(rank, world, B)
     host, offs = make_host_inputs(scene_ids)
-    pipe = pipeline.OpPipeline(B, N_POINTS, dev, seed=rank, backward=not args.no_backward, overlap=not args.no_overlap)
+    pipe = pipeline.OpPipeline(B, N_POINTS, dev, seed=rank, backward=not args.no_backward, overlap=not args.no_overlap,
+                               fused_crops=not args.unfused_crops)
     gather_buf = torch.empty((world * B, pipeline.NUM_SEED + 6 * pipeline.NUM_GRASP), dtype=torch.int64, device=dev) if world > 1 else None
 
     def step(resident, inputs=None):
@@ -314,6 +317,18 @@ def main():
     torch.cuda.synchronize()
     for _ in range(args.warmup):
         step(True, resident_inputs)
+    # allocator priming (untimed, on top of the W warm-up steps): the caching allocator keeps growing its pools for a few
+    # steps because blocks handed to side streams are recycled late; a cudaMalloc inside the timed region costs
+    # milliseconds.  Step until one whole step needs no new device allocation (at most 8 extra steps).
+    prime_steps = 0
+    while prime_steps < 8:
+        before = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
+        step(True, resident_inputs)
+        torch.cuda.synchronize()
+        prime_steps += 1
+        if torch.cuda.memory_stats(dev).get("num_device_alloc", 0) == before:
+            break
+    dev_allocs0 = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
 
     # ---- device-resident throughput ("value") ----
     sampler = ClockSampler(local_rank)
@@ -328,6 +343,7 @@ def main():
     if args.cuda_profiler_range:
         torch.cuda.profiler.stop()
     launches = _lib.launch_count() - launches0
+    dev_allocs_timed = torch.cuda.memory_stats(dev).get("num_device_alloc", 0) - dev_allocs0
     clocks = sampler.stop(tw0, tw1) if rank == 0 else None
     value = world * B * args.steps / (ms * 1e-3)
 
@@ -360,7 +376,7 @@ def main():
     fam = {}
     for name, evs in prof.items():
         tot_ms = sum(a.elapsed_time(b) for a, b, _ in evs)
-        base = name.replace("_set", "").replace("_strided", "")  # entry-point variants of one op share its kernels
+        base = name.replace("_set", "").replace("_strided", "").replace("_multi", "")  # entry-point variants of one op share its kernels
         f = fam.setdefault(base, {"launches": 0, "ms": 0.0, "bytes": 0, "big": None})
         f["launches"] += len(evs)
         f["ms"] += tot_ms
@@ -412,7 +428,8 @@ def main():
             "config": {"workload": workload_name(args), "scenes_per_gpu": B, "n_points": N_POINTS, "parallelism": f"scene-sharded x{world}",
                        "streams": "sampling chain + collision tests on side streams" if pipe.overlap else "single stream",
                        "l2": "per-step working set (>10 GB of grouped features) exceeds the 126 MB L2; no explicit flush",
-                       "algorithmic_bytes_per_scene": int(sum(algo.values()))},
+                       "algorithmic_bytes_per_scene": int(sum(algo.values())),
+                       "allocator_priming_steps": prime_steps, "device_allocs_in_timed_region": int(dev_allocs_timed)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "roofline_pass_ms_per_step": ms_prof / args.steps,
             "pipeline_hbm_frac": (sum(algo.values()) * world * B * args.steps / (ms * 1e-3) / 1e9) / (peak * world),

@@ -9,6 +9,7 @@ Python modules mirror the reference files they replace:
     graspbalance_b200.group / subsample / upsampling  <- ModifiedNetTools/{group,subsample,upsampling}.py
     graspbalance_b200.knn_modules           <- KNN/knn_modules.py
     graspbalance_b200.collision_detector    <- collision_detector.py
+    graspbalance_b200.modules               <- TrainModel/modules.py: GraspWidthGrouping (fused 4-depth grasp crop)
 
 All compute goes through libgbops.so (C ABI in include/gbops.h).  There is no CPU, Triton or PyTorch fallback.
 """

@@ -138,6 +138,27 @@ def cylinder_query(new_xyz, xyz, rot, radius, hmin, hmax, nsample):
     return idx
 
 
+def cylinder_query_multi(new_xyz, xyz, rot, radius, hmin, hmax_list, nsample):
+    """The depth loop of GraspWidthGrouping (TrainModel/modules.py:104-113) in one scan: len(hmax_list) <= 4 nested
+    cylinders per query.  Returns idx [B,m,D,nsample] i32 with idx[:, :, d] == cylinder_query(..., hmax_list[d], ...)."""
+    import ctypes
+    _contig(new_xyz, "new_xyz"); _contig(xyz, "xyz"); _contig(rot, "rot")
+    _is_float(new_xyz, "new_xyz"); _is_float(xyz, "xyz"); _is_float(rot, "rot")
+    if new_xyz.is_cuda:
+        _cuda(xyz, "xyz"); _cuda(rot, "rot")
+    _need_cuda(new_xyz)
+    D = len(hmax_list)
+    if not 1 <= D <= 4:
+        raise RuntimeError("cylinder_query_multi takes 1 to 4 depths")
+    B, m = new_xyz.shape[0], new_xyz.shape[1]
+    N = xyz.shape[1]
+    idx = torch.empty((B, m, D, int(nsample)), dtype=torch.int32, device=new_xyz.device)
+    hm = (ctypes.c_float * D)(*[float(h) for h in hmax_list])
+    _lib.call("gb_cylinder_query_multi", new_xyz, new_xyz.data_ptr(), xyz.data_ptr(), rot.data_ptr(), idx.data_ptr(), B, N, m, float(radius),
+              float(hmin), hm, D, int(nsample))
+    return idx
+
+
 def group_points(points, idx):
     """group_points.cpp:21-47.  points [B,C,N], idx [B,npoints,nsample] -> [B,C,npoints,nsample]."""
     _contig(points, "points"); _contig(idx, "idx"); _is_float(points, "points"); _is_int(idx, "idx")

@@ -39,6 +39,20 @@ __device__ __forceinline__ bool cyl_hit(const float (&r)[9], float qx, float qy,
   return (d2 < radius2) && (xr > hmin) && (xr < hmax);
 }
 
+// x_rot alone, the same instruction sequence as in cyl_hit (the multi-depth read-out re-derives it per hit)
+__device__ __forceinline__ float cyl_xrot(const float (&r)[9], float qx, float qy, float qz, float x, float y, float z) {
+  const float dx = x - qx, dy = y - qy, dz = z - qz;
+  return __fmaf_rn(r[6], dz, __fmaf_rn(r[0], dx, __fmul_rn(r[3], dy)));
+}
+
+// Multi-depth cylinder query (the 4-depth loop of GraspWidthGrouping, TrainModel/modules.py:104-113): the cylinders of one
+// call share axis, radius and hmin and differ in hmax only, so they are nested: ONE scan with the largest hmax finds every
+// candidate, and a hit belongs to depth d iff x_rot < hmax[d].  idx is laid out [b, m, nd, nsample].
+constexpr int kMaxDepths = 4;
+struct HMax4 {
+  float v[kMaxDepths];
+};
+
 // ---- uniform cell grid ------------------------------------------------------------------------------------------------
 constexpr int kGridMaxCells = 4096;
 constexpr int kGridMaxDim = 32;
@@ -200,12 +214,15 @@ __global__ void __launch_bounds__(kGridThreads) grid_build_kernel(const float *_
 // bounding box, much tighter than its bounding sphere); a rotation further than 1e-3 from orthonormal searches the
 // whole grid.  Every bound is widened by reach * (1e-4 + 4 err) + 1e-5 * (largest coordinate magnitude), orders of
 // magnitude above the fp32 rounding of the test (a few ulp of the coordinates), so no point that passes it is culled.
-template <bool CYL>
-__global__ void __launch_bounds__(kGridQueryWarps * 32, 5) grid_query_kernel(const float *__restrict__ new_xyz, const float4 *__restrict__ sorted,
+// MULTI (cylinder only): hmax is the largest of the nd depths hm.v[]; the read-out classifies every hit by depth (x_rot
+// re-derived from the original coordinates xyz_orig) and fills the nd index lists of the query, [nd, nsample] per query.
+template <bool CYL, bool MULTI>
+__global__ void __launch_bounds__(kGridQueryWarps * 32, MULTI ? 4 : 5) grid_query_kernel(const float *__restrict__ new_xyz, const float4 *__restrict__ sorted,
                                                                          const int *__restrict__ cell_start,
                                                                          const GridHeader *__restrict__ hdr, const float *__restrict__ rot,
                                                                          int *__restrict__ idx, int n, int m, float radius, float radius2,
-                                                                         float reach, float hmin, float hmax, int nsample, int words) {
+                                                                         float reach, float hmin, float hmax, int nsample, int words,
+                                                                         const float *__restrict__ xyz_orig, HMax4 hm, int nd) {
   extern __shared__ unsigned s_bm[];
   const int scene = blockIdx.y;
   const GridHeader h = hdr[scene];
@@ -305,6 +322,64 @@ __global__ void __launch_bounds__(kGridQueryWarps * 32, 5) grid_query_kernel(con
   }
   __syncwarp();
 
+  if (MULTI) {
+    // ---- multi-depth read-out: the bits of a word are classified by depth, then every depth compacts its own bits ----
+    xyz_orig += (size_t)scene * n * 3;
+    int *out = idx + qi * (size_t)nd * nsample;
+    int cntd[kMaxDepths], firstd[kMaxDepths];
+#pragma unroll
+    for (int d = 0; d < kMaxDepths; ++d) cntd[d] = d < nd ? 0 : nsample, firstd[d] = 0;
+    for (int wb = 0; wb < words; wb += 32) {
+      bool open = false;
+#pragma unroll
+      for (int d = 0; d < kMaxDepths; ++d) open |= cntd[d] < nsample;
+      if (!open) break;
+      const unsigned w = wb + lane < words ? bm[wb + lane] : 0u;
+      if (!__ballot_sync(0xffffffffu, w != 0u)) continue;
+      unsigned wd[kMaxDepths] = {0u, 0u, 0u, 0u};
+      for (unsigned t = w; t; t &= t - 1) {
+        const int bit = __ffs(t) - 1;
+        const size_t k = (size_t)(wb + lane) * 32 + bit;
+        const float xr = cyl_xrot(r, qx, qy, qz, __ldg(xyz_orig + 3 * k), __ldg(xyz_orig + 3 * k + 1), __ldg(xyz_orig + 3 * k + 2));
+#pragma unroll
+        for (int d = 0; d < kMaxDepths; ++d)
+          if (xr < hm.v[d]) wd[d] |= 1u << bit;
+      }
+#pragma unroll
+      for (int d = 0; d < kMaxDepths; ++d) {
+        if (cntd[d] >= nsample) continue;  // warp uniform
+        unsigned x = wd[d];
+        const unsigned any = __ballot_sync(0xffffffffu, x != 0u);
+        if (!any) continue;
+        const int pc = __popc(x);
+        int incl = pc;
+#pragma unroll
+        for (int dd = 1; dd < 32; dd <<= 1) {
+          const int o = __shfl_up_sync(0xffffffffu, incl, dd);
+          if (lane >= dd) incl += o;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (cntd[d] == 0) {
+          const int l0 = __ffs(any) - 1;
+          const unsigned w0 = __shfl_sync(0xffffffffu, x, l0);
+          firstd[d] = (wb + l0) * 32 + __ffs(w0) - 1;
+        }
+        int pos = cntd[d] + incl - pc;
+        while (x && pos < nsample) {
+          const int bit = __ffs(x) - 1;
+          out[d * nsample + pos++] = (wb + lane) * 32 + bit;
+          x &= x - 1;
+        }
+        cntd[d] += total;
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < kMaxDepths; ++d)
+      if (d < nd)
+        for (int sl = min(cntd[d], nsample) + lane; sl < nsample; sl += 32) out[d * nsample + sl] = firstd[d];
+    return;
+  }
+
   // ---- read the bitmap back in index order: first nsample hits, the rest padded with the first hit ----
   int *out = idx + qi * (size_t)nsample;
   int cnt = 0, first = 0;
@@ -339,11 +414,13 @@ __global__ void __launch_bounds__(kGridQueryWarps * 32, 5) grid_query_kernel(con
 constexpr int kQueryWarps = 8;
 constexpr int kQueryTile = 2016;  // points per shared-memory tile (23.6 KB, multiple of 32), two buffers fit the 48 KB static limit
 
-template <bool CYL, int QPW>
+// MULTI (CYL, QPW = kMaxDepths): the QPW slots of a warp are the nd depths of ONE query (hmax = hm.v[slot]) instead of
+// QPW different queries; idx is [b, m, nd, nsample].
+template <bool CYL, int QPW, bool MULTI = false>
 __global__ void __launch_bounds__(kQueryWarps * 32) query_kernel(const float *__restrict__ new_xyz, const float *__restrict__ xyz,
                                                                  const float *__restrict__ rot, int *__restrict__ idx, int n,
                                                                  int m, float radius2, float hmin, float hmax, int nsample,
-                                                                 int use_bulk, const GridHeader *__restrict__ hdr) {
+                                                                 int use_bulk, const GridHeader *__restrict__ hdr, HMax4 hm, int nd) {
   __shared__ __align__(128) float tile[2][kQueryTile * 3];
   __shared__ uint64_t full[2];
 
@@ -351,17 +428,19 @@ __global__ void __launch_bounds__(kQueryWarps * 32) query_kernel(const float *__
   if (hdr && hdr[scene].use_grid) return;  // this scene was answered by grid_query_kernel
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   xyz += (size_t)scene * n * 3;
-  const int q0 = (blockIdx.x * kQueryWarps + warp) * QPW;  // first query of this warp
+  const int q0 = (blockIdx.x * kQueryWarps + warp) * (MULTI ? 1 : QPW);  // first query of this warp
 
   float qx[QPW], qy[QPW], qz[QPW];
   float r[CYL ? QPW : 1][9];
+  float hmx[QPW];
   int cnt[QPW], first[QPW];
   int *out[QPW];
 #pragma unroll
   for (int q = 0; q < QPW; ++q) {
-    const int j = q0 + q;
-    const bool ok = j < m;
-    const size_t qi = (size_t)scene * m + (ok ? j : 0);
+    const int j = MULTI ? q0 : q0 + q;
+    const bool ok = j < m && (!MULTI || q < nd);
+    const size_t qi = (size_t)scene * m + (j < m ? j : 0);
+    hmx[q] = MULTI ? hm.v[q] : hmax;
     qx[q] = __ldg(new_xyz + qi * 3), qy[q] = __ldg(new_xyz + qi * 3 + 1), qz[q] = __ldg(new_xyz + qi * 3 + 2);
     if (CYL) {
 #pragma unroll
@@ -369,7 +448,7 @@ __global__ void __launch_bounds__(kQueryWarps * 32) query_kernel(const float *__
     }
     cnt[q] = ok ? 0 : nsample;  // out-of-range queries are "already full"
     first[q] = 0;
-    out[q] = idx + qi * (size_t)nsample;
+    out[q] = MULTI ? idx + (qi * (size_t)nd + (q < nd ? q : 0)) * nsample : idx + qi * (size_t)nsample;
   }
 
   const int ntiles = (n + kQueryTile - 1) / kQueryTile;
@@ -418,7 +497,7 @@ __global__ void __launch_bounds__(kQueryWarps * 32) query_kernel(const float *__
 #pragma unroll
         for (int q = 0; q < QPW; ++q) {
           if (cnt[q] < nsample) {  // warp uniform
-            const bool hit = valid && (CYL ? cyl_hit(r[q], qx[q], qy[q], qz[q], x, y, z, radius2, hmin, hmax)
+            const bool hit = valid && (CYL ? cyl_hit(r[q], qx[q], qy[q], qz[q], x, y, z, radius2, hmin, hmx[q])
                                            : ball_hit(qx[q], qy[q], qz[q], x, y, z, radius2));
             const unsigned mask = __ballot_sync(0xffffffffu, hit);
             if (mask) {
@@ -446,7 +525,7 @@ __global__ void __launch_bounds__(kQueryWarps * 32) query_kernel(const float *__
   // tail: slots [cnt, nsample) take the first hit; zeros when there was none (ball_query.cpp:24-26 relies on zeros)
 #pragma unroll
   for (int q = 0; q < QPW; ++q) {
-    if (q0 + q < m) {
+    if (MULTI ? (q0 < m && q < nd) : (q0 + q < m)) {
       const int c = min(cnt[q], nsample);
       const int fill = c > 0 ? first[q] : 0;
       for (int s = c + lane; s < nsample; s += 32) out[q][s] = fill;
@@ -454,9 +533,11 @@ __global__ void __launch_bounds__(kQueryWarps * 32) query_kernel(const float *__
   }
 }
 
-template <bool CYL>
+// nd = 0: one index list per query, [b, m, nsample].  nd >= 1 (cylinder only): nd nested depths hm.v[0..nd), hmax = the
+// largest of them, idx [b, m, nd, nsample].
+template <bool CYL, bool MULTI = false>
 static int launch_query(const float *new_xyz, const float *xyz, const float *rot, int *idx, int b, int n, int m, float radius,
-                        float hmin, float hmax, int nsample, cudaStream_t s) {
+                        float hmin, float hmax, int nsample, cudaStream_t s, HMax4 hm = HMax4{{0.f, 0.f, 0.f, 0.f}}, int nd = 0) {
   if (b < 0 || n <= 0 || m < 0 || nsample <= 0) return (int)cudaErrorInvalidValue;
   if (b == 0 || m == 0) return 0;  // nothing to do (empty tensors have null data pointers)
   if (!new_xyz || !xyz || !idx || (CYL && !rot)) return (int)cudaErrorInvalidValue;
@@ -479,15 +560,15 @@ static int launch_query(const float *new_xyz, const float *xyz, const float *rot
     // radius of a sphere around the query that contains the search region (rounded up)
     double reach = fabs((double)radius);
     if (CYL) {
-      const double hm = fmax(fabs((double)hmin), fabs((double)hmax));
-      reach = sqrt(reach * reach + hm * hm);
+      const double hh = fmax(fabs((double)hmin), fabs((double)hmax));
+      reach = sqrt(reach * reach + hh * hh);
     }
     const float reachf = (float)(reach * (1.0 + 1e-6));
     const float cell_frac = g_tuning.grid_cell_pct > 0 ? 0.01f * g_tuning.grid_cell_pct : 0.5f;
     grid_build_kernel<<<b, kGridThreads, 0, s>>>(xyz, n, reachf, g_tuning.query_mode == 2 ? 1 : 0, cell_frac, sorted, cell_start, hdr);
     count_launch();
     const size_t smem = (size_t)words * kGridQueryWarps * sizeof(unsigned);
-    auto kern = grid_query_kernel<CYL>;
+    auto kern = grid_query_kernel<CYL, MULTI>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       cudaFreeAsync(scratch, s);
@@ -495,8 +576,17 @@ static int launch_query(const float *new_xyz, const float *xyz, const float *rot
     }
     kern<<<dim3((m + kGridQueryWarps - 1) / kGridQueryWarps, b), kGridQueryWarps * 32, smem, s>>>(new_xyz, sorted, cell_start, hdr, rot, idx, n, m,
                                                                                                  fabsf(radius), radius2, reachf, hmin, hmax, nsample,
-                                                                                                 words);
+                                                                                                 words, xyz, hm, nd);
     count_launch();
+  }
+  if (MULTI) {
+    dim3 grid((m + kQueryWarps - 1) / kQueryWarps, b);
+    query_kernel<CYL, kMaxDepths, true><<<grid, kQueryWarps * 32, 0, s>>>(new_xyz, xyz, rot, idx, n, m, radius2, hmin, hmax, nsample, use_bulk,
+                                                                           hdr, hm, nd);
+    count_launch();
+    const int rc = finish_launch();
+    if (scratch) cudaFreeAsync(scratch, s);
+    return rc;
   }
   int qpw = g_tuning.query_qpw;
   if (qpw != 1 && qpw != 2 && qpw != 4) {
@@ -506,9 +596,9 @@ static int launch_query(const float *new_xyz, const float *xyz, const float *rot
   const int per_cta = kQueryWarps * qpw;
   dim3 grid((m + per_cta - 1) / per_cta, b);
   switch (qpw) {
-    case 4: query_kernel<CYL, 4><<<grid, kQueryWarps * 32, 0, s>>>(new_xyz, xyz, rot, idx, n, m, radius2, hmin, hmax, nsample, use_bulk, hdr); break;
-    case 2: query_kernel<CYL, 2><<<grid, kQueryWarps * 32, 0, s>>>(new_xyz, xyz, rot, idx, n, m, radius2, hmin, hmax, nsample, use_bulk, hdr); break;
-    default: query_kernel<CYL, 1><<<grid, kQueryWarps * 32, 0, s>>>(new_xyz, xyz, rot, idx, n, m, radius2, hmin, hmax, nsample, use_bulk, hdr); break;
+    case 4: query_kernel<CYL, 4><<<grid, kQueryWarps * 32, 0, s>>>(new_xyz, xyz, rot, idx, n, m, radius2, hmin, hmax, nsample, use_bulk, hdr, hm, nd); break;
+    case 2: query_kernel<CYL, 2><<<grid, kQueryWarps * 32, 0, s>>>(new_xyz, xyz, rot, idx, n, m, radius2, hmin, hmax, nsample, use_bulk, hdr, hm, nd); break;
+    default: query_kernel<CYL, 1><<<grid, kQueryWarps * 32, 0, s>>>(new_xyz, xyz, rot, idx, n, m, radius2, hmin, hmax, nsample, use_bulk, hdr, hm, nd); break;
   }
   count_launch();
   const int rc = finish_launch();
@@ -526,4 +616,19 @@ extern "C" int gb_ball_query(const float *new_xyz, const float *xyz, int *idx, i
 extern "C" int gb_cylinder_query(const float *new_xyz, const float *xyz, const float *rot, int *idx, int b, int n, int m,
                                  float radius, float hmin, float hmax, int nsample, gb_stream_t stream) {
   return gb::launch_query<true>(new_xyz, xyz, rot, idx, b, n, m, radius, hmin, hmax, nsample, (cudaStream_t)stream);
+}
+
+/* Multi-depth cylinder query: nd (1..4) nested cylinders per seed that differ in hmax only -- the loop over hmax_list of
+ * GraspWidthGrouping.forward (TrainModel/modules.py:104-113), which calls cylinder_query once per depth.  One scan;
+ * idx [b, m, nd, nsample]: idx[:, :, d, :] is bit-identical to gb_cylinder_query(..., hmax[d], ...). */
+extern "C" int gb_cylinder_query_multi(const float *new_xyz, const float *xyz, const float *rot, int *idx, int b, int n, int m,
+                                       float radius, float hmin, const float *hmax, int ndepth, int nsample, gb_stream_t stream) {
+  if (!hmax || ndepth < 1 || ndepth > gb::kMaxDepths) return (int)cudaErrorInvalidValue;
+  gb::HMax4 hm;
+  float top = hmax[0];  // the largest non-NaN depth bounds the scan; a NaN depth matches nothing (x_rot < NaN is false)
+  for (int d = 0; d < gb::kMaxDepths; ++d) {
+    hm.v[d] = hmax[d < ndepth ? d : 0];
+    if (d < ndepth && hmax[d] == hmax[d] && (top != top || hmax[d] > top)) top = hmax[d];
+  }
+  return gb::launch_query<true, true>(new_xyz, xyz, rot, idx, b, n, m, radius, hmin, top, nsample, (cudaStream_t)stream, hm, ndepth);
 }

@@ -1,0 +1,55 @@
+"""Drop-in for the grasp-crop grouping of TrainModel/modules.py (the caller right above the hot path).
+
+GraspWidthGrouping (modules.py:87-124) builds one CylinderQueryAndGroup per entry of hmax_list and calls them in a loop with
+the same seeds, approach rotations, radius and hmin -- four scans of the cloud whose cylinders are nested -- then stacks
+the four [B,3,num_seed,nsample] results along a new depth axis and views them as [B,3,num_seed*num_depth,nsample].
+Here the loop is ONE multi-depth scan (gb_cylinder_query_multi, index lists laid out [B,num_seed,num_depth,nsample]) and
+ONE grouped-coordinate launch that writes the stacked tensor directly (gb_group_xyz with nsample' = num_depth*nsample):
+bit-identical to the loop, 2 launches instead of 4 x (query + group + the stack copy).
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import pointnet2_utils as pu
+
+
+def _shared_mlp(dims):
+    """Conv2d(1x1, no bias) + BatchNorm2d + ReLU per layer: what pt_utils.SharedMLP(dims, bn=True) builds (pytorch_utils.py)."""
+    layers = []
+    for i in range(len(dims) - 1):
+        layers += [nn.Conv2d(dims[i], dims[i + 1], kernel_size=1, bias=False), nn.BatchNorm2d(dims[i + 1]), nn.ReLU(inplace=True)]
+    return nn.Sequential(*layers)
+
+
+class GraspWidthGrouping(nn.Module):
+    """modules.py:87-124.  `groupers` keeps the reference's per-depth CylinderQueryAndGroup list (same constructor
+    arguments) for callers that index it; forward() uses the fused path whenever the inputs allow it."""
+
+    def __init__(self, nsample, seed_feature_dim, cylinder_radius=0.05, hmin=-0.02, hmax_list=(0.01, 0.02, 0.03, 0.04), mlps=None):
+        super().__init__()
+        self.nsample = nsample
+        self.in_dim = seed_feature_dim
+        self.cylinder_radius = cylinder_radius
+        self.hmin = hmin
+        self.hmax_list = list(hmax_list)
+        self.groupers = [pu.CylinderQueryAndGroup(cylinder_radius, hmin, hmax, nsample, use_xyz=True) for hmax in self.hmax_list]
+        self.mlps = _shared_mlp([self.in_dim, 64, 128, 256]) if mlps is None else mlps
+
+    def group(self, seed_xyz, pointcloud, vp_rot):
+        """The grouped coordinates of all depths, [B, 3, num_seed*num_depth, nsample] (modules.py:107-117)."""
+        B, num_seed = vp_rot.shape[0], vp_rot.shape[1]
+        D = len(self.hmax_list)
+        if 1 <= D <= 4 and pu._fusable(pointcloud, seed_xyz, vp_rot):
+            rot = vp_rot.reshape(B, num_seed, 9)
+            idx = pu.cylinder_query_multi(self.cylinder_radius, self.hmin, self.hmax_list, self.nsample, pointcloud, seed_xyz, rot)
+            g = pu._FusedQueryGroup.apply(pointcloud, seed_xyz, idx.view(B, num_seed, D * self.nsample), rot, None, None)
+            return g.view(B, 3, num_seed * D, self.nsample)
+        grouped = torch.stack([grouper(pointcloud, seed_xyz, vp_rot) for grouper in self.groupers], dim=3)
+        return grouped.view(B, -1, num_seed * D, self.nsample)
+
+    def forward(self, seed_xyz, pointcloud, vp_rot):
+        B, num_seed = vp_rot.shape[0], vp_rot.shape[1]
+        vp_features = self.mlps(self.group(seed_xyz, pointcloud, vp_rot))
+        vp_features = F.max_pool2d(vp_features, kernel_size=[1, vp_features.size(3)])
+        return vp_features.view(B, -1, num_seed, len(self.hmax_list))

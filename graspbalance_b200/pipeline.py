@@ -10,8 +10,10 @@ Stages and the reference call sites they reproduce:
              variant B; radii/nsample from drp.py:169-247.
   FP1, FP2   PointnetFPModule.forward (pointnet2_modules.py:407-435): three_nn -> weights -> three_interpolate.
   UP         seed features back to the full cloud (TrainModel/graspbalance.py:37-41): three_nn + three_interpolate, C=256.
-  CROP       4 GraspWidthGrouping x 4 depths = 16 CylinderQueryAndGroup calls (TrainModel/modules.py:104-124,
-             graspbalance.py:84-87,123: radii 0.08 x {.25,.5,.75,1}, hmin -0.02, hmax {.01,.02,.03,.04}, nsample 64).
+  CROP       4 GraspWidthGrouping x 4 depths = 16 CylinderQueryAndGroup calls in the reference (TrainModel/modules.py:104-124,
+             graspbalance.py:84-87,123: radii 0.08 x {.25,.5,.75,1}, hmin -0.02, hmax {.01,.02,.03,.04}, nsample 64); here
+             each GraspWidthGrouping is one multi-depth scan + one grouped-coordinate launch (graspbalance_b200/modules.py,
+             bit-identical to the loop; `fused_crops=False` runs the reference's 16 separate calls).
   COLLISION  ModelFreeCollisionDetector.detect's occupancy test for 1024 grasps per scene (collision_detector.py:16-64).
 Every grouped / interpolated feature tensor is back-propagated with a random upstream gradient through the reference's
 autograd Functions (GroupingOperation / GatherOperation / ThreeInterpolate backward).
@@ -26,6 +28,7 @@ import torch
 from . import group as gb_group
 from . import pointnet2_utils as pu
 from .collision_detector import collision_counts
+from .modules import GraspWidthGrouping
 
 # (npoint, radius, nsample, C_in) of the four SA modules and (blocks, C, radius, nsample) of the InvResMLP groups
 SA_SPECS = [(2048, 0.04, 64, 0), (1024, 0.1, 32, 128), (512, 0.2, 16, 256), (256, 0.3, 16, 256)]
@@ -44,7 +47,7 @@ def _randn(shape, gen, device):
 class OpPipeline:
     """Holds the stand-in feature / gradient tensors (allocated once, outside any timed region) and runs the chain."""
 
-    def __init__(self, batch, n_points=20000, device="cuda", seed=0, backward=True, overlap=True):
+    def __init__(self, batch, n_points=20000, device="cuda", seed=0, backward=True, overlap=True, fused_crops=True):
         self.B, self.N, self.device, self.backward = batch, n_points, torch.device(device), backward
         # overlap: the sampling chain (4 x FPS + gather: latency-bound, a few warps per SM, depends on xyz only) and the
         # collision tests (independent of everything else) run on side streams next to the bandwidth-bound grouping work
@@ -58,8 +61,9 @@ class OpPipeline:
         self.sa_groupers = [pu.QueryAndGroup(r, ns, use_xyz=True, ret_grouped_xyz=True, normalize_xyz=True)
                             for (_, r, ns, _) in SA_SPECS]
         self.irm_groupers = [gb_group.QueryAndGroup(r, ns) for (_, _, r, ns) in IRM_SPECS]
-        self.crop_groupers = [[pu.CylinderQueryAndGroup(r, CROP_HMIN, h, 64, use_xyz=True) for h in CROP_HMAX]
-                              for r in CROP_RADII]
+        self.fused_crops = fused_crops
+        self.crop_modules = [GraspWidthGrouping(64, 3, cylinder_radius=r, hmin=CROP_HMIN, hmax_list=CROP_HMAX, mlps=torch.nn.Identity())
+                             for r in CROP_RADII]
         # stand-ins for MLP outputs (features entering each stage) and for upstream gradients
         self.sa_in_feats = [None] + [_randn((B, c, SA_SPECS[i - 1][0]), gen, self.device) for i, (_, _, _, c) in
                                      enumerate(SA_SPECS) if i > 0]
@@ -88,13 +92,13 @@ class OpPipeline:
 
     def _crops(self, xyz, view_rot, sa2_xyz, out):
         # ---- grasp crop: 4 radii x 4 depths cylinder query + group (seeds = fp2_xyz: 1024 points, drp.py:301-303) ----
-        crop_sum = None
-        for groupers in self.crop_groupers:
-            for gq in groupers:
-                g = gq(xyz, sa2_xyz, view_rot)  # [B,3,1024,64]
-                s = g[:, :, :4].sum()  # small contiguous slices: the checksums only give the step a result to return
-                crop_sum = s if crop_sum is None else crop_sum + s
-        out["crop_checksum"] = crop_sum
+        parts = []  # small slices: the checksum only gives the step a result to return
+        for mod in self.crop_modules:
+            if self.fused_crops:
+                parts.append(mod.group(sa2_xyz, xyz, view_rot)[:, :, :16])  # [B,3,1024*4,64] -> seeds 0..3 x 4 depths
+            else:
+                parts += [gq(xyz, sa2_xyz, view_rot)[:, :, :4] for gq in mod.groupers]  # 4 x [B,3,1024,64]
+        out["crop_checksum"] = torch.cat([p.reshape(-1) for p in parts]).sum()
 
     def _interpolation(self, xyz, sa2_xyz, sa3_xyz, sa4_xyz, out):
         bw = self.backward
@@ -222,8 +226,9 @@ def algorithmic_bytes_per_scene(n=20000, backward=True):
         by["interp_fwd"] += 4 * 256 * mm + 24 * nn + 4 * 256 * nn
         if backward:
             by["interp_bwd"] += 4 * 256 * mm + 24 * nn + 4 * 256 * nn
-    by["cylinder_query"] += 16 * (12 * n + 48 * NUM_SEED + 4 * NUM_SEED * 64)
-    by["group_fwd"] += 16 * (4 * 3 * n + 4 * NUM_SEED * 64 + 4 * 3 * NUM_SEED * 64)
+    # grasp crops: per radius the cloud, seeds and rotations are read once for the four depths
+    by["cylinder_query"] += 4 * (12 * n + 48 * NUM_SEED + 4 * 4 * NUM_SEED * 64)
+    by["group_fwd"] += 4 * (4 * 3 * n + 4 * 4 * NUM_SEED * 64 + 4 * 3 * 4 * NUM_SEED * 64)
     by["collision"] += 24 * 5000 + 120 * NUM_GRASP + NUM_GRASP
     return by
 

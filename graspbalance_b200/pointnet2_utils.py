@@ -125,6 +125,24 @@ class CylinderQuery(Function):
 cylinder_query = CylinderQuery.apply
 
 
+class CylinderQueryMulti(Function):
+    """All depths of GraspWidthGrouping's loop over hmax_list (TrainModel/modules.py:104-113) in one scan:
+    idx [B,npoint,D,nsample] with idx[:, :, d] == cylinder_query(radius, hmin, hmax_list[d], nsample, xyz, new_xyz, rot)."""
+
+    @staticmethod
+    def forward(ctx, radius, hmin, hmax_list, nsample, xyz, new_xyz, rot):
+        idx = _ext.cylinder_query_multi(new_xyz, xyz, rot, radius, hmin, list(hmax_list), nsample)
+        ctx.mark_non_differentiable(idx)
+        return idx
+
+    @staticmethod
+    def backward(ctx, a=None):
+        return (None,) * 7
+
+
+cylinder_query_multi = CylinderQueryMulti.apply
+
+
 class RandomDropout(nn.Module):
     """pointnet2_utils.py:35-43.  The reference calls pt_utils.feature_dropout_no_scaling, which its pytorch_utils.py
     does not define; this keeps the constructor and applies an unscaled whole-channel dropout with rate U(0, p)."""

@@ -69,6 +69,13 @@ GB_API int gb_ball_query(const float *new_xyz, const float *xyz, int *idx, int b
 GB_API int gb_cylinder_query(const float *new_xyz, const float *xyz, const float *rot, int *idx, int b, int n, int m,
                       float radius, float hmin, float hmax, int nsample, gb_stream_t stream);
 
+/* The depth loop of GraspWidthGrouping.forward (TrainModel/modules.py:104-113 calls CylinderQueryAndGroup once per hmax of
+ * hmax_list with the same seeds, rotations, radius and hmin): ndepth (1..4) nested cylinders per seed in ONE scan.
+ * hmax = HOST array of ndepth floats.  idx [b, m, ndepth, nsample] i32: idx[:, :, d, :] is bit-identical to what
+ * gb_cylinder_query(..., hmax[d], ...) writes. */
+GB_API int gb_cylinder_query_multi(const float *new_xyz, const float *xyz, const float *rot, int *idx, int b, int n, int m,
+                            float radius, float hmin, const float *hmax, int ndepth, int nsample, gb_stream_t stream);
+
 /* A: group_points_kernel_wrapper (group_points_gpu.cu:51-65); B: group_points_kernel_launcher_fast (:58-70).
  * points [b,c,n], idx [b,npoints,nsample] -> out [b,c,npoints,nsample]. */
 GB_API int gb_group_fwd(const float *points, const int *idx, float *out, int b, int c, int n, int npoints, int nsample,

@@ -112,6 +112,12 @@ def cylinder_query(radius, hmin, hmax, nsample, xyz, new_xyz, rot):
     return idx
 
 
+def cylinder_query_multi(radius, hmin, hmax_list, nsample, xyz, new_xyz, rot):
+    """The loop over hmax_list of GraspWidthGrouping.forward (TrainModel/modules.py:104-113), one cylinder_query per depth;
+    stacked along a depth axis: idx [B, m, D, nsample]."""
+    return np.stack([cylinder_query(radius, hmin, h, nsample, xyz, new_xyz, rot) for h in hmax_list], axis=2)
+
+
 def grouping_operation(features, idx):
     features, idx = _f32(features), _i32(idx)
     B, C, N = features.shape

@@ -160,3 +160,68 @@ def test_strided_group_entries_match_the_contiguous_ones(dev):
         _lib.call("gb_group_bwd_strided", gout, gout.data_ptr() + 4 * pad * per, idx.data_ptr(), got.data_ptr(), B, C, N, m, ns,
                   (pad + C) * per, 1)
         assert (got - want_g).abs().max().item() <= 1e-5 * max(want_g.abs().max().item(), 1e-30)
+
+
+# ---- multi-depth grasp crop (TrainModel/modules.py:87-124) -------------------------------------------------
+def _crop_inputs(dev, B, N, m, seed, kind="tabletop"):
+    xyz, new_xyz, _ = _inputs(dev, B, N, m, 0, seed, kind)
+    rng = np.random.default_rng(seed + 1)
+    v = rng.normal(size=(B, m, 3)).astype(np.float32)
+    rot = scenes.viewpoint_rotations(-v, rng.uniform(0, np.pi, (B, m)).astype(np.float32)).astype(np.float32)
+    return xyz, new_xyz, rot
+
+
+@pytest.mark.parametrize("B,N,m,ns,radius,hmaxs", [
+    (2, 20000, 128, 64, 0.05, [0.01, 0.02, 0.03, 0.04]),       # cell-grid path, the model's depths
+    (2, 20000, 64, 16, 0.08, [0.04, 0.01, 0.03, 0.02]),        # unsorted depths, lists that fill up early
+    (1, 20000, 40, 64, 0.02, [0.01, 0.04]),                    # two depths, sparse hits (padding with the first hit)
+    (2, 3000, 50, 16, 0.05, [0.01, 0.02, 0.03, 0.04]),         # full-scan path (n < 4096)
+    (1, 500, 9, 5, 0.05, [0.02]),                              # one depth
+    (2, 6000, 33, 32, 0.05, [0.03, 0.03, float("nan")]),       # duplicate and NaN depths
+    (1, 5000, 16, 8, 0.05, [-0.05, 0.0, 0.01, 0.04]),          # hmax below hmin: an empty cylinder
+    (1, 8000, 24, 64, 0.6, [0.01, 0.02, 0.03, 0.04]),          # radius comparable to the scene: the grid declines
+])
+def test_cylinder_query_multi_matches_one_call_per_depth(dev, B, N, m, ns, radius, hmaxs):
+    xyz, new_xyz, rot = _crop_inputs(dev, B, N, m, 61)
+    x, q, R = T(xyz, dev), T(new_xyz, dev), T(rot.reshape(B, m, 9), dev)
+    got = pu.cylinder_query_multi(radius, -0.02, hmaxs, ns, x, q, R)
+    assert got.shape == (B, m, len(hmaxs), ns) and got.dtype == torch.int32
+    want = oracle.cylinder_query_multi(radius, -0.02, hmaxs, ns, xyz, new_xyz, np.ascontiguousarray(rot.reshape(B, m, 9)))
+    assert np.array_equal(got.cpu().numpy(), want)
+    for d, h in enumerate(hmaxs):  # and against the product's own single-depth entry point
+        assert torch.equal(got[:, :, d], pu.cylinder_query(radius, -0.02, h, ns, x, q, R))
+
+
+def test_cylinder_query_multi_uniform_and_degenerate_rotations(dev):
+    B, N, m, ns = 2, 12000, 48, 32
+    xyz, new_xyz, rot = _crop_inputs(dev, B, N, m, 71, kind="uniform")
+    rot[0, :8] *= 1.5          # not orthonormal: the grid path searches every cell for these seeds
+    rot[1, 3] = np.nan
+    xyz[1, 100] = np.inf
+    hmaxs = [0.01, 0.02, 0.03, 0.04]
+    x, q, R = T(xyz, dev), T(new_xyz, dev), T(rot.reshape(B, m, 9), dev)
+    got = pu.cylinder_query_multi(0.1, -0.02, hmaxs, ns, x, q, R)
+    want = oracle.cylinder_query_multi(0.1, -0.02, hmaxs, ns, xyz, new_xyz, np.ascontiguousarray(rot.reshape(B, m, 9)))
+    assert np.array_equal(got.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("B,N,m,ns", [(2, 20000, 128, 64), (1, 2500, 30, 16)])
+def test_grasp_width_grouping_matches_the_reference_loop(dev, B, N, m, ns):
+    """GraspWidthGrouping.group() == torch.stack of the per-depth CylinderQueryAndGroup results viewed as
+    [B, 3, num_seed*num_depth, nsample] (modules.py:107-117); the product's per-depth groupers give the loop."""
+    from graspbalance_b200.modules import GraspWidthGrouping
+    torch.backends.cuda.matmul.allow_tf32 = False
+    xyz, new_xyz, rot = _crop_inputs(dev, B, N, m, 81)
+    x, q, R = T(xyz, dev), T(new_xyz, dev), T(rot, dev)
+    mod = GraspWidthGrouping(ns, 3, cylinder_radius=0.05, hmin=-0.02, hmax_list=[0.01, 0.02, 0.03, 0.04]).to(dev)
+    got = mod.group(q, x, R)
+    loop = torch.stack([g(x, q, R) for g in mod.groupers], dim=3).view(B, -1, m * 4, ns)
+    assert got.shape == loop.shape == (B, 3, m * 4, ns)
+    assert torch.equal(got, loop)  # same kernels, same arithmetic: bit-exact
+    # and against the literal restatement of the reference module on the oracle's indices
+    for d, h in enumerate(mod.hmax_list):
+        idx = T(oracle.cylinder_query(0.05, -0.02, h, ns, xyz, new_xyz, np.ascontiguousarray(rot.reshape(B, m, 9))), dev)
+        want, _ = reference_query_and_group(idx, x, q, None, 0.05, False, rot=R)
+        assert (got.view(B, 3, m, 4, ns)[:, :, :, d] - want).abs().max().item() <= 1e-6
+    out = mod.eval()(q, x, R)
+    assert out.shape == (B, 256, m, 4)

@@ -26,3 +26,17 @@ def test_overlapped_schedule_matches_single_stream(dev):
     np.testing.assert_array_equal(a["collision_counts"], b["collision_counts"])
     for k in ("up_checksum", "crop_checksum", "grad_checksum"):
         assert abs(float(a[k]) - float(b[k])) <= 1e-4 * max(1.0, abs(float(a[k]))), k
+
+
+def test_fused_grasp_crops_match_the_sixteen_separate_calls(dev):
+    import bench
+    from graspbalance_b200 import pipeline
+    host, offs = bench.make_host_inputs([5, 6], pin=False)
+    sums = []
+    for fused in (False, True):
+        pipe = pipeline.OpPipeline(2, bench.N_POINTS, dev, seed=0, backward=False, overlap=False, fused_crops=fused)
+        xyz, rot, grasps = bench.to_device(host, offs, dev)
+        o = pipe.run(xyz, rot, None)
+        torch.cuda.synchronize()
+        sums.append(float(o["crop_checksum"]))
+    assert abs(sums[0] - sums[1]) <= 1e-4 * max(1.0, abs(sums[0]))
