@@ -35,13 +35,14 @@ __device__ __forceinline__ uint32_t fps_tiekey_inv(uint32_t tk, int L) {
 
 struct FpsShared {
   uint32_t wc[2][32][8];  // per-warp candidates, double buffered by round parity: key, tiekey, x, y, z
-  uint32_t cc[2][16][8];  // per-CTA candidates received from the cluster (slot = sender rank)
-  uint64_t full[2];       // mbarriers: C * 20 bytes of st.async payload per round
+  uint32_t cc[2][32][8];  // candidates received from the cluster: slot = sender rank (per-CTA winners), or sender rank * W + warp
+                          // in direct mode (every warp's winner, at most 32 of them)
+  uint64_t full[2];       // mbarriers: 20 bytes of st.async payload per candidate per round
 };
 
 template <int P, int T>
 __global__ void __launch_bounds__(T, 1) fps_cluster_kernel(const float *__restrict__ xyz, float *__restrict__ temp,
-                                                           int *__restrict__ idxs, int n, int m, int variant, int L) {
+                                                           int *__restrict__ idxs, int n, int m, int variant, int L, int direct) {
   extern __shared__ float s_pts[];  // [3][P*T] copy of this CTA's coordinates (winner lookup without dynamic register indexing)
   __shared__ __align__(16) FpsShared sh;
 
@@ -91,14 +92,16 @@ __global__ void __launch_bounds__(T, 1) fps_cluster_kernel(const float *__restri
 
   uint32_t phases = 0u;  // bit p = parity to wait for on full[p]
   uint32_t cc0 = 0, cc1 = 0, bar0 = 0, bar1 = 0;  // this lane's push targets in CTA `lane` (slot = my rank), per parity
-  if (C > 1 && warp == 0 && lane < (int)C) {
-    cc0 = mapa_u32(smem_u32(&sh.cc[0][rank][0]), lane), cc1 = mapa_u32(smem_u32(&sh.cc[1][rank][0]), lane);
+  if (C > 1 && (warp == 0 || direct) && lane < (int)C) {
+    const int slot = direct ? (int)rank * W + warp : (int)rank;
+    cc0 = mapa_u32(smem_u32(&sh.cc[0][slot][0]), lane), cc1 = mapa_u32(smem_u32(&sh.cc[1][slot][0]), lane);
     bar0 = mapa_u32(smem_u32(&sh.full[0]), lane), bar1 = mapa_u32(smem_u32(&sh.full[1]), lane);
   }
+  const uint32_t ncand = direct ? C * W : C;  // candidates every CTA receives per round
 
   for (int j = 1; j < m; ++j) {
     const int par = j & 1;
-    if (C > 1 && tid == 0) mbar_arrive_expect_tx(&sh.full[par], C * 20u);
+    if (C > 1 && tid == 0) mbar_arrive_expect_tx(&sh.full[par], ncand * 20u);
 
     // 1. register-resident update + per-thread argmax (first strict maximum == lowest k among this thread's points)
     int bkey = kKeyNone, bi = 0;
@@ -114,29 +117,46 @@ __global__ void __launch_bounds__(T, 1) fps_cluster_kernel(const float *__restri
     const int wkey = __reduce_max_sync(0xffffffffu, bkey);
     const uint32_t tk = (bkey == wkey && bkey != kKeyNone) ? fps_tiekey(g + bi * stride, L) : 0xFFFFFFFFu;
     const uint32_t wtk = __reduce_min_sync(0xffffffffu, tk);
-    if (tk == wtk && bkey == wkey) {  // unique lane unless the whole warp is ineligible (then all write the same words)
-      uint32_t *w = sh.wc[par][warp];
-      const int s = bi * T + tid;
-      *reinterpret_cast<uint4 *>(w) = make_uint4((uint32_t)wkey, wtk, __float_as_uint(sx[s]), __float_as_uint(sy[s]));
-      w[4] = __float_as_uint(sz[s]);
-    }
-    __syncthreads();
-    // 3. every warp reduces the W warp candidates
+    const bool win = tk == wtk && bkey == wkey;  // unique lane unless the whole warp is ineligible (then all hold the same words)
     uint32_t ckey_u = (uint32_t)kKeyNone, ctk = 0xFFFFFFFFu, ux = 0, uy = 0, uz = 0;
-    if (lane < W) {
-      const uint4 v = *reinterpret_cast<const uint4 *>(sh.wc[par][lane]);
-      ckey_u = v.x, ctk = v.y, ux = v.z, uy = v.w;
-      uz = sh.wc[par][lane][4];
+    int key;
+    uint32_t mtk, btk;
+    int src;
+    if (direct) {
+      // 3'. DIRECT mode (C * W <= 32): every warp pushes its own winner to all C CTAs; no CTA-level stage at all (no shared
+      // memory round trip, no __syncthreads, one reduction level less on the critical path of the round)
+      if (win) {
+        const int s = bi * T + tid;
+        ux = __float_as_uint(sx[s]), uy = __float_as_uint(sy[s]), uz = __float_as_uint(sz[s]);
+      }
+      src = __ffs(__ballot_sync(0xffffffffu, win)) - 1;
+      ux = __shfl_sync(0xffffffffu, ux, src), uy = __shfl_sync(0xffffffffu, uy, src), uz = __shfl_sync(0xffffffffu, uz, src);
+      key = wkey, btk = wtk;
+    } else {
+      if (win) {
+        uint32_t *w = sh.wc[par][warp];
+        const int s = bi * T + tid;
+        *reinterpret_cast<uint4 *>(w) = make_uint4((uint32_t)wkey, wtk, __float_as_uint(sx[s]), __float_as_uint(sy[s]));
+        w[4] = __float_as_uint(sz[s]);
+      }
+      __syncthreads();
+      // 3. every warp reduces the W warp candidates
+      if (lane < W) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(sh.wc[par][lane]);
+        ckey_u = v.x, ctk = v.y, ux = v.z, uy = v.w;
+        uz = sh.wc[par][lane][4];
+      }
+      key = __reduce_max_sync(0xffffffffu, (int)ckey_u);
+      mtk = ((int)ckey_u == key) ? ctk : 0xFFFFFFFFu;
+      btk = __reduce_min_sync(0xffffffffu, mtk);
+      src = __ffs(__ballot_sync(0xffffffffu, (int)ckey_u == key && ctk == btk)) - 1;
+      ux = __shfl_sync(0xffffffffu, ux, src), uy = __shfl_sync(0xffffffffu, uy, src), uz = __shfl_sync(0xffffffffu, uz, src);
     }
-    int key = __reduce_max_sync(0xffffffffu, (int)ckey_u);
-    uint32_t mtk = ((int)ckey_u == key) ? ctk : 0xFFFFFFFFu;
-    uint32_t btk = __reduce_min_sync(0xffffffffu, mtk);
-    int src = __ffs(__ballot_sync(0xffffffffu, (int)ckey_u == key && ctk == btk)) - 1;
-    ux = __shfl_sync(0xffffffffu, ux, src), uy = __shfl_sync(0xffffffffu, uy, src), uz = __shfl_sync(0xffffffffu, uz, src);
 
     if (C > 1) {
-      // 4. push this CTA's winner to every CTA of the cluster (lane r -> CTA r), then wait for all C candidates
-      if (warp == 0 && lane < (int)C) {
+      // 4. push the winner (of this CTA; of this warp in direct mode) to every CTA of the cluster (lane r -> CTA r), then
+      // wait for all candidates
+      if ((warp == 0 || direct) && lane < (int)C) {
         const uint32_t dst = par ? cc1 : cc0, bar = par ? bar1 : bar0;
         st_async_v4(dst, (uint32_t)key, btk, ux, uy, bar);
         st_async_b32(dst + 16, uz, bar);
@@ -144,7 +164,7 @@ __global__ void __launch_bounds__(T, 1) fps_cluster_kernel(const float *__restri
       mbar_wait_cluster(&sh.full[par], (phases >> par) & 1u);
       phases ^= 1u << par;
       ckey_u = (uint32_t)kKeyNone, ctk = 0xFFFFFFFFu;
-      if (lane < (int)C) {
+      if (lane < (int)ncand) {
         const uint4 v = *reinterpret_cast<const uint4 *>(sh.cc[par][lane]);
         ckey_u = v.x, ctk = v.y, ux = v.z, uy = v.w;
         uz = sh.cc[par][lane][4];
@@ -260,7 +280,9 @@ static int launch_fps(const float *xyz, float *temp, int *idx, int b, int n, int
       return kFpsRetrySmallerCluster;
     }
   }
-  e = cudaLaunchKernelEx(&cfg, kern, xyz, temp, idx, n, m, variant, L);
+  // direct mode: every warp's winner goes straight to all CTAs when they fit one lane each (g_tuning.fps_direct: 1 = never)
+  const int direct = (C > 1 && C * (T / 32) <= 32 && g_tuning.fps_direct != 1) ? 1 : 0;
+  e = cudaLaunchKernelEx(&cfg, kern, xyz, temp, idx, n, m, variant, L, direct);
   count_launch();
   return (int)e;
 }

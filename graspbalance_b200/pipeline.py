@@ -196,7 +196,8 @@ class OpPipeline:
         elif grasps is not None:
             out["collision_counts"] = collide()
         if bw:
-            out["grad_checksum"] = sum(t.grad[:, :4, :64].sum() for t in self.sa_in_feats[1:] + self.irm_feats + self.fp_feats)
+            out["grad_checksum"] = torch.cat([t.grad[:, :4, :64].reshape(-1) for t in
+                                              self.sa_in_feats[1:] + self.irm_feats + self.fp_feats]).sum()
             for t in self.sa_in_feats[1:] + self.irm_feats + self.fp_feats:
                 t.grad = None
         return out
