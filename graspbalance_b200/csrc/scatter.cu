@@ -357,9 +357,12 @@ __host__ __device__ inline size_t seg_dense_blob(int n, int div, int mul) {
 }
 
 // grid (tiles, b); dynamic smem (n + 32) ints
+// deg (optional) [b, n]: every deg_stride-th tile adds its per-target counts -- a sampled degree of each target, which
+// seg_perm_kernel turns into the thread -> target assignment of the accumulate kernel.
 template <int DIV, int MUL>
 __global__ void __launch_bounds__(kSegSortThreads) seg_sort_dense_kernel(const int *__restrict__ idx, int per, int n,
-                                                                         unsigned char *__restrict__ blobs) {
+                                                                         unsigned char *__restrict__ blobs, int *__restrict__ deg,
+                                                                         int deg_stride) {
   constexpr int T = seg_dense_tile(DIV, MUL), kStride = seg_dense_stride(DIV, MUL);
   extern __shared__ int s_bins[];
   int *wsum = s_bins + n;
@@ -384,6 +387,13 @@ __global__ void __launch_bounds__(kSegSortThreads) seg_sort_dense_kernel(const i
     key[r] = k;
   }
   __syncthreads();
+  if (deg && blockIdx.x % deg_stride == 0) {
+    int *dg = deg + (size_t)blockIdx.y * n;
+    for (int i = tid; i < n; i += kSegSortThreads) {
+      const int cnt = s_bins[i];
+      if (cnt) atomicAdd(dg + i, cnt);
+    }
+  }
   const int chunk = (n + kSegSortThreads - 1) / kSegSortThreads;
   const int c0 = min(n, tid * chunk), c1 = min(n, c0 + chunk);
   int local = 0;
@@ -426,6 +436,59 @@ __global__ void __launch_bounds__(kSegSortThreads) seg_sort_dense_kernel(const i
   for (int e = total + tid; e < kStride; e += kSegSortThreads) tp[e] = 0;
 }
 
+// Thread -> target assignment of the accumulate kernel.  A warp walks the slices of its 32 targets in lock step, so a
+// tile costs it as many iterations as its LONGEST slice; the number of entries per target is far from uniform (ball-query
+// neighbourhoods padded with their first hit, dense and sparse regions: degrees of 0..400 around a mean of 64), so with
+// targets in index order most lanes idle (measured: 12 of 32 lanes active per instruction).  Sorting the targets by
+// degree puts targets of similar degree in the same warp.  grid b, 1024 threads: counting sort of the n <= 4096 targets
+// by (sampled) degree, descending; perm [b, n] u16 = target of slot s.  Ownership only: sums per target are unchanged.
+constexpr int kSegDegBins = 1024;
+__global__ void __launch_bounds__(kSegThreads) seg_perm_kernel(const int *__restrict__ deg, int n, unsigned short *__restrict__ perm) {
+  __shared__ int s_hist[kSegDegBins];
+  __shared__ int s_w[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  deg += (size_t)blockIdx.x * n;
+  perm += (size_t)blockIdx.x * n;
+  s_hist[tid] = 0;
+  __syncthreads();
+  int bin[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int t = r * kSegThreads + tid;
+    bin[r] = -1;
+    if (t < n) {
+      bin[r] = kSegDegBins - 1 - min(deg[t], kSegDegBins - 1);  // bin 0 = highest degree
+      atomicAdd(&s_hist[bin[r]], 1);
+    }
+  }
+  __syncthreads();
+  const int mine = s_hist[tid];
+  int incl = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int o = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += o;
+  }
+  if (lane == 31) s_w[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    const int w = s_w[lane];
+    int wi = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int o = __shfl_up_sync(0xffffffffu, wi, d);
+      if (lane >= d) wi += o;
+    }
+    s_w[lane] = wi - w;
+  }
+  __syncthreads();
+  s_hist[tid] = s_w[warp] + incl - mine;  // exclusive prefix = first slot of the bin, then its cursor
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+    if (bin[r] >= 0) perm[atomicAdd(&s_hist[bin[r]], 1)] = (unsigned short)(r * kSegThreads + tid);
+}
+
 // grid b * chunks, kSegThreads threads.  Thread -> target slot ts = tid % NT and channel group cg = tid / NT
 // (NT = 2^nt_log2 >= n when n <= 1024, else 1024 with TPT targets ts, ts + 1024, ...); CC = CT * (1024 / NT) channels per
 // CTA.  dynamic smem per stage: gt[CC][TP] f32 | wt[T] f32 (weighted) | blob.
@@ -433,7 +496,8 @@ template <int CT, int TPT, int DIV, bool WEIGHTED, int MUL>
 __global__ void __launch_bounds__(kSegThreads, 1) seg_dense_kernel(const float *__restrict__ src, const unsigned char *__restrict__ blobs,
                                                                    const float *__restrict__ weight, float *__restrict__ grad, int c,
                                                                    int n, int per_src, int tiles, int chunks, int nt_log2, int stages,
-                                                                   int stage_bytes, int bulk_ok, int overwrite, size_t src_stride) {
+                                                                   int stage_bytes, int bulk_ok, int overwrite, size_t src_stride,
+                                                                   const unsigned short *__restrict__ perm) {
   constexpr int T = seg_dense_tile(DIV, MUL), TP = T / DIV;
   extern __shared__ __align__(128) unsigned char s_raw[];
   __shared__ uint64_t full[kSegMaxStages];
@@ -474,10 +538,14 @@ __global__ void __launch_bounds__(kSegThreads, 1) seg_dense_kernel(const float *
   }
 
   float a[TPT][CT];
+  int tgt[TPT];  // the targets this thread owns: slot ts + j * NT of the (degree-sorted) assignment; -1 = none
 #pragma unroll
-  for (int j = 0; j < TPT; ++j)
+  for (int j = 0; j < TPT; ++j) {
+    const int slot = ts + j * NT;
+    tgt[j] = slot < n ? (perm ? (int)perm[(size_t)scene * n + slot] : slot) : -1;
 #pragma unroll
     for (int cc = 0; cc < CT; ++cc) a[j][cc] = 0.f;
+  }
 
   int sidx = 0, issue_sidx = stages - 1;
   uint32_t parity = 0;
@@ -502,8 +570,8 @@ __global__ void __launch_bounds__(kSegThreads, 1) seg_dense_kernel(const float *
     const unsigned short *start = tp + seg_dense_stride(DIV, MUL);
 #pragma unroll
     for (int j = 0; j < TPT; ++j) {
-      const int k = ts + j * NT;
-      if (k < n) {
+      const int k = tgt[j];
+      if (k >= 0) {
         const int e1 = start[k + 1];
         for (int i = start[k]; i < e1; ++i) {
           const unsigned p = tp[i];
@@ -523,8 +591,8 @@ __global__ void __launch_bounds__(kSegThreads, 1) seg_dense_kernel(const float *
   }
 #pragma unroll
   for (int j = 0; j < TPT; ++j) {
-    const int k = ts + j * NT;
-    if (k < n) {
+    const int k = tgt[j];
+    if (k >= 0) {
 #pragma unroll
       for (int cc = 0; cc < CT; ++cc) {
         const int ch = cg * CT + cc;
@@ -577,7 +645,8 @@ static int launch_seg_accum(const float *src, size_t src_stride, const unsigned 
 
 template <int CT, int TPT, int DIV, bool WEIGHTED, int MUL>
 static int launch_seg_dense(const float *src, size_t src_stride, const unsigned char *blobs, const float *weight, float *grad, int b, int c,
-                            int n, int per_src, int tiles, int nt_log2, int bulk_ok, int overwrite, cudaStream_t s) {
+                            int n, int per_src, int tiles, int nt_log2, int bulk_ok, int overwrite, const unsigned short *perm,
+                            cudaStream_t s) {
   constexpr int T = seg_dense_tile(DIV, MUL), TP = T / DIV;
   const int G = kSegThreads >> nt_log2, CC = CT * G;
   const size_t stage_bytes = ((size_t)CC * TP * 4 + (WEIGHTED ? (size_t)T * 4 : 0) + seg_dense_blob(n, DIV, MUL) + 127) & ~(size_t)127;
@@ -591,7 +660,7 @@ static int launch_seg_dense(const float *src, size_t src_stride, const unsigned 
   if (e != cudaSuccess) return (int)e;
   const int chunks = (c + CC - 1) / CC;
   kern<<<(unsigned)(b * chunks), kSegThreads, smem, s>>>(src, blobs, weight, grad, c, n, per_src, tiles, chunks, nt_log2, stages,
-                                                         (int)stage_bytes, bulk_ok, overwrite, src_stride);
+                                                         (int)stage_bytes, bulk_ok, overwrite, src_stride, perm);
   count_launch();
   return finish_launch();
 }
@@ -626,22 +695,43 @@ static int seg_scatter_dense(const float *src, size_t src_stride, const int *key
   const int T = seg_dense_tile(div, mul);
   const int tiles = (int)((entries + T - 1) / T);
   const size_t blob = seg_dense_blob(n, div, mul);
+  // degree-sorted thread -> target assignment (see seg_perm_kernel) when a scene has enough tiles for the imbalance to
+  // matter; degrees are sampled from every deg_stride-th tile (at least 8 tiles per scene)
+  const bool balance = tiles >= 8 && !(g_tuning.scatter_mode & 4);
+  const int deg_stride = tiles >= 32 ? tiles / 8 : (tiles >= 16 ? 2 : 1);
+  const size_t blobs_bytes = ((size_t)b * tiles * blob + 255) & ~(size_t)255;
+  const size_t deg_bytes = balance ? (((size_t)b * n * sizeof(int) + 255) & ~(size_t)255) : 0;
+  const size_t perm_bytes = balance ? (size_t)b * n * sizeof(unsigned short) : 0;
   unsigned char *blobs = nullptr;
-  cudaError_t e = scratch_alloc((void **)&blobs, (size_t)b * tiles * blob, s);
+  cudaError_t e = scratch_alloc((void **)&blobs, blobs_bytes + deg_bytes + perm_bytes, s);
   if (e != cudaSuccess) return (int)e;
+  int *deg = balance ? reinterpret_cast<int *>(blobs + blobs_bytes) : nullptr;
+  unsigned short *perm = balance ? reinterpret_cast<unsigned short *>(blobs + blobs_bytes + deg_bytes) : nullptr;
+  if (balance) {
+    e = cudaMemsetAsync(deg, 0, (size_t)b * n * sizeof(int), s);
+    if (e != cudaSuccess) {
+      cudaFreeAsync(blobs, s);
+      return (int)e;
+    }
+  }
   const size_t sort_smem = ((size_t)n + 32) * sizeof(int);
   const dim3 sgrid((unsigned)tiles, b);
-  if (div == 3) seg_sort_dense_kernel<3, 1><<<sgrid, kSegSortThreads, sort_smem, s>>>(key, (int)entries, n, blobs);
-  else if (mul == 1) seg_sort_dense_kernel<1, 1><<<sgrid, kSegSortThreads, sort_smem, s>>>(key, (int)entries, n, blobs);
-  else if (mul == 2) seg_sort_dense_kernel<1, 2><<<sgrid, kSegSortThreads, sort_smem, s>>>(key, (int)entries, n, blobs);
-  else seg_sort_dense_kernel<1, 4><<<sgrid, kSegSortThreads, sort_smem, s>>>(key, (int)entries, n, blobs);
+  if (div == 3) seg_sort_dense_kernel<3, 1><<<sgrid, kSegSortThreads, sort_smem, s>>>(key, (int)entries, n, blobs, deg, deg_stride);
+  else if (mul == 1) seg_sort_dense_kernel<1, 1><<<sgrid, kSegSortThreads, sort_smem, s>>>(key, (int)entries, n, blobs, deg, deg_stride);
+  else if (mul == 2) seg_sort_dense_kernel<1, 2><<<sgrid, kSegSortThreads, sort_smem, s>>>(key, (int)entries, n, blobs, deg, deg_stride);
+  else seg_sort_dense_kernel<1, 4><<<sgrid, kSegSortThreads, sort_smem, s>>>(key, (int)entries, n, blobs, deg, deg_stride);
   count_launch();
   int rc = finish_launch();
+  if (!rc && balance) {
+    seg_perm_kernel<<<b, kSegThreads, 0, s>>>(deg, n, perm);
+    count_launch();
+    rc = finish_launch();
+  }
   if (!rc) {
     // bulk copies: 16-byte aligned row pieces (and weight pieces: per_src * div * 4 bytes per scene)
     const int bulk_ok = (per_src % 4 == 0) && (((uintptr_t)src & 15u) == 0) && (!weight || ((uintptr_t)weight & 15u) == 0) &&
                         2 * stage_of(CT) <= kSegSmemBudget;
-#define GB_DENSE_ARGS src, src_stride, blobs, weight, grad, b, c, n, per_src, tiles, nt_log2, bulk_ok, overwrite, s
+#define GB_DENSE_ARGS src, src_stride, blobs, weight, grad, b, c, n, per_src, tiles, nt_log2, bulk_ok, overwrite, perm, s
 #define GB_DENSE_CASE(CTV, TPTV)                                                                      \
   do {                                                                                                \
     if (div == 3) rc = launch_seg_dense<CTV, TPTV, 3, true, 1>(GB_DENSE_ARGS);                        \

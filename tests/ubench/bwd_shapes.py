@@ -1,0 +1,107 @@
+#!/usr/bin/env python
+"""Backward (segmented scatter-add) on the shapes of the backbone: correctness against an fp64 scatter_add and timing of
+the degree-sorted thread -> target assignment (default) against targets in index order (scatter_mode bit 2).
+
+    python tests/ubench/bwd_shapes.py [--B 32] [--out gpurun_out/bwd_shapes.json]
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from graspbalance_b200 import _ext as A, _lib, scenes  # noqa: E402
+
+HBM = 6542.4
+dev = torch.device("cuda:0")
+_flush = None
+
+
+def flush_l2():
+    global _flush
+    if _flush is None:
+        _flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    _flush.fill_(1)
+
+
+def timeit(fn, iters=9, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        flush_l2()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        e1.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e3)
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--B", type=int, default=32)
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "bwd_shapes.json"))
+    args = ap.parse_args()
+    B = args.B
+    g = torch.Generator(device="cpu").manual_seed(0)
+    xyz = torch.from_numpy(scenes.scene_batch(range(B), 20000, "tabletop")).to(dev)
+    fidx = A.furthest_point_sampling(xyz, 2048).long()
+    lv0 = torch.gather(xyz, 1, fidx[:, :, None].expand(-1, -1, 3)).contiguous()
+    rows, all_ok = [], True
+
+    def run(label, fn, want, nbytes):
+        nonlocal all_ok
+        row = {"op": label}
+        for name, mode in (("index_order", 4), ("degree_sorted", 0)):
+            _lib.set_tuning("scatter_mode", mode)
+            got = fn()[:2]
+            err = (got.double() - want).abs().max().item()
+            ok = err <= 1e-5 * max(want.abs().max().item(), 1.0)
+            all_ok &= ok
+            t = timeit(fn)
+            row[name + "_us"] = round(t, 1)
+            row[name + "_hbm_frac"] = round(nbytes / (t * 1e-6) / 1e9 / HBM, 3)
+            row[name + "_ok"] = ok
+        _lib.set_tuning("scatter_mode", 0)
+        rows.append(row)
+        print(json.dumps(row), flush=True)
+
+    shapes = [("irm0", 2048, 2048, 64, 128, 0.08), ("irm1", 1024, 1024, 32, 256, 0.2), ("irm2", 512, 512, 16, 256, 0.4),
+              ("irm3", 256, 256, 16, 256, 0.6), ("sa2", 2048, 1024, 32, 128, 0.1), ("sa3", 1024, 512, 16, 256, 0.2),
+              ("sa4", 512, 256, 16, 256, 0.3)]
+    for (label, n, m, ns, C, r) in shapes:
+        tgt, qry = lv0[:, :n].contiguous(), lv0[:, :m].contiguous()
+        idx = A.ball_query(qry, tgt, r, ns)
+        gout = torch.randn((B, C, m, ns), generator=g).to(dev)
+        want = torch.zeros((2, C, n), dtype=torch.float64, device=dev)
+        want.scatter_add_(2, idx[:2].long().reshape(2, 1, m * ns).expand(-1, C, -1), gout[:2].double().reshape(2, C, m * ns))
+        run(f"group bwd {label} n={n} m={m} ns={ns} C={C} B={B}", lambda: A.group_points_grad(gout, idx, n), want,
+            B * (4 * C * n + 4 * m * ns + 4 * C * m * ns))
+    for (nn, mm) in ((20000, 1024), (1024, 512), (512, 256)):
+        unknown = xyz[:, :nn].contiguous() if nn == 20000 else lv0[:, :nn].contiguous()
+        known = lv0[:, :mm].contiguous()
+        d2, i3 = A.three_nn(unknown, known)
+        recip = 1.0 / (torch.sqrt(d2) + 1e-8)
+        w = (recip / recip.sum(dim=2, keepdim=True)).contiguous()
+        go = torch.randn((B, 256, nn), generator=g).to(dev)
+        want = torch.zeros((2, 256, mm), dtype=torch.float64, device=dev)
+        src = (go[:2].double()[:, :, :, None] * w[:2].double()[:, None, :, :]).reshape(2, 256, nn * 3)
+        want.scatter_add_(2, i3[:2].long().reshape(2, 1, nn * 3).expand(-1, 256, -1), src)
+        run(f"interp bwd {nn}<-{mm} C=256 B={B}", lambda: A.three_interpolate_grad(go, i3, w, mm), want,
+            B * (4 * 256 * mm + 24 * nn + 4 * 256 * nn))
+    os.makedirs(os.path.dirname(args.out), exist_ok=True)
+    with open(args.out, "w") as f:
+        json.dump({"B": B, "all_ok": bool(all_ok), "rows": rows}, f, indent=1)
+    print("ALL_OK" if all_ok else "MISMATCH", flush=True)
+    sys.exit(0 if all_ok else 1)
+
+
+if __name__ == "__main__":
+    main()
