@@ -320,14 +320,13 @@ def main():
     # allocator priming (untimed, on top of the W warm-up steps): the caching allocator keeps growing its pools for a few
     # steps because blocks handed to side streams are recycled late; a cudaMalloc inside the timed region costs
     # milliseconds.  Step until one whole step needs no new device allocation (at most 8 extra steps).
-    prime_steps = 0
-    while prime_steps < 8:
+    prime_steps, quiet = 0, 0
+    while prime_steps < 10 and quiet < 3:  # three steps in a row without a new device allocation
         before = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
         step(True, resident_inputs)
         torch.cuda.synchronize()
         prime_steps += 1
-        if torch.cuda.memory_stats(dev).get("num_device_alloc", 0) == before:
-            break
+        quiet = quiet + 1 if torch.cuda.memory_stats(dev).get("num_device_alloc", 0) == before else 0
     dev_allocs0 = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
 
     # ---- device-resident throughput ("value") ----

@@ -24,6 +24,7 @@ static int *tuning_slot(const char *key) {
   if (!strcmp(key, "interp_mode")) return &gb::g_tuning.interp_mode;
   if (!strcmp(key, "query_qpw")) return &gb::g_tuning.query_qpw;
   if (!strcmp(key, "scatter_cc")) return &gb::g_tuning.scatter_cc;
+  if (!strcmp(key, "scatter_nt")) return &gb::g_tuning.scatter_nt;
   if (!strcmp(key, "scatter_mode")) return &gb::g_tuning.scatter_mode;
   if (!strcmp(key, "query_mode")) return &gb::g_tuning.query_mode;
   if (!strcmp(key, "grid_cell_pct")) return &gb::g_tuning.grid_cell_pct;

@@ -43,6 +43,7 @@ struct Tuning {
   int interp_mode = 0;
   int query_qpw = 0;
   int scatter_cc = 0;
+  int scatter_nt = 0;  // dense backward: log2 of the target slots per CTA (8..10), 0 = smallest that holds n
   int scatter_mode = 0;  // bit 0: never use the dense (thread-owned targets) backward; bit 2: targets in index order (no degree sort)
   int query_mode = 0;  // 1: never use the cell grid, 2: always use it (when the shape allows)
   int grid_cell_pct = 0;  // cell edge as a percentage of the query reach (0 = default 50)

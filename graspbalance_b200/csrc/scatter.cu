@@ -541,7 +541,9 @@ __global__ void __launch_bounds__(kSegThreads, 1) seg_dense_kernel(const float *
   int tgt[TPT];  // the targets this thread owns: slot ts + j * NT of the (degree-sorted) assignment; -1 = none
 #pragma unroll
   for (int j = 0; j < TPT; ++j) {
-    const int slot = ts + j * NT;
+    // degree-sorted assignment: serpentine over the TPT rows of NT slots, so a thread (and hence a warp) pairs a
+    // high-degree target with a low-degree one and the warps of a CTA carry similar totals
+    const int slot = perm && (j & 1) ? (j + 1) * NT - 1 - ts : ts + j * NT;
     tgt[j] = slot < n ? (perm ? (int)perm[(size_t)scene * n + slot] : slot) : -1;
 #pragma unroll
     for (int cc = 0; cc < CT; ++cc) a[j][cc] = 0.f;
@@ -673,6 +675,8 @@ static int seg_scatter_dense(const float *src, size_t src_stride, const int *key
   const int per_src = (int)(entries / div);
   int nt_log2 = 8;  // >= 256 target slots: at most 4 channel groups per CTA, so one channel per thread always fits
   while ((1 << nt_log2) < n && nt_log2 < 10) ++nt_log2;
+  if (g_tuning.scatter_nt >= 8 && g_tuning.scatter_nt <= 10 && (n + (1 << g_tuning.scatter_nt) - 1) >> g_tuning.scatter_nt <= 4)
+    nt_log2 = g_tuning.scatter_nt;
   const int NT = 1 << nt_log2, G = kSegThreads / NT;
   const int tpt = (n + NT - 1) / NT;  // 1 when n <= 1024, else 2..4
   // tile multiplier of a channel count: ~64 KB of source rows per stage (group); the interpolate tile is 2040 points

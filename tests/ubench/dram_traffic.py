@@ -13,17 +13,18 @@ import json
 import re
 import sys
 
-MAIN = [  # (regex on the kernel name, family)
+_I, _B0, _B1 = r"(\(int\))?", r"(\(bool\))?(0|false)", r"(\(bool\))?(1|true)"
+MAIN = [  # (regex on the kernel name, family); seg_dense_kernel<CT, TPT, DIV, WEIGHTED, MUL>, seg_accum_kernel<CC, DIV, WEIGHTED>
     (r"group_fwd_kernel|group_fwd_generic", "gb_group_fwd"),
-    (r"seg_dense_kernel<[^>]*, ?(\(int\))?1, ?(\(bool\))?(0|false)>|seg_accum_kernel<[^>]*, ?(\(int\))?1, ?(\(bool\))?(0|false)>|group_bwd_kernel|group_bwd_generic", "gb_group_bwd"),
-    (r"seg_dense_kernel<[^>]*, ?(\(int\))?3, ?(\(bool\))?(1|true)>|seg_accum_kernel<[^>]*, ?(\(int\))?3, ?(\(bool\))?(1|true)>|interp_bwd_kernel", "gb_three_interp_bwd"),
+    (rf"seg_dense_kernel<[^>]*, ?{_I}1, ?{_B0}, ?{_I}\d+>|seg_accum_kernel<[^>]*, ?{_I}1, ?{_B0}>|group_bwd_kernel|group_bwd_generic", "gb_group_bwd"),
+    (rf"seg_dense_kernel<[^>]*, ?{_I}3, ?{_B1}, ?{_I}\d+>|seg_accum_kernel<[^>]*, ?{_I}3, ?{_B1}>|interp_bwd_kernel", "gb_three_interp_bwd"),
     (r"interp_fwd", "gb_three_interp_fwd"),
-    (r"grid_query_kernel<(\(bool\))?(1|true)>|query_kernel<(\(bool\))?(1|true)", "gb_cylinder_query"),
-    (r"grid_query_kernel<(\(bool\))?(0|false)>|query_kernel<(\(bool\))?(0|false)", "gb_ball_query"),
+    (rf"grid_query_kernel<{_B1}[,>]|query_kernel<{_B1}[,>]", "gb_cylinder_query"),
+    (rf"grid_query_kernel<{_B0}[,>]|query_kernel<{_B0}[,>]", "gb_ball_query"),
     (r"fps_", "gb_fps"), (r"three_nn", "gb_three_nn"), (r"collision", "gb_collision_counts"), (r"group_xyz", "gb_group_xyz"),
     (r"gather_", "gb_gather"), (r"knn", "gb_knn"),
 ]
-HELPER = r"seg_sort|grid_build"
+HELPER = r"seg_sort|seg_perm|grid_build"
 
 
 def main():
