@@ -549,7 +549,10 @@ static int launch_query(const float *new_xyz, const float *xyz, const float *rot
   GridHeader *hdr = nullptr;
   void *scratch = nullptr;
   const int words = (n + 31) / 32;
-  if (g_tuning.query_mode != 1 && (n >= 4096 || g_tuning.query_mode == 2) && (size_t)words * kGridQueryWarps * 4 <= 96u * 1024u) {
+  // the grid pays for its build (one CTA per scene, ~30 us) from ~4M candidate tests per scene on (B200, 32 scenes:
+  // n = m = 2048 113 us vs 165 us full scan; n = 2048, m = 1024 79 vs 62; n = m = 1024 85 vs 34)
+  const bool grid_worth = n >= 4096 || (n >= 2048 && (long long)m * n >= (1LL << 22));
+  if (g_tuning.query_mode != 1 && (grid_worth || g_tuning.query_mode == 2) && (size_t)words * kGridQueryWarps * 4 <= 96u * 1024u) {
     const size_t sorted_bytes = (size_t)b * n * sizeof(float4);
     const size_t cells_bytes = (((size_t)b * (kGridMaxCells + 1) * sizeof(int)) + 15) & ~(size_t)15;
     cudaError_t e = scratch_alloc(&scratch, sorted_bytes + cells_bytes + (size_t)b * sizeof(GridHeader), s);
