@@ -59,9 +59,8 @@ def main():
     def run(label, fn, want, nbytes):
         nonlocal all_ok
         row = {"op": label}
-        for name, mode, cc in (("index_order", 4, 0), ("degree_sorted", 0, 0)):
+        for name, mode in (("index_order", 4), ("degree_sorted", 0)):
             _lib.set_tuning("scatter_mode", mode)
-            _lib.set_tuning("scatter_cc", cc)
             got = fn()[:2]
             err = (got.double() - want).abs().max().item()
             ok = err <= 1e-5 * max(want.abs().max().item(), 1.0)
@@ -72,7 +71,6 @@ def main():
             if not ok:
                 row[name + "_ok"] = ok
         _lib.set_tuning("scatter_mode", 0)
-        _lib.set_tuning("scatter_cc", 0)
         rows.append(row)
         print(json.dumps(row), flush=True)
 
