@@ -84,6 +84,21 @@ def three_nn(unknowns, knows):
     return [dist2, idx]
 
 
+def three_nn_weights(unknowns, knows):
+    """three_nn + inverse-distance weights in one launch: (dist [B,n,3] = sqrt of the squared distances, idx [B,n,3] i32,
+    weight [B,n,3]) with weight = (1/(dist+1e-8)) / sum_k(1/(dist_k+1e-8)) (pointnet2_modules.py:413-416)."""
+    _contig(unknowns, "unknowns"); _contig(knows, "knows"); _is_float(unknowns, "unknowns"); _is_float(knows, "knows")
+    if unknowns.is_cuda:
+        _cuda(knows, "knows")
+    _need_cuda(unknowns)
+    B, n, m = unknowns.shape[0], unknowns.shape[1], knows.shape[1]
+    dist = torch.empty((B, n, 3), dtype=torch.float32, device=unknowns.device)
+    idx = torch.empty((B, n, 3), dtype=torch.int32, device=unknowns.device)
+    weight = torch.empty((B, n, 3), dtype=torch.float32, device=unknowns.device)
+    _lib.call("gb_three_nn_weights", unknowns, unknowns.data_ptr(), knows.data_ptr(), dist.data_ptr(), idx.data_ptr(), weight.data_ptr(), B, n, m)
+    return dist, idx, weight
+
+
 def three_interpolate(points, idx, weight):
     """interpolate.cpp:47-75.  points [B,C,m], idx/weight [B,n,3] -> [B,C,n]."""
     _contig(points, "points"); _contig(idx, "idx"); _contig(weight, "weight")

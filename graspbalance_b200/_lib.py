@@ -33,6 +33,7 @@ SIGNATURES = {
     "gb_group_bwd_strided": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _ll, _i, _vp],
     "gb_group_xyz": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _ll, _vp],
     "gb_three_nn": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp],
+    "gb_three_nn_weights": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp],
     "gb_three_interp_fwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "gb_three_interp_bwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "gb_three_interp_bwd_set": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
@@ -102,6 +103,7 @@ ALGO_BYTES = {
     "gb_group_fwd": lambda a: a[3] * (4 * a[4] * a[5] + 4 * a[6] * a[7] + 4 * a[4] * a[6] * a[7]),
     "gb_group_bwd": lambda a: a[3] * (4 * a[4] * a[5] + 4 * a[6] * a[7] + 4 * a[4] * a[6] * a[7]),
     "gb_three_nn": lambda a: a[4] * (12 * a[5] + 12 * a[6] + 24 * a[5]),                  # b*(12n + 12m + 24n)
+    "gb_three_nn_weights": lambda a: a[5] * (12 * a[6] + 12 * a[7] + 36 * a[6]),         # b*(12n + 12m + 36n)
     "gb_three_interp_fwd": lambda a: a[4] * (4 * a[5] * a[6] + 24 * a[7] + 4 * a[5] * a[7]),   # b*(4cm + 24n + 4cn)
     "gb_three_interp_bwd": lambda a: a[4] * (4 * a[5] * a[7] + 24 * a[6] + 4 * a[5] * a[6]),   # args (b,c,n,m)
     "gb_group_bwd_set": lambda a: a[3] * (4 * a[4] * a[5] + 4 * a[6] * a[7] + 4 * a[4] * a[6] * a[7]),

@@ -15,8 +15,16 @@ namespace gb {
 constexpr int kNNThreads = 256;
 constexpr int kNNTile = 2048;  // known points per shared-memory tile (32 KB as float4)
 
+// WEIGHTS: additionally the inverse-distance interpolation weights every caller derives from the result
+// (pointnet2_modules.py:413-416, upsampling.py:69-72, graspbalance.py:37-41):
+//   dist = sqrt(dist2); r = 1 / (dist + 1e-8); weight = r / (r0 + r1 + r2)
+// with the roundings of the torch ops they replace (IEEE sqrt, add, reciprocal, divide; the sum in the order torch's
+// reduce kernel adds three contiguous elements, (r0 + r2) + r1 -- checked bit for bit on a B200), and dist2 then
+// holds dist (the square root), which is what the Python-level three_nn returns.
+template <bool WEIGHTS>
 __global__ void __launch_bounds__(kNNThreads) three_nn_kernel(const float *__restrict__ unknown, const float *__restrict__ known,
-                                                              float *__restrict__ dist2, int *__restrict__ idx, int n, int m) {
+                                                              float *__restrict__ dist2, int *__restrict__ idx,
+                                                              float *__restrict__ weight, int n, int m) {
   __shared__ float4 tile[kNNTile];
   const int scene = blockIdx.y;
   const int j = blockIdx.x * kNNThreads + threadIdx.x;
@@ -52,6 +60,12 @@ __global__ void __launch_bounds__(kNNThreads) three_nn_kernel(const float *__res
     }
   }
   if (ok) {
+    if (WEIGHTS) {
+      b1 = __fsqrt_rn(b1), b2 = __fsqrt_rn(b2), b3 = __fsqrt_rn(b3);
+      const float r1 = __frcp_rn(__fadd_rn(b1, 1e-8f)), r2 = __frcp_rn(__fadd_rn(b2, 1e-8f)), r3 = __frcp_rn(__fadd_rn(b3, 1e-8f));
+      const float norm = __fadd_rn(__fadd_rn(r1, r3), r2);  // torch.sum over a 3-element inner dimension: (r0 + r2) + r1
+      weight[uj * 3] = __fdiv_rn(r1, norm), weight[uj * 3 + 1] = __fdiv_rn(r2, norm), weight[uj * 3 + 2] = __fdiv_rn(r3, norm);
+    }
     dist2[uj * 3] = b1, dist2[uj * 3 + 1] = b2, dist2[uj * 3 + 2] = b3;
     idx[uj * 3] = i1, idx[uj * 3 + 1] = i2, idx[uj * 3 + 2] = i3;
   }
@@ -66,7 +80,21 @@ extern "C" int gb_three_nn(const float *unknown, const float *known, float *dist
   if (!unknown || (m > 0 && !known) || !dist2 || !idx) return (int)cudaErrorInvalidValue;
   if (b > 65535) return (int)cudaErrorInvalidValue;
   dim3 grid((n + gb::kNNThreads - 1) / gb::kNNThreads, b);
-  gb::three_nn_kernel<<<grid, gb::kNNThreads, 0, (cudaStream_t)stream>>>(unknown, known, dist2, idx, n, m);
+  gb::three_nn_kernel<false><<<grid, gb::kNNThreads, 0, (cudaStream_t)stream>>>(unknown, known, dist2, idx, nullptr, n, m);
+  gb::count_launch();
+  return gb::finish_launch();
+}
+
+/* three_nn followed by the inverse-distance weights of its callers, one launch:
+ * dist [b,n,3] = sqrt of the squared distances, idx [b,n,3], weight [b,n,3] = (1/(dist+1e-8)) / sum_k (1/(dist_k+1e-8)). */
+extern "C" int gb_three_nn_weights(const float *unknown, const float *known, float *dist, int *idx, float *weight, int b, int n, int m,
+                                   gb_stream_t stream) {
+  if (b < 0 || n < 0 || m < 0) return (int)cudaErrorInvalidValue;
+  if (b == 0 || n == 0) return 0;
+  if (!unknown || (m > 0 && !known) || !dist || !idx || !weight) return (int)cudaErrorInvalidValue;
+  if (b > 65535) return (int)cudaErrorInvalidValue;
+  dim3 grid((n + gb::kNNThreads - 1) / gb::kNNThreads, b);
+  gb::three_nn_kernel<true><<<grid, gb::kNNThreads, 0, (cudaStream_t)stream>>>(unknown, known, dist, idx, weight, n, m);
   gb::count_launch();
   return gb::finish_launch();
 }

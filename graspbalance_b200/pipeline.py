@@ -82,9 +82,8 @@ class OpPipeline:
     # ------------------------------------------------------------------------------------------------------------
     @staticmethod
     def _interp(unknown, known, feats, grad):
-        dist, idx = pu.three_nn(unknown, known)
-        dist_recip = 1.0 / (dist + 1e-8)
-        weight = dist_recip / torch.sum(dist_recip, dim=2, keepdim=True)  # pointnet2_modules.py:413-416
+        # three_nn + weights of pointnet2_modules.py:413-416 (sqrt, +1e-8, reciprocal, sum, divide) in one launch
+        _, idx, weight = pu.three_nn_weights(unknown, known)
         out = pu.three_interpolate(feats, idx, weight)
         if grad is not None:
             out.backward(grad)

@@ -65,6 +65,25 @@ class ThreeNN(Function):
 three_nn = ThreeNN.apply
 
 
+class ThreeNNWeights(Function):
+    """three_nn and the inverse-distance weights every caller derives from it (pointnet2_modules.py:413-416,
+    TrainModel/graspbalance.py:37-41) in one launch: returns (dist, idx, weight), weight = (1/(dist+1e-8)) normalised over
+    the three neighbours -- bit-identical to the torch ops it replaces.  Like three_nn, nothing here is differentiable."""
+
+    @staticmethod
+    def forward(ctx, unknown, known):
+        dist, idx, weight = _ext.three_nn_weights(unknown, known)
+        ctx.mark_non_differentiable(dist, idx, weight)
+        return dist, idx, weight
+
+    @staticmethod
+    def backward(ctx, a=None, b=None, c=None):
+        return None, None
+
+
+three_nn_weights = ThreeNNWeights.apply
+
+
 class ThreeInterpolate(Function):
     @staticmethod
     def forward(ctx, features, idx, weight):

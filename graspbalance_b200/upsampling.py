@@ -56,7 +56,14 @@ three_interpolate = ThreeInterpolate.apply
 
 
 def three_interpolation(unknown_xyz, known_xyz, know_feat):
-    """upsampling.py:67-74: inverse-distance weights over the three nearest known points."""
+    """upsampling.py:67-74: inverse-distance weights over the three nearest known points.  The neighbour search and the
+    weight arithmetic (sqrt, +1e-8, reciprocal, sum, divide -- five elementwise passes in the reference) are one launch
+    (gb_three_nn_weights, bit-identical values); three_nn's outputs carry no gradient in the reference either."""
+    from . import pointnet2_utils as pu
+    if (unknown_xyz.is_cuda and unknown_xyz.dtype == torch.float32 and known_xyz.dtype == torch.float32 and unknown_xyz.is_contiguous()
+            and known_xyz.is_contiguous()):
+        _, idx, weight = pu.three_nn_weights(unknown_xyz, known_xyz)
+        return three_interpolate(know_feat, idx, weight)
     dist, idx = three_nn(unknown_xyz, known_xyz)
     dist_recip = 1.0 / (dist + 1e-8)
     weight = dist_recip / torch.sum(dist_recip, dim=2, keepdim=True)

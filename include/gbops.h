@@ -113,6 +113,12 @@ GB_API int gb_group_xyz(const float *xyz, const float *new_xyz, const int *idx, 
 GB_API int gb_three_nn(const float *unknown, const float *known, float *dist2, int *idx, int b, int n, int m,
                 gb_stream_t stream);
 
+/* three_nn + the inverse-distance weights every caller derives from it (pointnet2_modules.py:413-416, upsampling.py:69-72,
+ * graspbalance.py:37-41), one launch: dist [b,n,3] = sqrt(dist2), idx [b,n,3], weight [b,n,3] =
+ * (1/(dist+1e-8)) / sum_k (1/(dist_k+1e-8)), each op rounded as the torch op it replaces. */
+GB_API int gb_three_nn_weights(const float *unknown, const float *known, float *dist, int *idx, float *weight, int b, int n, int m,
+                        gb_stream_t stream);
+
 /* A: three_interpolate_kernel_wrapper (interpolate_gpu.cu:108-116); B: three_interpolate_kernel_launcher_fast (:106-124).
  * points [b,c,m], idx/weight [b,n,3] -> out [b,c,n]. */
 GB_API int gb_three_interp_fwd(const float *points, const int *idx, const float *weight, float *out, int b, int c, int m,

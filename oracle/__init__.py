@@ -152,6 +152,19 @@ def three_nn(unknown, known):
     return np.sqrt(d2), idx
 
 
+def three_nn_weights(unknown, known):
+    """three_nn followed by the weight arithmetic of its callers (pointnet2_modules.py:413-416, upsampling.py:69-72,
+    graspbalance.py:37-41), every step rounded to fp32 as the torch op does: dist_recip = 1 / (dist + 1e-8);
+    weight = dist_recip / sum(dist_recip, dim=2)."""
+    dist, idx = three_nn(unknown, known)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        recip = (np.float32(1.0) / (dist + np.float32(1e-8))).astype(np.float32)
+        # torch.sum over the 3-element inner dimension adds (r0 + r2) + r1 (two interleaved accumulators; torch 2.11, CUDA)
+        norm = ((recip[..., 0] + recip[..., 2]).astype(np.float32) + recip[..., 1]).astype(np.float32)
+        weight = (recip / norm[..., None]).astype(np.float32)
+    return dist, idx, weight
+
+
 def three_interpolate(features, idx, weight):
     features, idx, weight = _f32(features), _i32(idx), _f32(weight)
     B, C, m = features.shape

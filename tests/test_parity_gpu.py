@@ -354,6 +354,31 @@ def test_three_nn_vs_oracle(dev, B, n, m):
         np.testing.assert_array_equal(dist.cpu().numpy(), np.sqrt(want_d2))
 
 
+@pytest.mark.parametrize("B,n,m", [(2, 20000, 1024), (1, 513, 2), (2, 1000, 3), (1, 64, 1), (2, 4000, 2500), (1, 300, 300)])
+def test_three_nn_weights_matches_the_torch_ops_it_replaces(dev, B, n, m):
+    """gb_three_nn_weights == three_nn followed by pointnet2_modules.py:413-416 (sqrt, +1e-8, reciprocal, sum, divide):
+    bit for bit against the torch ops on the GPU and against the oracle's fp32 numpy restatement."""
+    unknown = scenes.scene_batch(range(B), n, "tabletop" if n >= 1000 else "uniform")
+    known = _queries(unknown, m, 4)
+    if n == 300:
+        known = unknown.copy()  # every unknown coincides with a known point: dist 0, weight 1 on the first neighbour
+    u, k = T(unknown, dev), T(known, dev)
+    dist, idx, weight = pu.three_nn_weights(u, k)
+    dist0, idx0 = pu.three_nn(u, k)
+    recip = 1.0 / (dist0 + 1e-8)
+    weight0 = recip / torch.sum(recip, dim=2, keepdim=True)
+    assert torch.equal(idx, idx0) and torch.equal(dist, dist0)
+    assert torch.equal(weight.view(torch.int32), weight0.view(torch.int32))  # NaN-safe bit comparison (m < 3: inf / inf)
+    wd, wi, ww = oracle.three_nn_weights(unknown, known)
+    np.testing.assert_array_equal(idx.cpu().numpy(), wi)
+    np.testing.assert_array_equal(dist.cpu().numpy(), wd)
+    np.testing.assert_array_equal(weight.cpu().numpy().view(np.int32), ww.view(np.int32))
+    # the B-side helper takes the fused path and gives what the reference's op sequence gives
+    feats = T(np.random.default_rng(0).normal(size=(B, 6, m)).astype(np.float32), dev)
+    if m >= 3:
+        assert torch.equal(gb_up.three_interpolation(u, k, feats), gb_up.three_interpolate(feats, idx0, weight0.contiguous()))
+
+
 @pytest.mark.parametrize("B,C,m,n", [(2, 256, 1024, 20000), (1, 7, 50, 333), (2, 64, 256, 512), (1, 130, 512, 1024),
                                      (1, 8, 4, 5000), (2, 16, 1, 999), (1, 5, 30000, 4096), (2, 4, 3, 2)])
 def test_three_interpolate_vs_oracle(dev, B, C, m, n):
