@@ -70,6 +70,18 @@ def furthest_point_sampling(points, nsamples):
     return out
 
 
+def furthest_point_sampling_xyz(points, nsamples):
+    """furthest_point_sampling + the coordinates of the samples (what gather_points fetches from the transposed cloud,
+    pointnet2_modules.py:151-158) in one launch: ([B,nsamples] i32, [B,nsamples,3] f32)."""
+    _contig(points, "points"); _is_float(points, "points")
+    _need_cuda(points)
+    B, N = points.shape[0], points.shape[1]
+    out = torch.empty((B, int(nsamples)), dtype=torch.int32, device=points.device)
+    new_xyz = torch.empty((B, int(nsamples), 3), dtype=torch.float32, device=points.device)
+    _lib.call("gb_fps_xyz", points, points.data_ptr(), None, out.data_ptr(), new_xyz.data_ptr(), B, N, int(nsamples), 0)
+    return out, new_xyz
+
+
 def three_nn(unknowns, knows):
     """interpolate.cpp:19-45.  unknowns [B,n,3], knows [B,m,3] -> [dist2 [B,n,3] f32 (squared), idx [B,n,3] i32]."""
     _contig(unknowns, "unknowns"); _contig(knows, "knows"); _is_float(unknowns, "unknowns"); _is_float(knows, "knows")

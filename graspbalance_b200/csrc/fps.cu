@@ -42,7 +42,8 @@ struct FpsShared {
 
 template <int P, int T>
 __global__ void __launch_bounds__(T, 1) fps_cluster_kernel(const float *__restrict__ xyz, float *__restrict__ temp,
-                                                           int *__restrict__ idxs, int n, int m, int variant, int L, int direct) {
+                                                           int *__restrict__ idxs, int n, int m, int variant, int L, int direct,
+                                                           float *__restrict__ new_xyz) {
   extern __shared__ float s_pts[];  // [3][P*T] copy of this CTA's coordinates (winner lookup without dynamic register indexing)
   __shared__ __align__(16) FpsShared sh;
 
@@ -56,6 +57,7 @@ __global__ void __launch_bounds__(T, 1) fps_cluster_kernel(const float *__restri
   xyz += (size_t)scene * n * 3;
   idxs += (size_t)scene * m;
   if (temp) temp += (size_t)scene * n;
+  if (new_xyz) new_xyz += (size_t)scene * m * 3;  // optional: coordinates of the picks (what gather_operation would fetch)
 
   if (tid == 0) {
     mbar_init(&sh.full[0], 1);
@@ -85,7 +87,10 @@ __global__ void __launch_bounds__(T, 1) fps_cluster_kernel(const float *__restri
   // picked when nothing is eligible (reference: besti stays 0)
   const float p0x = __ldg(xyz), p0y = __ldg(xyz + 1), p0z = __ldg(xyz + 2);
   float cx = p0x, cy = p0y, cz = p0z;
-  if (rank == 0 && tid == 0) idxs[0] = 0;
+  if (rank == 0 && tid == 0) {
+    idxs[0] = 0;
+    if (new_xyz) new_xyz[0] = p0x, new_xyz[1] = p0y, new_xyz[2] = p0z;
+  }
 
   __syncthreads();
   if (C > 1) cluster_sync_all();  // peers' mbarriers are initialised before anyone pushes
@@ -182,7 +187,10 @@ __global__ void __launch_bounds__(T, 1) fps_cluster_kernel(const float *__restri
     } else {
       cx = p0x, cy = p0y, cz = p0z;
     }
-    if (rank == 0 && tid == 0) idxs[j] = pick;
+    if (rank == 0 && tid == 0) {
+      idxs[j] = pick;
+      if (new_xyz) new_xyz[3 * j] = cx, new_xyz[3 * j + 1] = cy, new_xyz[3 * j + 2] = cz;
+    }
   }
 
   if (temp) {
@@ -199,7 +207,8 @@ __global__ void __launch_bounds__(T, 1) fps_cluster_kernel(const float *__restri
 // global memory (temp must be provided by the launcher), same key reduction.
 template <int T>
 __global__ void __launch_bounds__(T, 1) fps_global_kernel(const float *__restrict__ xyz, float *__restrict__ temp,
-                                                          int *__restrict__ idxs, int n, int m, int variant, int L) {
+                                                          int *__restrict__ idxs, int n, int m, int variant, int L,
+                                                          float *__restrict__ new_xyz) {
   __shared__ __align__(16) uint32_t wc[2][32][8];
   const int scene = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int W = T / 32;
@@ -208,7 +217,11 @@ __global__ void __launch_bounds__(T, 1) fps_global_kernel(const float *__restric
   temp += (size_t)scene * n;
   const float p0x = __ldg(xyz), p0y = __ldg(xyz + 1), p0z = __ldg(xyz + 2);
   float cx = p0x, cy = p0y, cz = p0z;
-  if (tid == 0) idxs[0] = 0;
+  if (new_xyz) new_xyz += (size_t)scene * m * 3;
+  if (tid == 0) {
+    idxs[0] = 0;
+    if (new_xyz) new_xyz[0] = p0x, new_xyz[1] = p0y, new_xyz[2] = p0z;
+  }
   for (int j = 1; j < m; ++j) {
     const int par = j & 1;
     int bkey = kKeyNone;
@@ -239,7 +252,10 @@ __global__ void __launch_bounds__(T, 1) fps_global_kernel(const float *__restric
     int pick = 0;
     if (key != kKeyNone) pick = (int)fps_tiekey_inv(btk, L);
     cx = __ldg(xyz + 3 * (size_t)pick), cy = __ldg(xyz + 3 * (size_t)pick + 1), cz = __ldg(xyz + 3 * (size_t)pick + 2);
-    if (tid == 0) idxs[j] = pick;
+    if (tid == 0) {
+      idxs[j] = pick;
+      if (new_xyz) new_xyz[3 * j] = cx, new_xyz[3 * j + 1] = cy, new_xyz[3 * j + 2] = cz;
+    }
   }
 }
 
@@ -250,7 +266,8 @@ __global__ void fill_kernel(float *p, size_t n, float v) {
 constexpr int kFpsRetrySmallerCluster = -1001;  // internal: cluster shape not schedulable, try half the size
 
 template <int P, int T>
-static int launch_fps(const float *xyz, float *temp, int *idx, int b, int n, int m, int variant, int L, int C, cudaStream_t s) {
+static int launch_fps(const float *xyz, float *temp, int *idx, float *new_xyz, int b, int n, int m, int variant, int L, int C,
+                      cudaStream_t s) {
   auto kern = fps_cluster_kernel<P, T>;
   const size_t dyn = (size_t)3 * P * T * sizeof(float);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
@@ -282,7 +299,7 @@ static int launch_fps(const float *xyz, float *temp, int *idx, int b, int n, int
   }
   // direct mode: every warp's winner goes straight to all CTAs when they fit one lane each (g_tuning.fps_direct: 1 = never)
   const int direct = (C > 1 && C * (T / 32) <= 32 && g_tuning.fps_direct != 1) ? 1 : 0;
-  e = cudaLaunchKernelEx(&cfg, kern, xyz, temp, idx, n, m, variant, L, direct);
+  e = cudaLaunchKernelEx(&cfg, kern, xyz, temp, idx, n, m, variant, L, direct, new_xyz);
   count_launch();
   return (int)e;
 }
@@ -297,7 +314,7 @@ static int floor_log2(int v) {
 
 using namespace gb;
 
-extern "C" int gb_fps(const float *xyz, float *temp, int *idx, int b, int n, int m, int variant, gb_stream_t stream) {
+static int fps_impl(const float *xyz, float *temp, int *idx, float *new_xyz, int b, int n, int m, int variant, gb_stream_t stream) {
   if (b < 0 || n <= 0 || m < 0 || (variant != GB_FPS_A && variant != GB_FPS_B)) return (int)cudaErrorInvalidValue;
   if (b == 0 || m == 0) return 0;  // nothing to do (empty tensors have null data pointers)
   if (!xyz || !idx) return (int)cudaErrorInvalidValue;
@@ -337,7 +354,7 @@ extern "C" int gb_fps(const float *xyz, float *temp, int *idx, int b, int n, int
     const int per_thread = (int)(((long)n + (long)Ce * T - 1) / ((long)Ce * T));
     int rc = kFpsRetrySmallerCluster - 1;  // "no instantiation"
 #define GB_FPS_CASE(PP, TT) \
-  else if (T == TT && per_thread <= PP) rc = launch_fps<PP, TT>(xyz, temp, idx, b, n, m, variant, L, Ce, s);
+  else if (T == TT && per_thread <= PP) rc = launch_fps<PP, TT>(xyz, temp, idx, new_xyz, b, n, m, variant, L, Ce, s);
     if (false) {}
     GB_FPS_CASE(1, 1024) GB_FPS_CASE(2, 1024) GB_FPS_CASE(3, 1024) GB_FPS_CASE(4, 1024) GB_FPS_CASE(5, 1024)
     GB_FPS_CASE(6, 1024) GB_FPS_CASE(8, 1024) GB_FPS_CASE(10, 1024)
@@ -359,9 +376,21 @@ extern "C" int gb_fps(const float *xyz, float *temp, int *idx, int b, int n, int
     fill_kernel<<<1024, 256, 0, s>>>(tmp, (size_t)b * n, 1e10f);
     count_launch();
   }
-  fps_global_kernel<1024><<<b, 1024, 0, s>>>(xyz, tmp, idx, n, m, variant, L);
+  fps_global_kernel<1024><<<b, 1024, 0, s>>>(xyz, tmp, idx, n, m, variant, L, new_xyz);
   count_launch();
   int err = finish_launch();
   if (!temp) cudaFreeAsync(tmp, s);
   return err;
+}
+
+extern "C" int gb_fps(const float *xyz, float *temp, int *idx, int b, int n, int m, int variant, gb_stream_t stream) {
+  return fps_impl(xyz, temp, idx, nullptr, b, n, m, variant, stream);
+}
+
+/* FPS + the gather_operation every caller runs on its result (pointnet2_modules.py:151-158: new_xyz = the sampled
+ * coordinates), SURVEY 8f-2: new_xyz [b, m, 3] is written by the same launch -- the kernel holds the coordinates of
+ * every pick anyway (they are the centre of the next round). */
+extern "C" int gb_fps_xyz(const float *xyz, float *temp, int *idx, float *new_xyz, int b, int n, int m, int variant, gb_stream_t stream) {
+  if (!new_xyz && b > 0 && m > 0) return (int)cudaErrorInvalidValue;
+  return fps_impl(xyz, temp, idx, new_xyz, b, n, m, variant, stream);
 }

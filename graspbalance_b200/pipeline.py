@@ -47,7 +47,7 @@ def _randn(shape, gen, device):
 class OpPipeline:
     """Holds the stand-in feature / gradient tensors (allocated once, outside any timed region) and runs the chain."""
 
-    def __init__(self, batch, n_points=20000, device="cuda", seed=0, backward=True, overlap=True, fused_crops=True):
+    def __init__(self, batch, n_points=20000, device="cuda", seed=0, backward=True, overlap=True, fused_crops=True, fused_sampling=True):
         self.B, self.N, self.device, self.backward = batch, n_points, torch.device(device), backward
         # overlap: the sampling chain (4 x FPS + gather: latency-bound, a few warps per SM, depends on xyz only) and the
         # collision tests (independent of everything else) run on side streams next to the bandwidth-bound grouping work
@@ -62,6 +62,7 @@ class OpPipeline:
                             for (_, r, ns, _) in SA_SPECS]
         self.irm_groupers = [gb_group.QueryAndGroup(r, ns) for (_, _, r, ns) in IRM_SPECS]
         self.fused_crops = fused_crops
+        self.fused_sampling = fused_sampling
         self.crop_modules = [GraspWidthGrouping(64, 3, cylinder_radius=r, hmin=CROP_HMIN, hmax_list=CROP_HMAX, mlps=torch.nn.Identity())
                              for r in CROP_RADII]
         # stand-ins for MLP outputs (features entering each stage) and for upstream gradients
@@ -116,6 +117,8 @@ class OpPipeline:
         main = torch.cuda.current_stream(self.device) if self.overlap else None
 
         def sample(cur, npoint):  # furthest_point_sample + gather_operation of one SA module (pointnet2_modules.py:151-158)
+            if self.fused_sampling:  # one launch: the FPS kernel holds the coordinates of every pick
+                return pu.furthest_point_sample_xyz(cur, npoint)
             inds = pu.furthest_point_sample(cur, npoint)
             return inds, pu.gather_operation(cur.transpose(1, 2).contiguous(), inds).transpose(1, 2).contiguous()
 

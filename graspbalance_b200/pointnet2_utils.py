@@ -34,6 +34,25 @@ class FurthestPointSampling(Function):
 furthest_point_sample = FurthestPointSampling.apply
 
 
+class FurthestPointSamplingXYZ(Function):
+    """furthest_point_sample + the gather_operation PointnetSAModuleVotes runs on its result
+    (pointnet2_modules.py:151-158): returns (inds [B,npoint] i32, new_xyz [B,npoint,3]) from one launch.  new_xyz carries no
+    gradient to xyz on this path (callers that need one use gather_operation)."""
+
+    @staticmethod
+    def forward(ctx, xyz, npoint):
+        inds, new_xyz = _ext.furthest_point_sampling_xyz(xyz, npoint)
+        ctx.mark_non_differentiable(inds, new_xyz)
+        return inds, new_xyz
+
+    @staticmethod
+    def backward(ctx, a=None, b=None):
+        return None, None
+
+
+furthest_point_sample_xyz = FurthestPointSamplingXYZ.apply
+
+
 class GatherOperation(Function):
     @staticmethod
     def forward(ctx, features, idx):

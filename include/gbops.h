@@ -49,6 +49,11 @@ GB_API const char *gb_error_string(int err);
  * reference; when NULL, 1e10 is used and nothing is written back. */
 GB_API int gb_fps(const float *xyz, float *temp, int *idx, int b, int n, int m, int variant, gb_stream_t stream);
 
+/* FPS + the gather_operation every caller runs on its result (pointnet2_modules.py:151-158 `new_xyz = gather_operation(
+ * xyz_flipped, inds)`), SURVEY 8f-2: as gb_fps, and new_xyz [b, m, 3] = xyz[b, idx[b, j]] written by the same launch. */
+GB_API int gb_fps_xyz(const float *xyz, float *temp, int *idx, float *new_xyz, int b, int n, int m, int variant,
+               gb_stream_t stream);
+
 /* A: gather_points_kernel_wrapper (sampling_gpu.cu:27-35); B: gather_points_kernel_launcher_fast (:21-34).
  * points [b,c,n], idx [b,m] -> out [b,c,m]. */
 GB_API int gb_gather_fwd(const float *points, const int *idx, float *out, int b, int c, int n, int m, gb_stream_t stream);

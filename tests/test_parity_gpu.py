@@ -339,6 +339,20 @@ def test_group_full_size_vs_reference(dev, ref_a, ref_b):
         assert_grad_close(got_g.cpu().numpy(), want_g.cpu().numpy())
 
 
+@pytest.mark.parametrize("B,N,m", [(2, 20000, 1024), (3, 2048, 512), (1, 700, 700), (2, 40000, 64), (1, 100000, 16)])
+def test_fps_xyz_is_fps_plus_gather(dev, B, N, m):
+    """gb_fps_xyz == furthest_point_sample followed by the gather of pointnet2_modules.py:151-158 (cluster and global paths)."""
+    xyz_np = scenes.scene_batch(range(B), N, "tabletop" if N >= 1000 else "uniform")
+    xyz = T(xyz_np, dev)
+    inds, new_xyz = pu.furthest_point_sample_xyz(xyz, m)
+    want = pu.furthest_point_sample(xyz, m)
+    assert torch.equal(inds, want)
+    want_xyz = pu.gather_operation(xyz.transpose(1, 2).contiguous(), want).transpose(1, 2).contiguous()
+    assert torch.equal(new_xyz, want_xyz)
+    if N <= 20000:
+        np.testing.assert_array_equal(inds.cpu().numpy(), oracle.furthest_point_sample(xyz_np, m, "A"))
+
+
 # ------------------------------------------------------------------------------------------- three_nn / interpolate
 @pytest.mark.parametrize("B,n,m", [(2, 20000, 1024), (1, 513, 2), (2, 1000, 3), (1, 64, 1), (2, 4000, 2500)])
 def test_three_nn_vs_oracle(dev, B, n, m):

@@ -34,9 +34,11 @@ def test_fused_grasp_crops_match_the_sixteen_separate_calls(dev):
     host, offs = bench.make_host_inputs([5, 6], pin=False)
     sums = []
     for fused in (False, True):
-        pipe = pipeline.OpPipeline(2, bench.N_POINTS, dev, seed=0, backward=False, overlap=False, fused_crops=fused)
+        pipe = pipeline.OpPipeline(2, bench.N_POINTS, dev, seed=0, backward=False, overlap=False, fused_crops=fused, fused_sampling=fused)
         xyz, rot, grasps = bench.to_device(host, offs, dev)
         o = pipe.run(xyz, rot, None)
         torch.cuda.synchronize()
-        sums.append(float(o["crop_checksum"]))
-    assert abs(sums[0] - sums[1]) <= 1e-4 * max(1.0, abs(sums[0]))
+        sums.append((float(o["crop_checksum"]), o["sa1_inds"].cpu().numpy(), float(o["up_checksum"])))
+    assert abs(sums[0][0] - sums[1][0]) <= 1e-4 * max(1.0, abs(sums[0][0]))
+    np.testing.assert_array_equal(sums[0][1], sums[1][1])  # FPS + gather in one launch: same samples
+    assert abs(sums[0][2] - sums[1][2]) <= 1e-4 * max(1.0, abs(sums[0][2]))
