@@ -50,13 +50,33 @@ def read_peaks():
 # clocks sampling during the timed region
 # ------------------------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region.  NVML in-process (pynvml: two light queries every 50 ms);
+    a looping `nvidia-smi` process beside the benchmark was measured to stall the GPU for 60-80 ms now and then (one step
+    of ten taking 70-85 ms instead of 13.3), so it is only the fallback when pynvml is missing."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, gpu_index):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.rows, self.proc, self.gpu, self.nvml, self._stop = [], None, gpu_index, None, False
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            idx = self.gpu
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.gpu])
+                except Exception:
+                    idx = self.gpu
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nvml = pynvml
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            threading.Thread(target=self._poll, daemon=True).start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -64,30 +84,47 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        bits = (("hw_slowdown", getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8)),
+                ("hw_thermal_slowdown", getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40)),
+                ("sw_thermal_slowdown", getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20)),
+                ("sw_power_cap", getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4)))
+        while not self._stop:
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.rows.append((time.time(), sm, self.max_sm, [name for name, b in bits if mask & b]))
+            except Exception:
+                pass
+            time.sleep(0.05)
+
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append((time.time(), line.strip()))
-
-    def stop(self, t0, t1):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        for ts, line in self.rows:
-            if ts < t0 or ts > t1 + 0.1:
-                continue
-            p = [x.strip() for x in line.split(",")]
+            p = [x.strip() for x in line.strip().split(",")]
             try:
-                sm.append(float(p[0])); mx.append(float(p[1]))
+                reasons = [name for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[2:6])
+                           if v.lower().startswith("active")]
+                self.rows.append((time.time(), float(p[0]), float(p[1]), reasons))
             except Exception:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
+
+    def stop(self, t0, t1):
+        if self.nvml is None and self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["NVML and nvidia-smi unavailable"]}
+        time.sleep(0.05 if self.nvml is not None else 0.15)
+        self._stop = True
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ts, clk, mxclk, rs in list(self.rows):
+            if ts < t0 or ts > t1 + (0.0 if self.nvml is not None else 0.1):
+                continue
+            sm.append(clk); mx.append(mxclk); reasons.update(rs)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples inside the timed region"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -302,11 +339,15 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t_wall0 = time.time()
         e0.record()
+        marks = []
         for _ in range(n_steps):
             step(resident, inputs)
+            marks.append(torch.cuda.Event(enable_timing=True))
+            marks[-1].record()  # per-step marks on the main stream: diagnostics only (the value is e0..e1 over all K steps)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
+        timed.per_step = [a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks)]
         if world > 1:
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -320,6 +361,20 @@ def main():
     # allocator priming (untimed, on top of the W warm-up steps): the caching allocator keeps growing its pools for a few
     # steps because blocks handed to side streams are recycled late; a cudaMalloc inside the timed region costs
     # milliseconds.  Step until one whole step needs no new device allocation (at most 8 extra steps).
+    # ... and leave it slack: a block as large as everything reserved so far (the allocator splits it on demand) plus 128 MB
+    # of small-pool blocks.  A cudaMalloc needs the driver's resource-manager lock; when an NVML / nvidia-smi clock query
+    # holds that lock at the same moment the step stalls for 40-120 ms (measured: one step of ten at 70-128 ms instead of
+    # 13.3 ms in a third of the runs).  Kernel launches do not take the lock, so with no allocation inside the timed region
+    # the clock sampling is harmless.
+    slack = [torch.empty(max(torch.cuda.memory_reserved(dev), 1 << 30), dtype=torch.uint8, device=dev)]
+    slack += [torch.empty(64 << 10, dtype=torch.uint8, device=dev) for _ in range(2048)]
+    for st in (getattr(pipe, n, None) for n in ("_fps_stream", "_col_stream", "_aux_stream")):  # pools are per stream
+        if st is not None:
+            with torch.cuda.stream(st):
+                slack += [torch.empty(2 << 30, dtype=torch.uint8, device=dev)]
+                slack += [torch.empty(64 << 10, dtype=torch.uint8, device=dev) for _ in range(512)]
+    torch.cuda.synchronize()
+    del slack
     prime_steps, quiet = 0, 0
     while prime_steps < 10 and quiet < 3:  # three steps in a row without a new device allocation
         before = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
@@ -343,6 +398,11 @@ def main():
         torch.cuda.profiler.stop()
     launches = _lib.launch_count() - launches0
     dev_allocs_timed = torch.cuda.memory_stats(dev).get("num_device_alloc", 0) - dev_allocs0
+    per_step = sorted(timed.per_step)
+    mstats = torch.cuda.memory_stats(dev)
+    step_diag = {"min_ms": per_step[0], "median_ms": per_step[len(per_step) // 2], "max_ms": per_step[-1],
+                 "reserved_gb": mstats.get("reserved_bytes.all.current", 0) / 1e9, "device_frees": mstats.get("num_device_free", 0),
+                 "alloc_retries": mstats.get("num_alloc_retries", 0)}
     clocks = sampler.stop(tw0, tw1) if rank == 0 else None
     value = world * B * args.steps / (ms * 1e-3)
 
@@ -428,7 +488,8 @@ def main():
                        "streams": "sampling chain + collision tests on side streams" if pipe.overlap else "single stream",
                        "l2": "per-step working set (>10 GB of grouped features) exceeds the 126 MB L2; no explicit flush",
                        "algorithmic_bytes_per_scene": int(sum(algo.values())),
-                       "allocator_priming_steps": prime_steps, "device_allocs_in_timed_region": int(dev_allocs_timed)},
+                       "allocator_priming_steps": prime_steps, "device_allocs_in_timed_region": int(dev_allocs_timed),
+                       "step_diagnostics": step_diag},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "roofline_pass_ms_per_step": ms_prof / args.steps,
             "pipeline_hbm_frac": (sum(algo.values()) * world * B * args.steps / (ms * 1e-3) / 1e9) / (peak * world),
