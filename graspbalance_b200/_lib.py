@@ -8,7 +8,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgbops.so")
+LIB_PATH = os.environ.get("GBOPS_LIB") or os.path.join(_HERE, "libgbops.so")  # GBOPS_LIB: experiments with an alternative build
 CSRC = os.path.join(_HERE, "csrc")
 ABI_VERSION = 1
 
