@@ -19,6 +19,7 @@ static int *tuning_slot(const char *key) {
   if (!strcmp(key, "fps_cluster")) return &gb::g_tuning.fps_cluster;
   if (!strcmp(key, "fps_threads")) return &gb::g_tuning.fps_threads;
   if (!strcmp(key, "fps_direct")) return &gb::g_tuning.fps_direct;
+  if (!strcmp(key, "fps_defer")) return &gb::g_tuning.fps_defer;
   if (!strcmp(key, "group_split")) return &gb::g_tuning.group_split;
   if (!strcmp(key, "group_mode")) return &gb::g_tuning.group_mode;
   if (!strcmp(key, "group_target_kb")) return &gb::g_tuning.group_target_kb;

@@ -37,6 +37,7 @@ inline int num_sms() {
 struct Tuning {
   int fps_cluster = 0;
   int fps_threads = 0;
+  int fps_defer = 0;   // 1: store every pick to global memory inside the round loop
   int fps_direct = 0;  // 1: CTA-level stage before the cluster exchange even when every warp could push directly
   int group_split = 0;
   int group_mode = 0;  // flags: 1 plain stores, 2 generic kernel, 4 no sorted backward, 8 no single-row TMA kernel, 16 flattened forward split

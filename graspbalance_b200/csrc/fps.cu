@@ -43,7 +43,7 @@ struct FpsShared {
 template <int P, int T>
 __global__ void __launch_bounds__(T, 1) fps_cluster_kernel(const float *__restrict__ xyz, float *__restrict__ temp,
                                                            int *__restrict__ idxs, int n, int m, int variant, int L, int direct,
-                                                           float *__restrict__ new_xyz) {
+                                                           float *__restrict__ new_xyz, int defer) {
   extern __shared__ float s_pts[];  // [3][P*T] copy of this CTA's coordinates (winner lookup without dynamic register indexing)
   __shared__ __align__(16) FpsShared sh;
 
@@ -69,6 +69,7 @@ __global__ void __launch_bounds__(T, 1) fps_cluster_kernel(const float *__restri
   const uint32_t g = rank * T + tid;
   const uint32_t stride = C * T;
   float *sx = s_pts, *sy = s_pts + P * T, *sz = s_pts + 2 * P * T;
+  uint32_t *s_picks = reinterpret_cast<uint32_t *>(s_pts + 3 * P * T);  // [m] tie keys of the picks (defer mode)
 #pragma unroll
   for (int i = 0; i < P; ++i) {
     const uint32_t k = g + i * stride;
@@ -177,14 +178,25 @@ __global__ void __launch_bounds__(T, 1) fps_cluster_kernel(const float *__restri
       src = __ffs(__ballot_sync(0xffffffffu, (int)ckey_u == key && ctk == btk)) - 1;
       ux = __shfl_sync(0xffffffffu, ux, src), uy = __shfl_sync(0xffffffffu, uy, src), uz = __shfl_sync(0xffffffffu, uz, src);
     }
-    int pick = 0;
     if (key != kKeyNone) {
-      pick = (int)fps_tiekey_inv(btk, L);
       cx = __uint_as_float(ux), cy = __uint_as_float(uy), cz = __uint_as_float(uz);
     } else {
       cx = p0x, cy = p0y, cz = p0z;
+      btk = 0xFFFFFFFFu;
     }
-    if (rank == 0 && tid == 0) idxs[j] = pick;
+    // defer mode: the round only parks the winner's tie key in shared memory; index conversion and the global stores
+    // happen once, after the loop (the round loop is latency-critical: every instruction in it is paid m - 1 times)
+    if (rank == 0 && tid == 0) {
+      if (defer) s_picks[j] = btk;
+      else idxs[j] = btk == 0xFFFFFFFFu ? 0 : (int)fps_tiekey_inv(btk, L);
+    }
+  }
+  if (defer && rank == 0) {
+    __syncthreads();
+    for (int j = 1 + tid; j < m; j += T) {
+      const uint32_t tk = s_picks[j];
+      idxs[j] = tk == 0xFFFFFFFFu ? 0 : (int)fps_tiekey_inv(tk, L);
+    }
   }
 
   // optional epilogue: coordinates of the picks, gathered here rather than stored round by round (three predicated
@@ -273,7 +285,9 @@ template <int P, int T>
 static int launch_fps(const float *xyz, float *temp, int *idx, float *new_xyz, int b, int n, int m, int variant, int L, int C,
                       cudaStream_t s) {
   auto kern = fps_cluster_kernel<P, T>;
-  const size_t dyn = (size_t)3 * P * T * sizeof(float);
+  // defer mode parks the picks in shared memory (4 bytes each) when they fit beside the coordinate copy
+  const int defer = ((size_t)3 * P * T * sizeof(float) + (size_t)m * 4 <= 200u * 1024u && g_tuning.fps_defer != 1) ? 1 : 0;
+  const size_t dyn = (size_t)3 * P * T * sizeof(float) + (defer ? (size_t)m * 4 : 0);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
   if (e != cudaSuccess) return (int)e;
   if (C > 8) {
@@ -303,7 +317,7 @@ static int launch_fps(const float *xyz, float *temp, int *idx, float *new_xyz, i
   }
   // direct mode: every warp's winner goes straight to all CTAs when they fit one lane each (g_tuning.fps_direct: 1 = never)
   const int direct = (C > 1 && C * (T / 32) <= 32 && g_tuning.fps_direct != 1) ? 1 : 0;
-  e = cudaLaunchKernelEx(&cfg, kern, xyz, temp, idx, n, m, variant, L, direct, new_xyz);
+  e = cudaLaunchKernelEx(&cfg, kern, xyz, temp, idx, n, m, variant, L, direct, new_xyz, defer);
   count_launch();
   return (int)e;
 }
