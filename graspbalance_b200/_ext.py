@@ -82,6 +82,18 @@ def furthest_point_sampling_xyz(points, nsamples):
     return out, new_xyz
 
 
+def furthest_point_sampling_segments(points, seg, max_n, max_m, total_out):
+    """Segmented FPS (gb_fps_segments): points [total,3] f32 packed segments; seg [S,4] i32 CUDA rows (first point, points,
+    samples, first output slot).  Returns segment-local indices [total_out] i32, each segment sampled exactly as
+    furthest_point_sampling samples it alone."""
+    _contig(points, "points"); _is_float(points, "points"); _contig(seg, "seg"); _is_int(seg, "seg")
+    _need_cuda(points); _cuda(seg, "seg")
+    out = torch.zeros((int(total_out),), dtype=torch.int32, device=points.device)
+    if seg.shape[0]:
+        _lib.call("gb_fps_segments", points, points.data_ptr(), seg.data_ptr(), out.data_ptr(), None, int(seg.shape[0]), int(max_n), int(max_m), 0)
+    return out
+
+
 def three_nn(unknowns, knows):
     """interpolate.cpp:19-45.  unknowns [B,n,3], knows [B,m,3] -> [dist2 [B,n,3] f32 (squared), idx [B,n,3] i32]."""
     _contig(unknowns, "unknowns"); _contig(knows, "knows"); _is_float(unknowns, "unknowns"); _is_float(knows, "knows")

@@ -43,7 +43,7 @@ struct FpsShared {
 template <int P, int T>
 __global__ void __launch_bounds__(T, 1) fps_cluster_kernel(const float *__restrict__ xyz, float *__restrict__ temp,
                                                            int *__restrict__ idxs, int n, int m, int variant, int L, int direct,
-                                                           float *__restrict__ new_xyz, int defer) {
+                                                           float *__restrict__ new_xyz, int defer, const int4 *__restrict__ seg) {
   extern __shared__ float s_pts[];  // [3][P*T] copy of this CTA's coordinates (winner lookup without dynamic register indexing)
   __shared__ __align__(16) FpsShared sh;
 
@@ -54,10 +54,28 @@ __global__ void __launch_bounds__(T, 1) fps_cluster_kernel(const float *__restri
   const int lane = tid & 31, warp = tid >> 5;
   constexpr int W = T / 32;
 
-  xyz += (size_t)scene * n * 3;
-  idxs += (size_t)scene * m;
-  if (temp) temp += (size_t)scene * n;
-  if (new_xyz) new_xyz += (size_t)scene * m * 3;  // optional: coordinates of the picks (what gather_operation would fetch)
+  if (seg) {
+    // segmented mode (one CTA per segment, C = 1): segments of a packed point array with their own sizes -- the per-object
+    // FPS loop of ObjectBalanceSampling (TrainModel/modules.py:186-213) in one launch.  seg = (first point, points,
+    // samples, first output slot); the tie order follows the segment's own BS = opt_n_threads(points).
+    const int4 sg = seg[scene];
+    xyz += (size_t)sg.x * 3;
+    n = sg.y, m = sg.z;
+    idxs += sg.w;
+    if (new_xyz) new_xyz += (size_t)sg.w * 3;
+    temp = nullptr;
+    if (m <= 0) return;
+    if (n <= 0) {  // nothing to sample from: index 0, as the reference's untouched besti
+      for (int j = tid; j < m; j += T) idxs[j] = 0;
+      return;
+    }
+    L = min(31 - __clz(n), variant == GB_FPS_A ? 9 : 10);
+  } else {
+    xyz += (size_t)scene * n * 3;
+    idxs += (size_t)scene * m;
+    if (temp) temp += (size_t)scene * n;
+    if (new_xyz) new_xyz += (size_t)scene * m * 3;  // optional: coordinates of the picks (what gather_operation would fetch)
+  }
 
   if (tid == 0) {
     mbar_init(&sh.full[0], 1);
@@ -283,7 +301,7 @@ constexpr int kFpsRetrySmallerCluster = -1001;  // internal: cluster shape not s
 
 template <int P, int T>
 static int launch_fps(const float *xyz, float *temp, int *idx, float *new_xyz, int b, int n, int m, int variant, int L, int C,
-                      cudaStream_t s) {
+                      cudaStream_t s, const int4 *seg = nullptr) {
   auto kern = fps_cluster_kernel<P, T>;
   // defer mode parks the picks in shared memory (4 bytes each) when they fit beside the coordinate copy
   const int defer = ((size_t)3 * P * T * sizeof(float) + (size_t)m * 4 <= 200u * 1024u && g_tuning.fps_defer != 1) ? 1 : 0;
@@ -317,7 +335,7 @@ static int launch_fps(const float *xyz, float *temp, int *idx, float *new_xyz, i
   }
   // direct mode: every warp's winner goes straight to all CTAs when they fit one lane each (g_tuning.fps_direct: 1 = never)
   const int direct = (C > 1 && C * (T / 32) <= 32 && g_tuning.fps_direct != 1) ? 1 : 0;
-  e = cudaLaunchKernelEx(&cfg, kern, xyz, temp, idx, n, m, variant, L, direct, new_xyz, defer);
+  e = cudaLaunchKernelEx(&cfg, kern, xyz, temp, idx, n, m, variant, L, direct, new_xyz, defer, seg);
   count_launch();
   return (int)e;
 }
@@ -411,4 +429,32 @@ extern "C" int gb_fps(const float *xyz, float *temp, int *idx, int b, int n, int
 extern "C" int gb_fps_xyz(const float *xyz, float *temp, int *idx, float *new_xyz, int b, int n, int m, int variant, gb_stream_t stream) {
   if (!new_xyz && b > 0 && m > 0) return (int)cudaErrorInvalidValue;
   return fps_impl(xyz, temp, idx, new_xyz, b, n, m, variant, stream);
+}
+
+/* Segmented FPS: nseg independent point sets of different sizes packed in one array, one launch -- the per-object loop of
+ * ObjectBalanceSampling (TrainModel/modules.py:186-213: `furthest_point_sample(object_points.unsqueeze(0), k)` per object
+ * of every scene).  seg [nseg,4] i32 on the DEVICE = (first point, points, samples, first output slot) per segment;
+ * idx (and new_xyz, optional) are indexed by output slot; indices are segment-local, ties resolved as gb_fps resolves
+ * them for a cloud of the segment's size.  max_n / max_m = the largest points / samples entry (host knowledge; a segment
+ * of up to 10240 points is held in the registers of one CTA, larger ones are refused with cudaErrorInvalidValue). */
+extern "C" int gb_fps_segments(const float *xyz, const int *seg, int *idx, float *new_xyz, int nseg, int max_n, int max_m, int variant,
+                               gb_stream_t stream) {
+  if (nseg < 0 || max_n < 0 || max_m < 0 || (variant != GB_FPS_A && variant != GB_FPS_B)) return (int)cudaErrorInvalidValue;
+  if (nseg == 0 || max_m == 0) return 0;
+  if (!xyz || !seg || !idx) return (int)cudaErrorInvalidValue;
+  if (((uintptr_t)seg & 15u) != 0) return (int)cudaErrorInvalidValue;
+  const int T = variant == GB_FPS_A ? 512 : 1024;  // one CTA per segment: T must be a multiple of every segment's BS
+  const int per_thread = (max_n + T - 1) / T;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int4 *sg = reinterpret_cast<const int4 *>(seg);
+  int rc = (int)cudaErrorInvalidValue;
+#define GB_FPS_SEG(PP, TT) \
+  else if (T == TT && per_thread <= PP) rc = launch_fps<PP, TT>(xyz, nullptr, idx, new_xyz, nseg, max_n, max_m, variant, 0, 1, s, sg);
+  if (false) {}
+  GB_FPS_SEG(1, 512) GB_FPS_SEG(2, 512) GB_FPS_SEG(4, 512) GB_FPS_SEG(6, 512) GB_FPS_SEG(8, 512) GB_FPS_SEG(10, 512) GB_FPS_SEG(12, 512)
+  GB_FPS_SEG(16, 512) GB_FPS_SEG(20, 512)
+  GB_FPS_SEG(1, 1024) GB_FPS_SEG(2, 1024) GB_FPS_SEG(4, 1024) GB_FPS_SEG(6, 1024) GB_FPS_SEG(8, 1024) GB_FPS_SEG(10, 1024)
+#undef GB_FPS_SEG
+  if (rc == kFpsRetrySmallerCluster) rc = (int)cudaErrorInvalidValue;
+  return rc;
 }

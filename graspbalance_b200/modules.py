@@ -53,3 +53,44 @@ class GraspWidthGrouping(nn.Module):
         vp_features = self.mlps(self.group(seed_xyz, pointcloud, vp_rot))
         vp_features = F.max_pool2d(vp_features, kernel_size=[1, vp_features.size(3)])
         return vp_features.view(B, -1, num_seed, len(self.hmax_list))
+
+
+def ObjectBalanceSampling(end_points, num_seed=1024):
+    """TrainModel/modules.py:177-223: every segmented object of a scene contributes num_seed // num_objects seeds (the last
+    one takes the remainder), chosen by FPS among the object's points; the seeds' indices, coordinates and up-sampled
+    features replace fp2_inds / fp2_xyz / fp2_features.  The reference loops over scenes and objects with one B=1
+    furthest_point_sample per object; here all objects of all scenes are sampled by ONE segmented launch
+    (gb_fps_segments), with identical picks.  Label 0 is background, as in the reference."""
+    batch_seg_res = end_points["seed_cluster"]
+    batch_points = end_points["point_clouds"]
+    batch_features = end_points["up_sample_features"].permute(0, 2, 1)
+    B, N = batch_seg_res.shape
+    order = torch.argsort(batch_seg_res, dim=1, stable=True)          # points of a scene grouped by label, index order kept
+    packed_src, counts, ks, scene_of_obj = [], [], [], []
+    for i in range(B):
+        labels, cnt = torch.unique(batch_seg_res[i], return_counts=True)  # sorted labels (one host sync per scene, as upstream)
+        labels, cnt = labels.tolist(), cnt.tolist()
+        num_objects = len(labels) - 1
+        per_obj = [num_seed // num_objects] * num_objects
+        per_obj[-1] += num_seed % num_objects
+        start, t = 0, 0
+        for lab, c in zip(labels, cnt):
+            if lab != 0:
+                packed_src.append(order[i, start:start + c])
+                counts.append(c)
+                ks.append(per_obj[t])
+                scene_of_obj.append(i)
+                t += 1
+            start += c
+    src = torch.cat(packed_src)                                         # scene-local index of every packed point
+    scene_ids = torch.repeat_interleave(torch.tensor(scene_of_obj, device=src.device), torch.tensor(counts, device=src.device))
+    packed_xyz = batch_points[scene_ids, src].contiguous().float()
+    local = pu.furthest_point_sample_segments(packed_xyz, counts, ks).long()
+    firsts = torch.tensor([0] + counts[:-1], device=src.device).cumsum(0)
+    pick = src[torch.repeat_interleave(firsts, torch.tensor(ks, device=src.device)) + local]  # scene-local indices, scene-major
+    fp2_inds = pick.view(B, num_seed)
+    end_points["fp2_inds_fps"] = end_points["fp2_inds"]
+    end_points["fp2_inds"] = fp2_inds.int()
+    end_points["fp2_xyz"] = torch.gather(batch_points, 1, fp2_inds.unsqueeze(-1).expand(-1, -1, 3))
+    end_points["fp2_features"] = torch.gather(batch_features, 1, fp2_inds.unsqueeze(-1).expand(-1, -1, batch_features.shape[-1])).permute(0, 2, 1)
+    return end_points

@@ -53,6 +53,23 @@ class FurthestPointSamplingXYZ(Function):
 furthest_point_sample_xyz = FurthestPointSamplingXYZ.apply
 
 
+def furthest_point_sample_segments(points, counts, nsamples):
+    """FPS of many point sets of different sizes in one launch -- the per-object loop of ObjectBalanceSampling
+    (TrainModel/modules.py:186-213).  points [total,3] f32 CUDA = the sets back to back; counts / nsamples = per-set sizes
+    and sample counts (host sequences).  Returns the concatenated set-local indices ([sum(nsamples)] i32), each set sampled
+    exactly as furthest_point_sample(set.unsqueeze(0), k)[0] samples it."""
+    counts, nsamples = [int(c) for c in counts], [int(k) for k in nsamples]
+    assert len(counts) == len(nsamples)
+    rows, first, slot = [], 0, 0
+    for c, k in zip(counts, nsamples):
+        rows.append((first, c, k, slot))
+        first += c
+        slot += k
+    assert first <= points.shape[0]
+    seg = torch.tensor(rows, dtype=torch.int32).reshape(-1, 4).to(points.device)
+    return _ext.furthest_point_sampling_segments(points, seg, max(counts, default=0), max(nsamples, default=0), slot)
+
+
 class GatherOperation(Function):
     @staticmethod
     def forward(ctx, features, idx):

@@ -54,6 +54,14 @@ GB_API int gb_fps(const float *xyz, float *temp, int *idx, int b, int n, int m, 
 GB_API int gb_fps_xyz(const float *xyz, float *temp, int *idx, float *new_xyz, int b, int n, int m, int variant,
                gb_stream_t stream);
 
+/* Segmented FPS: nseg independent point sets of different sizes packed in one array, one launch -- the per-object loop of
+ * ObjectBalanceSampling (TrainModel/modules.py:186-213 calls furthest_point_sample once per object of every scene).
+ * seg [nseg,4] i32 on the DEVICE (16-byte aligned) = (first point, points, samples, first output slot) per segment; idx and
+ * the optional new_xyz are indexed by output slot; indices are segment-local and bit-identical to gb_fps on the segment
+ * alone.  max_n / max_m = the largest `points` / `samples` entry; segments of more than 10240 points are refused. */
+GB_API int gb_fps_segments(const float *xyz, const int *seg, int *idx, float *new_xyz, int nseg, int max_n, int max_m, int variant,
+                    gb_stream_t stream);
+
 /* A: gather_points_kernel_wrapper (sampling_gpu.cu:27-35); B: gather_points_kernel_launcher_fast (:21-34).
  * points [b,c,n], idx [b,m] -> out [b,c,m]. */
 GB_API int gb_gather_fwd(const float *points, const int *idx, float *out, int b, int c, int n, int m, gb_stream_t stream);

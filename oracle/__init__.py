@@ -93,6 +93,18 @@ def gather_operation_grad(grad_out, idx, N):
     return out
 
 
+def furthest_point_sample_segments(points, counts, nsamples, variant="A"):
+    """The per-object FPS loop of ObjectBalanceSampling (TrainModel/modules.py:201-209): one furthest_point_sample call per
+    point set; returns the concatenated set-local indices."""
+    points = _f32(points)
+    out, first = [], 0
+    for c, k in zip(counts, nsamples):
+        if k > 0:
+            out.append(furthest_point_sample(points[None, first:first + c], k, variant)[0] if c > 0 else np.zeros(k, np.int32))
+        first += c
+    return np.concatenate(out) if out else np.zeros(0, np.int32)
+
+
 def ball_query(radius, nsample, xyz, new_xyz):
     xyz, new_xyz = _f32(xyz), _f32(new_xyz)
     B, N, _ = xyz.shape

@@ -353,6 +353,87 @@ def test_fps_xyz_is_fps_plus_gather(dev, B, N, m):
         np.testing.assert_array_equal(inds.cpu().numpy(), oracle.furthest_point_sample(xyz_np, m, "A"))
 
 
+def test_fps_segments_match_one_call_per_segment(dev):
+    """gb_fps_segments == furthest_point_sample on every segment alone (the per-object loop of ObjectBalanceSampling,
+    TrainModel/modules.py:201-209): sizes from 1 to 9000 points, more samples than points, duplicated points (ties),
+    points near the origin (variant A's norm skip), an empty segment."""
+    rng = np.random.default_rng(7)
+    counts = [1, 2, 33, 700, 512, 513, 4096, 9000, 0, 257, 64, 3000]
+    ks = [1, 5, 33, 128, 512, 100, 341, 343, 0, 300, 64, 1]
+    parts = []
+    for c in counts:
+        p = rng.uniform(-0.3, 0.3, (c, 3)).astype(np.float32) + np.array([0, 0, 0.5], np.float32)
+        if c >= 64:
+            p[c // 2:c // 2 + 16] = p[:16]          # exact duplicates: equal distances, the tie rule decides
+        if c == 700:
+            p[100:110] = rng.uniform(-0.01, 0.01, (10, 3)).astype(np.float32)  # |p|^2 <= 1e-3: skipped by variant A
+        parts.append(p)
+    packed = np.concatenate(parts)
+    got = pu.furthest_point_sample_segments(T(packed, dev), counts, ks).cpu().numpy()
+    want = oracle.furthest_point_sample_segments(packed, counts, ks)
+    np.testing.assert_array_equal(got, want)
+    first = slot = 0
+    for c, k in zip(counts, ks):  # and against the product's own single-cloud entry point
+        if c > 0 and k > 0:
+            alone = pu.furthest_point_sample(T(packed[None, first:first + c], dev), k)[0].cpu().numpy()
+            np.testing.assert_array_equal(got[slot:slot + k], alone)
+        first += c
+        slot += k
+    with pytest.raises(RuntimeError):  # a segment that does not fit the registers of one CTA is refused, not mis-sampled
+        pu.furthest_point_sample_segments(T(np.zeros((20000, 3), np.float32), dev), [20000], [8])
+
+
+def reference_object_balance_sampling(end_points):
+    """TrainModel/modules.py:177-223, literally, on top of the product's single-cloud furthest_point_sample."""
+    batch_seg_res = end_points["seed_cluster"]
+    batch_points = end_points["point_clouds"]
+    batch_features = end_points["up_sample_features"].permute(0, 2, 1)
+    B, N = batch_seg_res.shape
+    new_xyz, new_feat, new_inds = [], [], []
+    for i in range(B):
+        seg_res, points, features = batch_seg_res[i], batch_points[i], batch_features[i]
+        idxs = torch.unique(seg_res)
+        num_objects = len(idxs) - 1
+        per = [1024 // num_objects for _ in range(num_objects)]
+        per[-1] += 1024 % num_objects
+        li, lp, lf, t = [], [], [], 0
+        for j in idxs:
+            if j == 0:
+                continue
+            inds = torch.where(seg_res == j)[0]
+            object_points = points[seg_res == j]
+            sample = pu.furthest_point_sample(object_points.unsqueeze(0).contiguous(), per[t])[0].long()
+            t += 1
+            sel = torch.gather(inds, 0, sample)
+            li.append(sel)
+            lp.append(torch.gather(points, 0, sel.unsqueeze(1).expand(-1, 3)))
+            lf.append(torch.gather(features, 0, sel.unsqueeze(1).expand(-1, features.shape[1])))
+        new_inds.append(torch.cat(li, 0)); new_xyz.append(torch.cat(lp, 0)); new_feat.append(torch.cat(lf, 0))
+    return torch.stack(new_inds, 0).int(), torch.stack(new_xyz, 0), torch.stack(new_feat, 0).permute(0, 2, 1)
+
+
+def test_object_balance_sampling_matches_the_reference_loop(dev):
+    from graspbalance_b200.modules import ObjectBalanceSampling
+    B, N, C = 3, 20000, 32
+    rng = np.random.default_rng(11)
+    xyz = scenes.scene_batch(range(B), N, "tabletop")
+    labels = np.zeros((B, N), np.int64)
+    for b in range(B):  # 3..7 "objects": nearest of a few random centres within 8 cm, everything else background
+        nobj = 3 + 2 * b
+        centres = xyz[b, rng.choice(N, nobj, replace=False)]
+        d = np.linalg.norm(xyz[b][:, None] - centres[None], axis=-1)
+        near = d.min(1) < 0.08
+        labels[b, near] = d.argmin(1)[near] + 1 + b  # label values differ between scenes
+    ep = {"seed_cluster": T(labels, dev), "point_clouds": T(xyz, dev), "up_sample_features": T(rng.normal(size=(B, C, N)).astype(np.float32), dev),
+          "fp2_inds": torch.zeros((B, 1024), dtype=torch.int32, device=dev)}
+    want_inds, want_xyz, want_feat = reference_object_balance_sampling(ep)
+    out = ObjectBalanceSampling(dict(ep))
+    assert torch.equal(out["fp2_inds"], want_inds) and out["fp2_inds"].dtype == torch.int32
+    assert torch.equal(out["fp2_xyz"], want_xyz)
+    assert torch.equal(out["fp2_features"], want_feat)
+    assert out["fp2_inds_fps"] is ep["fp2_inds"]
+
+
 # ------------------------------------------------------------------------------------------- three_nn / interpolate
 @pytest.mark.parametrize("B,n,m", [(2, 20000, 1024), (1, 513, 2), (2, 1000, 3), (1, 64, 1), (2, 4000, 2500)])
 def test_three_nn_vs_oracle(dev, B, n, m):
