@@ -6,5 +6,5 @@ CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-overla
 $CMD > gpurun_out/${TAG}_plain.log 2>&1 && \
 ncu --set full --clock-control none --profile-from-start off \
     -k regex:'seg_dense_kernel|group_fwd_kernel|fps_cluster_kernel|grid_query_kernel|interp_fwd_kernel' \
-    -c 36 -o gpurun_out/${TAG} $CMD > gpurun_out/${TAG}_ncu.log 2>&1
+    -c 30 -o gpurun_out/${TAG} $CMD > gpurun_out/${TAG}_ncu.log 2>&1
 echo "rc=$?"
