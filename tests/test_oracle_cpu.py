@@ -193,3 +193,36 @@ def test_voxel_down_sample_restatement():
         assert np.abs(out - mean).sum(1).min() < 1e-12
     from graspbalance_b200.collision_detector import voxel_down_sample as product_vds
     np.testing.assert_array_equal(product_vds(pts, 0.02), out)
+
+
+# ---- the composite operations of the callers above the hot path: restated as the reference's own loops -----
+def test_composite_oracles_are_the_reference_loops():
+    """cylinder_query_multi = one cylinder_query per depth (modules.py:104-113); three_nn_weights = three_nn + the weight
+    arithmetic of pointnet2_modules.py:413-416; furthest_point_sample_segments = one FPS per object (modules.py:201-209)."""
+    rng = np.random.default_rng(3)
+    xyz = scenes.scene_batch([1, 2], 1500, "tabletop")
+    q = xyz[:, :40].copy()
+    rot = scenes.viewpoint_rotations(-rng.normal(size=(2, 40, 3)).astype(np.float32), np.zeros((2, 40), np.float32)).reshape(2, 40, 9)
+    depths = [0.01, 0.02, 0.03, 0.04]
+    multi = oracle.cylinder_query_multi(0.05, -0.02, depths, 8, xyz, q, rot)
+    assert multi.shape == (2, 40, 4, 8)
+    for d, h in enumerate(depths):
+        np.testing.assert_array_equal(multi[:, :, d], oracle.cylinder_query(0.05, -0.02, h, 8, xyz, q, rot))
+    # nested cylinders: without truncation (nsample >= all hits) the hits of a shallower depth are hits of the deeper one
+    full = oracle.cylinder_query_multi(0.05, -0.02, depths, 512, xyz, q, rot)
+    assert all(set(full[b, j, 0]) <= set(full[b, j, 3]) or not full[b, j, 0].any() for b in range(2) for j in range(40))
+
+    dist, idx, w = oracle.three_nn_weights(xyz, q)
+    d0, i0 = oracle.three_nn(xyz, q)
+    np.testing.assert_array_equal(idx, i0)
+    np.testing.assert_array_equal(dist, d0)
+    np.testing.assert_allclose(w.sum(-1), 1.0, rtol=0, atol=3e-7)
+    r = 1.0 / (d0.astype(np.float64) + 1e-8)
+    np.testing.assert_allclose(w, r / r.sum(-1, keepdims=True), rtol=2e-6)
+
+    counts, ks = [5, 300, 0, 64], [5, 40, 0, 80]
+    packed = xyz[0, :sum(counts)]
+    got = oracle.furthest_point_sample_segments(packed, counts, ks)
+    assert got.shape == (sum(ks),)
+    np.testing.assert_array_equal(got[5:45], oracle.furthest_point_sample(packed[None, 5:305], 40, "A")[0])
+    np.testing.assert_array_equal(got[45:], oracle.furthest_point_sample(packed[None, 305:369], 80, "A")[0])
