@@ -65,7 +65,7 @@ def furthest_point_sampling(points, nsamples):
     _contig(points, "points"); _is_float(points, "points")
     _need_cuda(points)
     B, N = points.shape[0], points.shape[1]
-    out = torch.zeros((B, int(nsamples)), dtype=torch.int32, device=points.device)
+    out = torch.empty((B, int(nsamples)), dtype=torch.int32, device=points.device)  # every index is written
     _lib.call("gb_fps", points, points.data_ptr(), None, out.data_ptr(), B, N, int(nsamples), 0)
     return out
 

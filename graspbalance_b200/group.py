@@ -123,7 +123,9 @@ class BallQuery(Function):
         assert xyz.is_contiguous()
         B, N, _ = xyz.size()
         npoint = new_xyz.size(1)
-        idx = torch.zeros((B, npoint, nsample), dtype=torch.int32, device=xyz.device)
+        # group.py:136 zero-fills because the reference kernel leaves the slots of an empty neighbourhood untouched; gb_ball_query
+        # writes every slot (zeros when there is no hit), so the fill pass is skipped
+        idx = torch.empty((B, npoint, nsample), dtype=torch.int32, device=xyz.device)
         pointnet2_cuda.ball_query_wrapper(B, N, npoint, radius, nsample, new_xyz, xyz, idx)
         ctx.mark_non_differentiable(idx)
         return idx
