@@ -198,6 +198,28 @@ def cylinder_query_multi(new_xyz, xyz, rot, radius, hmin, hmax_list, nsample):
     return idx
 
 
+def cylinder_query_multi_radius(new_xyz, xyz, rot, radii, hmin, hmax_list, nsample):
+    """The four GraspWidthGrouping modules of graspbalance.py:104-107 (same seeds, rotations, hmin and depths; four radii)
+    in one scan.  Returns idx [R,B,m,D,nsample] i32 with idx[k, :, :, d] == cylinder_query(..., radii[k], hmin, hmax_list[d], ...)."""
+    import ctypes
+    _contig(new_xyz, "new_xyz"); _contig(xyz, "xyz"); _contig(rot, "rot")
+    _is_float(new_xyz, "new_xyz"); _is_float(xyz, "xyz"); _is_float(rot, "rot")
+    if new_xyz.is_cuda:
+        _cuda(xyz, "xyz"); _cuda(rot, "rot")
+    _need_cuda(new_xyz)
+    R, D = len(radii), len(hmax_list)
+    if not (1 <= D <= 4 and 1 <= R <= 4):
+        raise RuntimeError("cylinder_query_multi_radius takes 1 to 4 radii and 1 to 4 depths")
+    B, m = new_xyz.shape[0], new_xyz.shape[1]
+    N = xyz.shape[1]
+    idx = torch.empty((R, B, m, D, int(nsample)), dtype=torch.int32, device=new_xyz.device)
+    rr = (ctypes.c_float * R)(*[float(r) for r in radii])
+    hm = (ctypes.c_float * D)(*[float(h) for h in hmax_list])
+    _lib.call("gb_cylinder_query_multi_radius", new_xyz, new_xyz.data_ptr(), xyz.data_ptr(), rot.data_ptr(), idx.data_ptr(), B, N, m, rr, R,
+              float(hmin), hm, D, int(nsample))
+    return idx
+
+
 def group_points(points, idx):
     """group_points.cpp:21-47.  points [B,C,N], idx [B,npoints,nsample] -> [B,C,npoints,nsample]."""
     _contig(points, "points"); _contig(idx, "idx"); _is_float(points, "points"); _is_int(idx, "idx")

@@ -28,6 +28,8 @@ SIGNATURES = {
     "gb_ball_query": [_vp, _vp, _vp, _i, _i, _i, _f, _i, _vp],
     "gb_cylinder_query": [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _f, _i, _vp],
     "gb_cylinder_query_multi": [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, ctypes.POINTER(ctypes.c_float), _i, _i, _vp],
+    "gb_cylinder_query_multi_radius": [_vp, _vp, _vp, _vp, _i, _i, _i, ctypes.POINTER(ctypes.c_float), _i, _f,
+                                       ctypes.POINTER(ctypes.c_float), _i, _i, _vp],
     "gb_group_fwd": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "gb_group_bwd": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "gb_group_bwd_set": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
@@ -104,6 +106,7 @@ ALGO_BYTES = {
     "gb_ball_query": lambda a: a[3] * (12 * a[4] + 12 * a[5] + 4 * a[5] * a[7]),          # b*(12n + 12m + 4 m ns)
     "gb_cylinder_query": lambda a: a[4] * (12 * a[5] + 48 * a[6] + 4 * a[6] * a[10]),     # b*(12n + 48m + 4 m ns)
     "gb_cylinder_query_multi": lambda a: a[4] * (12 * a[5] + 48 * a[6] + 4 * a[6] * a[10] * a[11]),  # b*(12n + 48m + 4 m nd ns)
+    "gb_cylinder_query_multi_radius": lambda a: a[4] * (12 * a[5] + 48 * a[6] + 4 * a[6] * a[8] * a[11] * a[12]),  # b*(12n+48m+4 m nr nd ns)
     "gb_group_fwd": lambda a: a[3] * (4 * a[4] * a[5] + 4 * a[6] * a[7] + 4 * a[4] * a[6] * a[7]),
     "gb_group_bwd": lambda a: a[3] * (4 * a[4] * a[5] + 4 * a[6] * a[7] + 4 * a[4] * a[6] * a[7]),
     "gb_three_nn": lambda a: a[4] * (12 * a[5] + 12 * a[6] + 24 * a[5]),                  # b*(12n + 12m + 24n)

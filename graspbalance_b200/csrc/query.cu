@@ -28,29 +28,37 @@ namespace gb {
 __device__ __forceinline__ bool ball_hit(float qx, float qy, float qz, float x, float y, float z, float radius2) {
   return sqdist3(qx - x, qy - y, qz - z) < radius2;
 }
+// x_rot and the squared radial distance alone, the same instruction sequences as in cyl_hit (the multi read-out
+// re-derives them per hit)
+__device__ __forceinline__ void cyl_coords(const float (&r)[9], float qx, float qy, float qz, float x, float y, float z, float &xr,
+                                           float &d2) {
+  const float dx = x - qx, dy = y - qy, dz = z - qz;
+  xr = __fmaf_rn(r[6], dz, __fmaf_rn(r[0], dx, __fmul_rn(r[3], dy)));
+  const float yr = __fmaf_rn(r[7], dz, __fmaf_rn(r[1], dx, __fmul_rn(r[4], dy)));
+  const float zr = __fmaf_rn(r[8], dz, __fmaf_rn(r[2], dx, __fmul_rn(r[5], dy)));
+  d2 = __fmaf_rn(yr, yr, __fmul_rn(zr, zr));
+}
+
 // (x_rot, y_rot, z_rot) = (p - q)^T R with the reference's contraction (cylinder_query_gpu.cu:58-66, SASS-checked)
 __device__ __forceinline__ bool cyl_hit(const float (&r)[9], float qx, float qy, float qz, float x, float y, float z, float radius2,
                                         float hmin, float hmax) {
-  const float dx = x - qx, dy = y - qy, dz = z - qz;
-  const float xr = __fmaf_rn(r[6], dz, __fmaf_rn(r[0], dx, __fmul_rn(r[3], dy)));
-  const float yr = __fmaf_rn(r[7], dz, __fmaf_rn(r[1], dx, __fmul_rn(r[4], dy)));
-  const float zr = __fmaf_rn(r[8], dz, __fmaf_rn(r[2], dx, __fmul_rn(r[5], dy)));
-  const float d2 = __fmaf_rn(yr, yr, __fmul_rn(zr, zr));
+  float xr, d2;
+  cyl_coords(r, qx, qy, qz, x, y, z, xr, d2);
   return (d2 < radius2) && (xr > hmin) && (xr < hmax);
-}
-
-// x_rot alone, the same instruction sequence as in cyl_hit (the multi-depth read-out re-derives it per hit)
-__device__ __forceinline__ float cyl_xrot(const float (&r)[9], float qx, float qy, float qz, float x, float y, float z) {
-  const float dx = x - qx, dy = y - qy, dz = z - qz;
-  return __fmaf_rn(r[6], dz, __fmaf_rn(r[0], dx, __fmul_rn(r[3], dy)));
 }
 
 // Multi-depth cylinder query (the 4-depth loop of GraspWidthGrouping, TrainModel/modules.py:104-113): the cylinders of one
 // call share axis, radius and hmin and differ in hmax only, so they are nested: ONE scan with the largest hmax finds every
 // candidate, and a hit belongs to depth d iff x_rot < hmax[d].  idx is laid out [b, m, nd, nsample].
+// Multi-radius on top (the four GraspWidthGrouping modules of GraspPoseStage2_seed_features_multi_scale.forward,
+// TrainModel/graspbalance.py:104-107, differ in the cylinder radius only): a hit belongs to radius k iff d2 < r2[k], so
+// the scan with the largest radius serves all nr x nd lists.  idx is laid out [nr, b, m, nd, nsample].
 constexpr int kMaxDepths = 4;
 struct HMax4 {
-  float v[kMaxDepths];
+  float v[kMaxDepths];            // hmax of each depth
+  float r2[kMaxDepths];           // radius * radius (fp32 product, as the single-radius launcher computes it) of each radius
+  int nr;                         // number of radii (>= 1)
+  unsigned long long rstride;     // elements of idx between two radii
 };
 
 // ---- uniform cell grid ------------------------------------------------------------------------------------------------
@@ -58,6 +66,7 @@ constexpr int kGridMaxCells = 4096;
 constexpr int kGridMaxDim = 32;
 constexpr int kGridThreads = 1024;
 constexpr int kGridQueryWarps = 8;
+constexpr int kMultiHitCap = 1024;  // records of the per-warp hit buffer of the multi read-out (>= 32 words x 32 bits)
 
 struct __align__(16) GridHeader {
   float ox, oy, oz, inv;      // cell = clamp(floor((p - o) * inv))
@@ -323,60 +332,76 @@ __global__ void __launch_bounds__(kGridQueryWarps * 32, MULTI ? 4 : 5) grid_quer
   __syncwarp();
 
   if (MULTI) {
-    // ---- multi-depth read-out: the bits of a word are classified by depth, then every depth compacts its own bits ----
+    // ---- multi read-out.  Phase A: the set bits of the bitmap (hits of the scan with the largest radius and hmax) are
+    // compacted, in ascending index, into a per-warp buffer of records  index | radius mask << 24 | depth mask << 28
+    // (bit k of the radius mask: d2 < r2[k]; bit d of the depth mask: x_rot < hmax[d]) -- ONE warp prefix sum per 32
+    // bitmap words whatever the number of lists.  Phase B (when the buffer is full, and at the end): every open list
+    // (k, d) sweeps the buffer 32 records at a time and takes those with both of its bits, ballot-compacted.
+    // Lane L keeps the count and the first hit of list L = k * nd + d. ----
     xyz_orig += (size_t)scene * n * 3;
-    int *out = idx + qi * (size_t)nd * nsample;
-    int cntd[kMaxDepths], firstd[kMaxDepths];
-#pragma unroll
-    for (int d = 0; d < kMaxDepths; ++d) cntd[d] = d < nd ? 0 : nsample, firstd[d] = 0;
+    unsigned *hits = s_bm + (size_t)kGridQueryWarps * words + (size_t)warp * kMultiHitCap;
+    const int nr = hm.nr, nlists = nr * nd;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    int mycnt = lane < nlists ? 0 : nsample, myfirst = 0;
+    int hcount = 0;
+    auto flush = [&]() {
+      __syncwarp();
+      for (int L = 0; L < nlists; ++L) {
+        int c = __shfl_sync(0xffffffffu, mycnt, L);
+        if (c >= nsample) continue;
+        const unsigned need = (0x01000000u << (L / nd)) | (0x10000000u << (L % nd));
+        int *out = idx + (size_t)(L / nd) * hm.rstride + (qi * (size_t)nd + (L % nd)) * nsample;
+        int first = __shfl_sync(0xffffffffu, myfirst, L);
+        for (int base = 0; base < hcount && c < nsample; base += 32) {
+          const unsigned rec = base + lane < hcount ? hits[base + lane] : 0u;
+          const bool hit = (rec & need) == need;
+          const unsigned mask = __ballot_sync(0xffffffffu, hit);
+          if (!mask) continue;
+          if (c == 0) first = (int)(__shfl_sync(0xffffffffu, rec, __ffs(mask) - 1) & 0xFFFFFFu);
+          const int slot = c + __popc(mask & lt_mask);
+          if (hit && slot < nsample) out[slot] = (int)(rec & 0xFFFFFFu);
+          c += __popc(mask);
+        }
+        if (lane == L) mycnt = c, myfirst = first;
+      }
+      hcount = 0;
+      __syncwarp();
+    };
     for (int wb = 0; wb < words; wb += 32) {
-      bool open = false;
-#pragma unroll
-      for (int d = 0; d < kMaxDepths; ++d) open |= cntd[d] < nsample;
-      if (!open) break;
+      if (!__ballot_sync(0xffffffffu, mycnt < nsample)) break;  // every list is full
       const unsigned w = wb + lane < words ? bm[wb + lane] : 0u;
       if (!__ballot_sync(0xffffffffu, w != 0u)) continue;
-      unsigned wd[kMaxDepths] = {0u, 0u, 0u, 0u};
+      const int pc = __popc(w);
+      int incl = pc;
+#pragma unroll
+      for (int dd = 1; dd < 32; dd <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, incl, dd);
+        if (lane >= dd) incl += o;
+      }
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      if (hcount + total > kMultiHitCap) flush();  // total <= 1024 = kMultiHitCap
+      int pos = hcount + incl - pc;
       for (unsigned t = w; t; t &= t - 1) {
         const int bit = __ffs(t) - 1;
-        const size_t k = (size_t)(wb + lane) * 32 + bit;
-        const float xr = cyl_xrot(r, qx, qy, qz, __ldg(xyz_orig + 3 * k), __ldg(xyz_orig + 3 * k + 1), __ldg(xyz_orig + 3 * k + 2));
+        const unsigned k = (unsigned)(wb + lane) * 32u + bit;
+        float xr, d2;
+        cyl_coords(r, qx, qy, qz, __ldg(xyz_orig + 3 * (size_t)k), __ldg(xyz_orig + 3 * (size_t)k + 1), __ldg(xyz_orig + 3 * (size_t)k + 2), xr, d2);
+        unsigned rec = k;
 #pragma unroll
-        for (int d = 0; d < kMaxDepths; ++d)
-          if (xr < hm.v[d]) wd[d] |= 1u << bit;
+        for (int e = 0; e < kMaxDepths; ++e) {
+          if (e < nr && d2 < hm.r2[e]) rec |= 0x01000000u << e;
+          if (e < nd && xr < hm.v[e]) rec |= 0x10000000u << e;
+        }
+        hits[pos++] = rec;
       }
-#pragma unroll
-      for (int d = 0; d < kMaxDepths; ++d) {
-        if (cntd[d] >= nsample) continue;  // warp uniform
-        unsigned x = wd[d];
-        const unsigned any = __ballot_sync(0xffffffffu, x != 0u);
-        if (!any) continue;
-        const int pc = __popc(x);
-        int incl = pc;
-#pragma unroll
-        for (int dd = 1; dd < 32; dd <<= 1) {
-          const int o = __shfl_up_sync(0xffffffffu, incl, dd);
-          if (lane >= dd) incl += o;
-        }
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        if (cntd[d] == 0) {
-          const int l0 = __ffs(any) - 1;
-          const unsigned w0 = __shfl_sync(0xffffffffu, x, l0);
-          firstd[d] = (wb + l0) * 32 + __ffs(w0) - 1;
-        }
-        int pos = cntd[d] + incl - pc;
-        while (x && pos < nsample) {
-          const int bit = __ffs(x) - 1;
-          out[d * nsample + pos++] = (wb + lane) * 32 + bit;
-          x &= x - 1;
-        }
-        cntd[d] += total;
-      }
+      hcount += total;
     }
-#pragma unroll
-    for (int d = 0; d < kMaxDepths; ++d)
-      if (d < nd)
-        for (int sl = min(cntd[d], nsample) + lane; sl < nsample; sl += 32) out[d * nsample + sl] = firstd[d];
+    flush();
+    for (int L = 0; L < nlists; ++L) {  // padding: the first hit (zeros when the list is empty)
+      const int c = min(__shfl_sync(0xffffffffu, mycnt, L), nsample), f = __shfl_sync(0xffffffffu, myfirst, L);
+      int *out = idx + (size_t)(L / nd) * hm.rstride + (qi * (size_t)nd + (L % nd)) * nsample;
+      for (int sl = c + lane; sl < nsample; sl += 32) out[sl] = f;
+    }
     return;
   }
 
@@ -537,7 +562,8 @@ __global__ void __launch_bounds__(kQueryWarps * 32) query_kernel(const float *__
 // largest of them, idx [b, m, nd, nsample].
 template <bool CYL, bool MULTI = false>
 static int launch_query(const float *new_xyz, const float *xyz, const float *rot, int *idx, int b, int n, int m, float radius,
-                        float hmin, float hmax, int nsample, cudaStream_t s, HMax4 hm = HMax4{{0.f, 0.f, 0.f, 0.f}}, int nd = 0) {
+                        float hmin, float hmax, int nsample, cudaStream_t s, HMax4 hm = HMax4{{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}, 1, 0ull},
+                        int nd = 0) {
   if (b < 0 || n <= 0 || m < 0 || nsample <= 0) return (int)cudaErrorInvalidValue;
   if (b == 0 || m == 0) return 0;  // nothing to do (empty tensors have null data pointers)
   if (!new_xyz || !xyz || !idx || (CYL && !rot)) return (int)cudaErrorInvalidValue;
@@ -552,7 +578,8 @@ static int launch_query(const float *new_xyz, const float *xyz, const float *rot
   // the grid pays for its build (one CTA per scene, ~30 us) from ~4M candidate tests per scene on (B200, 32 scenes:
   // n = m = 2048 113 us vs 165 us full scan; n = 2048, m = 1024 79 vs 62; n = m = 1024 85 vs 34)
   const bool grid_worth = n >= 4096 || (n >= 2048 && (long long)m * n >= (1LL << 22));
-  if (g_tuning.query_mode != 1 && (grid_worth || g_tuning.query_mode == 2) && (size_t)words * kGridQueryWarps * 4 <= 96u * 1024u) {
+  if (g_tuning.query_mode != 1 && (grid_worth || g_tuning.query_mode == 2) && (size_t)words * kGridQueryWarps * 4 <= 96u * 1024u &&
+      (!MULTI || n < (1 << 24))) {  // the multi read-out packs a point index in 24 bits
     const size_t sorted_bytes = (size_t)b * n * sizeof(float4);
     const size_t cells_bytes = (((size_t)b * (kGridMaxCells + 1) * sizeof(int)) + 15) & ~(size_t)15;
     cudaError_t e = scratch_alloc(&scratch, sorted_bytes + cells_bytes + (size_t)b * sizeof(GridHeader), s);
@@ -570,7 +597,7 @@ static int launch_query(const float *new_xyz, const float *xyz, const float *rot
     const float cell_frac = g_tuning.grid_cell_pct > 0 ? 0.01f * g_tuning.grid_cell_pct : 0.5f;
     grid_build_kernel<<<b, kGridThreads, 0, s>>>(xyz, n, reachf, g_tuning.query_mode == 2 ? 1 : 0, cell_frac, sorted, cell_start, hdr);
     count_launch();
-    const size_t smem = (size_t)words * kGridQueryWarps * sizeof(unsigned);
+    const size_t smem = ((size_t)words + (MULTI ? kMultiHitCap : 0)) * kGridQueryWarps * sizeof(unsigned);
     auto kern = grid_query_kernel<CYL, MULTI>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
@@ -583,10 +610,14 @@ static int launch_query(const float *new_xyz, const float *xyz, const float *rot
     count_launch();
   }
   if (MULTI) {
+    // scenes the grid declined (and small clouds): the full scan, the nd depths of a query as the slots of one warp, once
+    // per radius
     dim3 grid((m + kQueryWarps - 1) / kQueryWarps, b);
-    query_kernel<CYL, kMaxDepths, true><<<grid, kQueryWarps * 32, 0, s>>>(new_xyz, xyz, rot, idx, n, m, radius2, hmin, hmax, nsample, use_bulk,
-                                                                           hdr, hm, nd);
-    count_launch();
+    for (int kr = 0; kr < hm.nr; ++kr) {
+      query_kernel<CYL, kMaxDepths, true><<<grid, kQueryWarps * 32, 0, s>>>(new_xyz, xyz, rot, idx + (size_t)kr * hm.rstride, n, m, hm.r2[kr],
+                                                                             hmin, hmax, nsample, use_bulk, hdr, hm, nd);
+      count_launch();
+    }
     const int rc = finish_launch();
     if (scratch) cudaFreeAsync(scratch, s);
     return rc;
@@ -621,17 +652,31 @@ extern "C" int gb_cylinder_query(const float *new_xyz, const float *xyz, const f
   return gb::launch_query<true>(new_xyz, xyz, rot, idx, b, n, m, radius, hmin, hmax, nsample, (cudaStream_t)stream);
 }
 
-/* Multi-depth cylinder query: nd (1..4) nested cylinders per seed that differ in hmax only -- the loop over hmax_list of
- * GraspWidthGrouping.forward (TrainModel/modules.py:104-113), which calls cylinder_query once per depth.  One scan;
- * idx [b, m, nd, nsample]: idx[:, :, d, :] is bit-identical to gb_cylinder_query(..., hmax[d], ...). */
-extern "C" int gb_cylinder_query_multi(const float *new_xyz, const float *xyz, const float *rot, int *idx, int b, int n, int m,
-                                       float radius, float hmin, const float *hmax, int ndepth, int nsample, gb_stream_t stream) {
-  if (!hmax || ndepth < 1 || ndepth > gb::kMaxDepths) return (int)cudaErrorInvalidValue;
+/* Multi-depth / multi-radius cylinder query.  The loop over hmax_list of GraspWidthGrouping.forward (TrainModel/modules.py:
+ * 104-113) calls cylinder_query once per depth, and GraspPoseStage2_seed_features_multi_scale.forward (TrainModel/
+ * graspbalance.py:104-107) calls four such modules that differ in the radius only: nradii x ndepth (1..4 each) nested
+ * cylinders per seed, ONE scan.  idx [nradii, b, m, ndepth, nsample]: idx[k, :, :, d, :] is bit-identical to
+ * gb_cylinder_query(..., radii[k], hmin, hmax[d], ...).  radii / hmax are HOST arrays. */
+extern "C" int gb_cylinder_query_multi_radius(const float *new_xyz, const float *xyz, const float *rot, int *idx, int b, int n, int m,
+                                              const float *radii, int nradii, float hmin, const float *hmax, int ndepth, int nsample,
+                                              gb_stream_t stream) {
+  if (!hmax || !radii || ndepth < 1 || ndepth > gb::kMaxDepths || nradii < 1 || nradii > gb::kMaxDepths) return (int)cudaErrorInvalidValue;
   gb::HMax4 hm;
-  float top = hmax[0];  // the largest non-NaN depth bounds the scan; a NaN depth matches nothing (x_rot < NaN is false)
+  float top = hmax[0];   // the largest non-NaN depth bounds the scan; a NaN depth matches nothing (x_rot < NaN is false)
+  float rtop = 0.f;      // the radius with the largest fp32 square bounds it radially (a NaN radius matches nothing)
   for (int d = 0; d < gb::kMaxDepths; ++d) {
     hm.v[d] = hmax[d < ndepth ? d : 0];
     if (d < ndepth && hmax[d] == hmax[d] && (top != top || hmax[d] > top)) top = hmax[d];
+    const float rk = radii[d < nradii ? d : 0];
+    hm.r2[d] = rk * rk;  // fp32 product, as the single-radius launcher computes radius2
+    if (d < nradii && rk == rk && fabsf(rk) > fabsf(rtop)) rtop = rk;
   }
-  return gb::launch_query<true, true>(new_xyz, xyz, rot, idx, b, n, m, radius, hmin, top, nsample, (cudaStream_t)stream, hm, ndepth);
+  hm.nr = nradii;
+  hm.rstride = (unsigned long long)b * m * ndepth * nsample;
+  return gb::launch_query<true, true>(new_xyz, xyz, rot, idx, b, n, m, rtop, hmin, top, nsample, (cudaStream_t)stream, hm, ndepth);
+}
+
+extern "C" int gb_cylinder_query_multi(const float *new_xyz, const float *xyz, const float *rot, int *idx, int b, int n, int m,
+                                       float radius, float hmin, const float *hmax, int ndepth, int nsample, gb_stream_t stream) {
+  return gb_cylinder_query_multi_radius(new_xyz, xyz, rot, idx, b, n, m, &radius, 1, hmin, hmax, ndepth, nsample, stream);
 }

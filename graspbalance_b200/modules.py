@@ -55,6 +55,24 @@ class GraspWidthGrouping(nn.Module):
         return vp_features.view(B, -1, num_seed, len(self.hmax_list))
 
 
+def multi_scale_group(width_groups, seed_xyz, pointcloud, vp_rot):
+    """The grouped coordinates of several GraspWidthGrouping modules that see the same inputs -- WidthGroup1..4 of
+    GraspPoseStage2_seed_features_multi_scale.forward (TrainModel/graspbalance.py:104-107), which differ in the cylinder radius
+    only.  One scan of the cloud with the largest radius serves all radii x depths (gb_cylinder_query_multi_radius), then one
+    grouped-coordinate launch per module.  Returns [m.group(seed_xyz, pointcloud, vp_rot) for m in width_groups], bit for bit."""
+    g0 = width_groups[0]
+    same = all(m.hmin == g0.hmin and m.hmax_list == g0.hmax_list and m.nsample == g0.nsample for m in width_groups)
+    D, R = len(g0.hmax_list), len(width_groups)
+    if not (same and 1 <= D <= 4 and 2 <= R <= 4 and pu._fusable(pointcloud, seed_xyz, vp_rot)):
+        return [m.group(seed_xyz, pointcloud, vp_rot) for m in width_groups]
+    B, num_seed = vp_rot.shape[0], vp_rot.shape[1]
+    rot = vp_rot.reshape(B, num_seed, 9)
+    idx = pu.cylinder_query_multi_radius([m.cylinder_radius for m in width_groups], g0.hmin, g0.hmax_list, g0.nsample, pointcloud,
+                                         seed_xyz, rot)
+    return [pu._FusedQueryGroup.apply(pointcloud, seed_xyz, idx[k].view(B, num_seed, D * g0.nsample), rot, None, None)
+            .view(B, 3, num_seed * D, g0.nsample) for k in range(R)]
+
+
 def ObjectBalanceSampling(end_points, num_seed=1024):
     """TrainModel/modules.py:177-223: every segmented object of a scene contributes num_seed // num_objects seeds (the last
     one takes the remainder), chosen by FPS among the object's points; the seeds' indices, coordinates and up-sampled

@@ -28,7 +28,7 @@ import torch
 from . import group as gb_group
 from . import pointnet2_utils as pu
 from .collision_detector import collision_counts
-from .modules import GraspWidthGrouping
+from .modules import GraspWidthGrouping, multi_scale_group
 
 # (npoint, radius, nsample, C_in) of the four SA modules and (blocks, C, radius, nsample) of the InvResMLP groups
 SA_SPECS = [(2048, 0.04, 64, 0), (1024, 0.1, 32, 128), (512, 0.2, 16, 256), (256, 0.3, 16, 256)]
@@ -93,10 +93,11 @@ class OpPipeline:
     def _crops(self, xyz, view_rot, sa2_xyz, out):
         # ---- grasp crop: 4 radii x 4 depths cylinder query + group (seeds = fp2_xyz: 1024 points, drp.py:301-303) ----
         parts = []  # small slices: the checksum only gives the step a result to return
-        for mod in self.crop_modules:
-            if self.fused_crops:
-                parts.append(mod.group(sa2_xyz, xyz, view_rot)[:, :, :16])  # [B,3,1024*4,64] -> seeds 0..3 x 4 depths
-            else:
+        if self.fused_crops:
+            # WidthGroup1..4 of graspbalance.py:104-107 differ in the radius only: one scan for all 4 x 4 cylinders
+            parts = [g[:, :, :16] for g in multi_scale_group(self.crop_modules, sa2_xyz, xyz, view_rot)]  # seeds 0..3 x 4 depths
+        else:
+            for mod in self.crop_modules:
                 parts += [gq(xyz, sa2_xyz, view_rot)[:, :, :4] for gq in mod.groupers]  # 4 x [B,3,1024,64]
         out["crop_checksum"] = torch.cat([p.reshape(-1) for p in parts]).sum()
 
@@ -230,7 +231,7 @@ def algorithmic_bytes_per_scene(n=20000, backward=True):
         if backward:
             by["interp_bwd"] += 4 * 256 * mm + 24 * nn + 4 * 256 * nn
     # grasp crops: per radius the cloud, seeds and rotations are read once for the four depths
-    by["cylinder_query"] += 4 * (12 * n + 48 * NUM_SEED + 4 * 4 * NUM_SEED * 64)
+    by["cylinder_query"] += 12 * n + 48 * NUM_SEED + 4 * 16 * NUM_SEED * 64  # one scan for the 4 radii x 4 depths
     by["group_fwd"] += 4 * (4 * 3 * n + 4 * 4 * NUM_SEED * 64 + 4 * 3 * 4 * NUM_SEED * 64)
     by["collision"] += 24 * 5000 + 120 * NUM_GRASP + NUM_GRASP
     return by

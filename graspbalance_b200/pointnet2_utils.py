@@ -198,6 +198,25 @@ class CylinderQueryMulti(Function):
 cylinder_query_multi = CylinderQueryMulti.apply
 
 
+class CylinderQueryMultiRadius(Function):
+    """All radii x depths of the four GraspWidthGrouping modules of GraspPoseStage2_seed_features_multi_scale.forward
+    (TrainModel/graspbalance.py:104-107) in one scan: idx [R,B,npoint,D,nsample] with
+    idx[k, :, :, d] == cylinder_query(radii[k], hmin, hmax_list[d], nsample, xyz, new_xyz, rot)."""
+
+    @staticmethod
+    def forward(ctx, radii, hmin, hmax_list, nsample, xyz, new_xyz, rot):
+        idx = _ext.cylinder_query_multi_radius(new_xyz, xyz, rot, list(radii), hmin, list(hmax_list), nsample)
+        ctx.mark_non_differentiable(idx)
+        return idx
+
+    @staticmethod
+    def backward(ctx, a=None):
+        return (None,) * 7
+
+
+cylinder_query_multi_radius = CylinderQueryMultiRadius.apply
+
+
 class RandomDropout(nn.Module):
     """pointnet2_utils.py:35-43.  The reference calls pt_utils.feature_dropout_no_scaling, which its pytorch_utils.py
     does not define; this keeps the constructor and applies an unscaled whole-channel dropout with rate U(0, p)."""

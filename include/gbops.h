@@ -89,6 +89,14 @@ GB_API int gb_cylinder_query(const float *new_xyz, const float *xyz, const float
 GB_API int gb_cylinder_query_multi(const float *new_xyz, const float *xyz, const float *rot, int *idx, int b, int n, int m,
                             float radius, float hmin, const float *hmax, int ndepth, int nsample, gb_stream_t stream);
 
+/* The four GraspWidthGrouping modules of GraspPoseStage2_seed_features_multi_scale.forward (TrainModel/graspbalance.py:
+ * 104-107) see the same seeds, rotations, hmin and depths and differ in the cylinder radius only: nradii x ndepth (1..4
+ * each) nested cylinders per seed in ONE scan.  radii, hmax = HOST arrays.  idx [nradii, b, m, ndepth, nsample] i32:
+ * idx[k, :, :, d, :] is bit-identical to what gb_cylinder_query(..., radii[k], hmin, hmax[d], ...) writes. */
+GB_API int gb_cylinder_query_multi_radius(const float *new_xyz, const float *xyz, const float *rot, int *idx, int b, int n, int m,
+                                   const float *radii, int nradii, float hmin, const float *hmax, int ndepth, int nsample,
+                                   gb_stream_t stream);
+
 /* A: group_points_kernel_wrapper (group_points_gpu.cu:51-65); B: group_points_kernel_launcher_fast (:58-70).
  * points [b,c,n], idx [b,npoints,nsample] -> out [b,c,npoints,nsample]. */
 GB_API int gb_group_fwd(const float *points, const int *idx, float *out, int b, int c, int n, int npoints, int nsample,

@@ -130,6 +130,12 @@ def cylinder_query_multi(radius, hmin, hmax_list, nsample, xyz, new_xyz, rot):
     return np.stack([cylinder_query(radius, hmin, h, nsample, xyz, new_xyz, rot) for h in hmax_list], axis=2)
 
 
+def cylinder_query_multi_radius(radii, hmin, hmax_list, nsample, xyz, new_xyz, rot):
+    """WidthGroup1..4 of GraspPoseStage2_seed_features_multi_scale.forward (TrainModel/graspbalance.py:104-107): one
+    GraspWidthGrouping (= one cylinder_query per depth) per radius; idx [R, B, m, D, nsample]."""
+    return np.stack([cylinder_query_multi(r, hmin, hmax_list, nsample, xyz, new_xyz, rot) for r in radii], axis=0)
+
+
 def grouping_operation(features, idx):
     features, idx = _f32(features), _i32(idx)
     B, C, N = features.shape

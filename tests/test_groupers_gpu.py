@@ -225,3 +225,35 @@ def test_grasp_width_grouping_matches_the_reference_loop(dev, B, N, m, ns):
         assert (got.view(B, 3, m, 4, ns)[:, :, :, d] - want).abs().max().item() <= 1e-6
     out = mod.eval()(q, x, R)
     assert out.shape == (B, 256, m, 4)
+
+
+@pytest.mark.parametrize("B,N,m,ns,radii,hmaxs", [
+    (2, 20000, 128, 64, [0.02, 0.04, 0.06, 0.08], [0.01, 0.02, 0.03, 0.04]),   # the model's four scales x four depths
+    (2, 20000, 48, 16, [0.08, 0.02, 0.05], [0.04, 0.01]),                      # unsorted radii and depths
+    (2, 3000, 40, 16, [0.02, 0.04, 0.06, 0.08], [0.01, 0.02, 0.03, 0.04]),     # full-scan path (n < 4096)
+    (1, 6000, 20, 32, [0.05, 0.05, float("nan"), 0.0], [0.03, float("nan")]),  # duplicate, NaN and zero radii
+    (1, 9000, 16, 64, [0.7, 0.05], [0.01, 0.04]),                              # one radius as large as the scene: the grid declines
+])
+def test_cylinder_query_multi_radius_matches_one_call_per_cylinder(dev, B, N, m, ns, radii, hmaxs):
+    xyz, new_xyz, rot = _crop_inputs(dev, B, N, m, 91)
+    x, q, R = T(xyz, dev), T(new_xyz, dev), T(rot.reshape(B, m, 9), dev)
+    got = pu.cylinder_query_multi_radius(radii, -0.02, hmaxs, ns, x, q, R)
+    assert got.shape == (len(radii), B, m, len(hmaxs), ns) and got.dtype == torch.int32
+    want = oracle.cylinder_query_multi_radius(radii, -0.02, hmaxs, ns, xyz, new_xyz, np.ascontiguousarray(rot.reshape(B, m, 9)))
+    assert np.array_equal(got.cpu().numpy(), want)
+    for k, r in enumerate(radii):
+        for d, h in enumerate(hmaxs):
+            assert torch.equal(got[k, :, :, d], pu.cylinder_query(r, -0.02, h, ns, x, q, R))
+
+
+def test_multi_scale_group_matches_the_four_modules(dev):
+    from graspbalance_b200.modules import GraspWidthGrouping, multi_scale_group
+    torch.backends.cuda.matmul.allow_tf32 = False
+    B, N, m, ns = 2, 20000, 96, 64
+    xyz, new_xyz, rot = _crop_inputs(dev, B, N, m, 95)
+    x, q, R = T(xyz, dev), T(new_xyz, dev), T(rot, dev)
+    mods = [GraspWidthGrouping(ns, 3, cylinder_radius=0.08 * s, hmin=-0.02, hmax_list=[0.01, 0.02, 0.03, 0.04], mlps=torch.nn.Identity())
+            for s in (0.25, 0.5, 0.75, 1.0)]
+    got = multi_scale_group(mods, q, x, R)
+    for g, mod in zip(got, mods):
+        assert torch.equal(g, mod.group(q, x, R))
