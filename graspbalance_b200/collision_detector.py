@@ -10,8 +10,10 @@ The ten half-space thresholds are also evaluated on the host with the reference'
 compares against exactly the doubles numpy would.
 
 `__init__` keeps the reference's voxel down-sampling step: it uses open3d when that package is importable (as the
-reference does, :11-14) and otherwise a numpy restatement of open3d's voxel_down_sample (parity unpinned: open3d is an
-un-vendored third-party dependency of the reference; `detect` does not depend on the point order).
+reference does, :11-14); otherwise the restatement of open3d's voxel_down_sample runs on the GPU (voxel_down_sample_gpu:
+torch sort + gb_voxel_means, same voxel index and the same sequential fp64 means as the numpy restatement
+voxel_down_sample below, which stays for CPU devices).  Parity of this step is unpinned: open3d is an un-vendored
+third-party dependency of the reference; `detect` does not depend on the point order.
 """
 import numpy as np
 import torch
@@ -33,6 +35,30 @@ def voxel_down_sample(points, voxel_size):
     np.add.at(sums, inverse, pts)
     means = sums / np.bincount(inverse, minlength=first.shape[0]).astype(np.float64)[:, None]
     return means[np.argsort(first, kind="stable")]
+
+
+def voxel_down_sample_gpu(points_dev, voxel_size):
+    """voxel_down_sample on the GPU: points_dev [N,3] f64 CUDA -> [V,3] f64 CUDA, the same voxel index and the same
+    sequential fp64 means as the host restatement (voxels come out in key order instead of first-occurrence order; `detect`
+    does not depend on the order).  Keys, stable sort and segment boundaries are torch ops; the ordered per-voxel sums are
+    gb_voxel_means.  Returns None when a voxel coordinate would not fit the 21-bit key fields (the caller falls back)."""
+    pts = points_dev.reshape(-1, 3)
+    if pts.shape[0] == 0:
+        return pts
+    origin = pts.min(dim=0).values - 0.5 * voxel_size
+    cell = torch.floor((pts - origin) / voxel_size).to(torch.int64)
+    if not bool(((cell >= 0) & (cell < (1 << 21))).all()):  # NaN / inf coordinates or an extent of more than 2M voxels
+        return None
+    key = (cell[:, 0] << 42) | (cell[:, 1] << 21) | cell[:, 2]
+    skey, order = torch.sort(key, stable=True)
+    _, counts = torch.unique_consecutive(skey, return_counts=True)
+    V = counts.shape[0]
+    seg = torch.zeros(V + 1, dtype=torch.int64, device=pts.device)
+    torch.cumsum(counts, 0, out=seg[1:])
+    out = torch.empty((V, 3), dtype=torch.float64, device=pts.device)
+    pts = pts.contiguous()
+    _lib.call("gb_voxel_means", pts, pts.data_ptr(), order.data_ptr(), seg.data_ptr(), out.data_ptr(), V)
+    return out
 
 
 def _down_sample(scene_points, voxel_size):
@@ -63,9 +89,23 @@ class ModelFreeCollisionDetector():
         self.finger_width = 0.01
         self.finger_length = 0.06
         self.voxel_size = voxel_size
-        self.scene_points = _down_sample(scene_points, voxel_size)
         self.device = torch.device(device)
-        self._scene_dev = torch.as_tensor(np.ascontiguousarray(self.scene_points, dtype=np.float64)).to(self.device)
+        self._scene_dev = None
+        try:
+            import open3d  # noqa: F401  (the reference's path, collision_detector.py:11-14, when the package exists)
+            have_o3d = True
+        except ImportError:
+            have_o3d = False
+        if not have_o3d and self.device.type == "cuda":
+            # down-sample on the GPU: the cloud goes up once, the voxel means stay there for detect()
+            raw = scene_points if torch.is_tensor(scene_points) else torch.from_numpy(np.ascontiguousarray(scene_points, dtype=np.float64))
+            self._scene_dev = voxel_down_sample_gpu(raw.to(self.device, dtype=torch.float64), voxel_size)
+        if self._scene_dev is not None:
+            self.scene_points = self._scene_dev.cpu().numpy()
+        else:
+            host = scene_points.detach().cpu().numpy() if torch.is_tensor(scene_points) else scene_points
+            self.scene_points = _down_sample(host, voxel_size)
+            self._scene_dev = torch.as_tensor(np.ascontiguousarray(self.scene_points, dtype=np.float64)).to(self.device)
 
     def _thresholds(self, heights, depths, widths, approach_dist):
         fw, fl = self.finger_width, self.finger_length

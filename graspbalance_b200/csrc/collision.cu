@@ -81,6 +81,25 @@ __global__ void __launch_bounds__(kColWarps * 32) collision_kernel(const double 
   }
 }
 
+// Per-voxel means for the voxel down-sampling of ModelFreeCollisionDetector.__init__ (collision_detector.py:11-14, open3d's
+// PointCloud.voxel_down_sample): the points of a voxel, listed in INPUT order, are summed sequentially in fp64 by one
+// thread and divided by their count -- the running sum open3d keeps per voxel, so the means are bit-identical to the host
+// restatement.  order [n] = point indices grouped by voxel (stable sort by voxel key), seg [v+1] = first position of
+// every voxel in `order`.
+__global__ void voxel_means_kernel(const double *__restrict__ points, const long long *__restrict__ order,
+                                   const long long *__restrict__ seg, double *__restrict__ out, int v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= v) return;
+  const long long s0 = seg[i], s1 = seg[i + 1];
+  double sx = 0.0, sy = 0.0, sz = 0.0;
+  for (long long k = s0; k < s1; ++k) {
+    const double *p = points + 3 * order[k];
+    sx = __dadd_rn(sx, p[0]), sy = __dadd_rn(sy, p[1]), sz = __dadd_rn(sz, p[2]);
+  }
+  const double cnt = (double)(s1 - s0);
+  out[3 * (size_t)i] = sx / cnt, out[3 * (size_t)i + 1] = sy / cnt, out[3 * (size_t)i + 2] = sz / cnt;
+}
+
 static int collision_launch(const double *points, int np, const double *T, const double *R, const double *thr, int g, int64_t *counts,
                             cudaStream_t s) {
   cudaError_t e = cudaMemsetAsync(counts, 0, (size_t)g * 6 * sizeof(int64_t), s);
@@ -135,4 +154,17 @@ extern "C" int gb_collision_counts_host(const double *points, int np, const doub
   cudaFree(d);
   cudaStreamDestroy(s);
   return rc;
+}
+
+/* Voxel means for the down-sampling step of ModelFreeCollisionDetector.__init__ (collision_detector.py:11-14): points [n,3]
+ * f64, order [n] i64 = point indices grouped by voxel with the input order kept inside a voxel, seg [v+1] i64 = first
+ * position of every voxel in `order`; out [v,3] f64 = sequential fp64 sum of the voxel's points divided by their count. */
+extern "C" int gb_voxel_means(const double *points, const long long *order, const long long *seg, double *out, int v,
+                              gb_stream_t stream) {
+  if (v < 0) return (int)cudaErrorInvalidValue;
+  if (v == 0) return 0;
+  if (!points || !order || !seg || !out) return (int)cudaErrorInvalidValue;
+  gb::voxel_means_kernel<<<(v + 127) / 128, 128, 0, (cudaStream_t)stream>>>(points, order, seg, out, v);
+  gb::count_launch();
+  return gb::finish_launch();
 }

@@ -174,6 +174,13 @@ GB_API int gb_collision_counts(const double *points, int np, const double *T, co
 GB_API int gb_collision_counts_host(const double *points, int np, const double *T, const double *R, const double *thr, int g,
                              int64_t *counts);
 
+/* The per-voxel means of the voxel down-sampling in ModelFreeCollisionDetector.__init__ (collision_detector.py:11-14, open3d
+ * PointCloud.voxel_down_sample).  points [n,3] f64; order [n] i64 = point indices grouped by voxel, input order
+ * kept inside a voxel; seg [v+1] i64 = first position of every voxel in `order`.  out [v,3] f64 = the sequential fp64 sum
+ * of a voxel's points divided by their count (open3d's running sum), one thread per voxel. */
+GB_API int gb_voxel_means(const double *points, const long long *order, const long long *seg, double *out, int v,
+                   gb_stream_t stream);
+
 /* Tuning knobs for benchmarking sweeps (never change results).  Unknown keys return cudaErrorInvalidValue.
  *   "fps_cluster"  0 = auto, else 1/2/4/8/16 CTAs per scene
  *   "fps_threads"  0 = auto, else 256/512/1024

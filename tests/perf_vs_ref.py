@@ -205,6 +205,21 @@ def main():
         det.detect(gg)
     rows.append({"op": "collision detect() e2e host->host", "us": round((time.perf_counter() - t0) / 5 * 1e6, 1)})
     print(json.dumps(rows[-1]), flush=True)
+    # BASELINE config 1 end to end: constructor (voxel down-sample of the raw 20k-point scene) + detect, host arrays in, mask out
+    from graspbalance_b200.collision_detector import voxel_down_sample
+    for _ in range(2):
+        ModelFreeCollisionDetector(raw, voxel_size=0.01, device=dev).detect(gg)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        ModelFreeCollisionDetector(raw, voxel_size=0.01, device=dev).detect(gg)
+    t_gpu = (time.perf_counter() - t0) / 5
+    t0 = time.perf_counter()
+    for _ in range(3):
+        voxel_down_sample(raw, 0.01)
+    t_np = (time.perf_counter() - t0) / 3
+    rows.append({"op": "collision __init__(20k points, voxel .01) + detect(1024 grasps) e2e", "us": round(t_gpu * 1e6, 1),
+                 "host_numpy_voxel_down_sample_alone_us": round(t_np * 1e6, 1)})
+    print(json.dumps(rows[-1]), flush=True)
 
     if args.sweep:
         for C in (1, 2, 4, 8, 16):

@@ -575,6 +575,26 @@ def test_collision_full_size_vs_oracle(dev):
     assert 0 < got[0].sum() < 1024
 
 
+@pytest.mark.parametrize("n,voxel,kind", [(20000, 0.01, "tabletop"), (20000, 0.005, "tabletop"), (5000, 0.05, "uniform"), (1, 0.01, "uniform"),
+                                           (3000, 1e-4, "uniform")])
+def test_voxel_down_sample_gpu_matches_the_host_restatement(dev, n, voxel, kind):
+    """voxel_down_sample_gpu (torch sort + gb_voxel_means) == the numpy restatement of open3d's voxel_down_sample: the same
+    set of voxel means, bit for bit (sequential fp64 sums in input order); only the order of the voxels differs."""
+    from graspbalance_b200.collision_detector import voxel_down_sample, voxel_down_sample_gpu
+    pts = scenes.scene_batch([9], n, kind)[0].astype(np.float64)
+    pts[n // 2:n // 2 + min(50, n // 3)] = pts[:min(50, n // 3)]  # duplicates share a voxel
+    got = voxel_down_sample_gpu(T(pts, dev), voxel).cpu().numpy()
+    want = voxel_down_sample(pts, voxel)
+    assert got.shape == want.shape
+    key = lambda a: a[np.lexsort((a[:, 2], a[:, 1], a[:, 0]))]
+    np.testing.assert_array_equal(key(got), key(want))
+    np.testing.assert_array_equal(key(want), key(oracle.voxel_down_sample(pts, voxel)))
+    det = ModelFreeCollisionDetector(pts, voxel_size=voxel, device=dev)       # the constructor takes the GPU path ...
+    np.testing.assert_array_equal(key(det.scene_points), key(want))
+    det_t = ModelFreeCollisionDetector(T(pts, dev), voxel_size=voxel, device=dev)  # ... and accepts a tensor already on the device
+    np.testing.assert_array_equal(key(det_t.scene_points), key(want))
+
+
 # ------------------------------------------------------------------------------------------------- sizes at the edges
 def test_empty_inputs_return_empty_outputs(dev):
     """Zero queries / samples / scenes: the entry points return without launching (the reference would launch empty grids)."""

@@ -59,8 +59,10 @@ def main():
     def run(label, fn, want, nbytes):
         nonlocal all_ok
         row = {"op": label}
-        for name, mode in (("index_order", 4), ("degree_sorted", 0)):
+        for name, mode, cc in (("index_order", 4, 0), ("degree_sorted", 0, 0), ("degree_sorted_cc2", 0, 2), ("degree_sorted_cc4", 0, 4),
+                               ("degree_sorted_cc8", 0, 8)):
             _lib.set_tuning("scatter_mode", mode)
+            _lib.set_tuning("scatter_cc", cc)
             got = fn()[:2]
             err = (got.double() - want).abs().max().item()
             ok = err <= 1e-5 * max(want.abs().max().item(), 1.0)
@@ -71,6 +73,7 @@ def main():
             if not ok:
                 row[name + "_ok"] = ok
         _lib.set_tuning("scatter_mode", 0)
+        _lib.set_tuning("scatter_cc", 0)
         rows.append(row)
         print(json.dumps(row), flush=True)
 
