@@ -44,6 +44,7 @@ SIGNATURES = {
     "gb_knn": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "gb_collision_counts": [_vp, _i, _vp, _vp, _vp, _i, _vp, _vp],
     "gb_collision_counts_host": [_vp, _i, _vp, _vp, _vp, _i, _vp],
+    "gb_collision_counts_batched": [_vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp],
     "gb_voxel_means": [_vp, _vp, _vp, _vp, _i, _vp],
     "gb_set_tuning": [ctypes.c_char_p, _i],
     "gb_get_tuning": [ctypes.c_char_p, ctypes.POINTER(ctypes.c_int)],
@@ -121,6 +122,7 @@ ALGO_BYTES = {
     "gb_group_xyz": lambda a: a[5] * (12 * a[6] + 12 * a[7] + (36 * a[7] if a[3] else 0) + 16 * a[7] * a[8]),  # b*(12n+12m(+36m)+(4+12) m ns)
     "gb_knn": lambda a: a[3] * (4 * a[4] * (a[5] + a[6]) + 8 * a[7] * a[6]),              # b*(4d(R+Q) + 8kQ)
     "gb_collision_counts": lambda a: 24 * a[1] + 176 * a[5] + 48 * a[5],
+    "gb_collision_counts_batched": lambda a: a[2] * (24 * a[3] + 176 * a[7] + 48 * a[7]),
     "gb_voxel_means": lambda a: 48 * a[4] * 4 + 24 * a[4],  # ~4 points per voxel read (24 B + 8 B index), 24 B written
 }
 

@@ -84,6 +84,26 @@ def collision_counts(scene_points_dev, T, R, thr):
     return counts
 
 
+def collision_counts_batched(scene_points_list, T, R, thr):
+    """collision_counts for several scenes in one launch: scene_points_list = per-scene [N'_s,3] f64 CUDA
+    tensors; T [S,G,3], R [S,G,3,3], thr [S,G,10] f64 CUDA -> counts [S,G,6] int64.  Row s equals
+    collision_counts(scene_points_list[s], T[s], R[s], thr[s])."""
+    for t, name in ((T, "translations"), (R, "rotation_matrices"), (thr, "thresholds")):
+        if not (t.is_cuda and t.is_contiguous() and t.dtype == torch.float64):
+            raise RuntimeError(f"{name} must be a contiguous float64 CUDA tensor")
+    S, G = T.shape[0], T.shape[1]
+    sizes = [int(p.shape[0]) for p in scene_points_list]
+    assert len(sizes) == S
+    packed = torch.cat([p.reshape(-1, 3) for p in scene_points_list]).contiguous() if S else T.new_zeros((0, 3))
+    if packed.dtype != torch.float64 or not packed.is_cuda:
+        raise RuntimeError("scene_points must be float64 CUDA tensors")
+    off = torch.tensor([0] + list(np.cumsum(sizes)), dtype=torch.int64).to(T.device)
+    counts = torch.empty((S, G, 6), dtype=torch.int64, device=T.device)
+    _lib.call("gb_collision_counts_batched", T, packed.data_ptr(), off.data_ptr(), S, max(sizes, default=0), T.data_ptr(), R.data_ptr(),
+              thr.data_ptr(), G, counts.data_ptr())
+    return counts
+
+
 class ModelFreeCollisionDetector():
     def __init__(self, scene_points, voxel_size=0.005, device="cuda"):
         self.finger_width = 0.01

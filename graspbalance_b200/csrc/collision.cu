@@ -19,9 +19,17 @@ constexpr int kColTile = 1024;  // points per tile: 24 KB
 
 __global__ void __launch_bounds__(kColWarps * 32) collision_kernel(const double *__restrict__ points, int np, const double *__restrict__ T,
                                                                    const double *__restrict__ R, const double *__restrict__ thr, int g,
-                                                                   unsigned long long *__restrict__ counts, int pts_per_split) {
+                                                                   unsigned long long *__restrict__ counts, int pts_per_split,
+                                                                   const long long *__restrict__ scene_off) {
   __shared__ double tile[kColTile * 3];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (scene_off) {  // batched: blockIdx.z = scene; its points are rows scene_off[z] .. scene_off[z+1] of the packed array
+    const long long o0 = scene_off[blockIdx.z];
+    points += 3 * o0;
+    np = (int)(scene_off[blockIdx.z + 1] - o0);
+    const size_t go = (size_t)blockIdx.z * g;
+    T += go * 3, R += go * 9, thr += go * 10, counts += go * 6;
+  }
   const int gi = blockIdx.x * kColWarps + warp;
   const bool gok = gi < g;
   const size_t gs = gok ? gi : 0;
@@ -114,7 +122,7 @@ static int collision_launch(const double *points, int np, const double *T, const
   pps = ((pps + kColTile - 1) / kColTile) * kColTile;
   splits = (np + pps - 1) / pps;
   dim3 grid(gx, splits);
-  collision_kernel<<<grid, kColWarps * 32, 0, s>>>(points, np, T, R, thr, g, reinterpret_cast<unsigned long long *>(counts), pps);
+  collision_kernel<<<grid, kColWarps * 32, 0, s>>>(points, np, T, R, thr, g, reinterpret_cast<unsigned long long *>(counts), pps, nullptr);
   count_launch();
   return finish_launch();
 }
@@ -165,6 +173,33 @@ extern "C" int gb_voxel_means(const double *points, const long long *order, cons
   if (v == 0) return 0;
   if (!points || !order || !seg || !out) return (int)cudaErrorInvalidValue;
   gb::voxel_means_kernel<<<(v + 127) / 128, 128, 0, (cudaStream_t)stream>>>(points, order, seg, out, v);
+  gb::count_launch();
+  return gb::finish_launch();
+}
+
+/* The occupancy test of several scenes in one launch: scene z has the rows scene_off[z] .. scene_off[z+1] of the
+ * packed `points` [sum N', 3] f64 (scene_off: nscenes + 1 i64 on the DEVICE) and g grasps, T [nscenes, g, 3], R [nscenes, g,
+ * 3, 3], thr [nscenes, g, 10]; counts [nscenes, g, 6] i64.  max_np = the largest scene (host knowledge: sizes the grid).
+ * Per scene the counts equal gb_collision_counts on that scene alone. */
+extern "C" int gb_collision_counts_batched(const double *points, const long long *scene_off, int nscenes, int max_np, const double *T,
+                                           const double *R, const double *thr, int g, int64_t *counts, gb_stream_t stream) {
+  if (nscenes < 0 || max_np < 0 || g < 0) return (int)cudaErrorInvalidValue;
+  if (nscenes == 0 || g == 0) return 0;
+  if (!scene_off || !T || !R || !thr || !counts || (max_np > 0 && !points) || nscenes > 65535) return (int)cudaErrorInvalidValue;
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(counts, 0, (size_t)nscenes * g * 6 * sizeof(int64_t), s);
+  if (e != cudaSuccess) return (int)e;
+  if (max_np == 0) return 0;
+  const int gx = (g + gb::kColWarps - 1) / gb::kColWarps;
+  int splits = (4 * gb::num_sms() + gx * nscenes - 1) / (gx * nscenes);
+  const int max_splits = (max_np + gb::kColTile - 1) / gb::kColTile;
+  splits = splits > max_splits ? max_splits : (splits < 1 ? 1 : splits);
+  int pps = (max_np + splits - 1) / splits;
+  pps = ((pps + gb::kColTile - 1) / gb::kColTile) * gb::kColTile;
+  splits = (max_np + pps - 1) / pps;
+  dim3 grid(gx, splits, nscenes);
+  gb::collision_kernel<<<grid, gb::kColWarps * 32, 0, s>>>(points, 0, T, R, thr, g, reinterpret_cast<unsigned long long *>(counts), pps,
+                                                           scene_off);
   gb::count_launch();
   return gb::finish_launch();
 }

@@ -27,7 +27,7 @@ import torch
 
 from . import group as gb_group
 from . import pointnet2_utils as pu
-from .collision_detector import collision_counts
+from .collision_detector import collision_counts, collision_counts_batched
 from .modules import GraspWidthGrouping, multi_scale_group
 
 # (npoint, radius, nsample, C_in) of the four SA modules and (blocks, C, radius, nsample) of the InvResMLP groups
@@ -47,7 +47,7 @@ def _randn(shape, gen, device):
 class OpPipeline:
     """Holds the stand-in feature / gradient tensors (allocated once, outside any timed region) and runs the chain."""
 
-    def __init__(self, batch, n_points=20000, device="cuda", seed=0, backward=True, overlap=True, fused_crops=True, fused_sampling=True):
+    def __init__(self, batch, n_points=20000, device="cuda", seed=0, backward=True, overlap=True, fused_crops=True, fused_sampling=True, batched_collision=True):
         self.B, self.N, self.device, self.backward = batch, n_points, torch.device(device), backward
         # overlap: the sampling chain (4 x FPS + gather: latency-bound, a few warps per SM, depends on xyz only) and the
         # collision tests (independent of everything else) run on side streams next to the bandwidth-bound grouping work
@@ -63,6 +63,7 @@ class OpPipeline:
         self.irm_groupers = [gb_group.QueryAndGroup(r, ns) for (_, _, r, ns) in IRM_SPECS]
         self.fused_crops = fused_crops
         self.fused_sampling = fused_sampling
+        self.batched_collision = batched_collision
         self.crop_modules = [GraspWidthGrouping(64, 3, cylinder_radius=r, hmin=CROP_HMIN, hmax_list=CROP_HMAX, mlps=torch.nn.Identity())
                              for r in CROP_RADII]
         # stand-ins for MLP outputs (features entering each stage) and for upstream gradients
@@ -124,6 +125,8 @@ class OpPipeline:
             return inds, pu.gather_operation(cur.transpose(1, 2).contiguous(), inds).transpose(1, 2).contiguous()
 
         def collide():
+            if self.batched_collision:  # all scenes' occupancy tests in one launch (packed points + offsets)
+                return collision_counts_batched(grasps["scene_points"], grasps["T"], grasps["R"], grasps["thr"])
             return torch.stack([collision_counts(grasps["scene_points"][b], grasps["T"][b], grasps["R"][b], grasps["thr"][b])
                                 for b in range(len(grasps["scene_points"]))])
 

@@ -174,6 +174,12 @@ GB_API int gb_collision_counts(const double *points, int np, const double *T, co
 GB_API int gb_collision_counts_host(const double *points, int np, const double *T, const double *R, const double *thr, int g,
                              int64_t *counts);
 
+/* gb_collision_counts for several scenes in one launch: scene z = rows scene_off[z] .. scene_off[z+1] of the
+ * packed points [sum N', 3] f64 (scene_off: nscenes + 1 i64 on the DEVICE), g grasps per scene: T [nscenes,g,3], R
+ * [nscenes,g,3,3], thr [nscenes,g,10] -> counts [nscenes,g,6] i64.  max_np = the largest scene. */
+GB_API int gb_collision_counts_batched(const double *points, const long long *scene_off, int nscenes, int max_np, const double *T,
+                                const double *R, const double *thr, int g, int64_t *counts, gb_stream_t stream);
+
 /* The per-voxel means of the voxel down-sampling in ModelFreeCollisionDetector.__init__ (collision_detector.py:11-14, open3d
  * PointCloud.voxel_down_sample).  points [n,3] f64; order [n] i64 = point indices grouped by voxel, input order
  * kept inside a voxel; seg [v+1] i64 = first position of every voxel in `order`.  out [v,3] f64 = the sequential fp64 sum

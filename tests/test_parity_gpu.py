@@ -575,6 +575,22 @@ def test_collision_full_size_vs_oracle(dev):
     assert 0 < got[0].sum() < 1024
 
 
+def test_collision_counts_batched_equals_one_launch_per_scene(dev):
+    from graspbalance_b200.collision_detector import collision_counts, collision_counts_batched
+    dets, Ts, Rs, thrs = [], [], [], []
+    for sid, n in ((3, 20000), (4, 6000), (5, 300), (6, 20000)):  # scenes of different sizes after down-sampling
+        det = ModelFreeCollisionDetector(scenes.tabletop_scene(sid, n).astype(np.float64), voxel_size=0.01, device=dev)
+        gs = scenes.grasp_set(sid, det.scene_points, 96)
+        thr = det._thresholds(gs["heights"][:, None], gs["depths"][:, None], gs["widths"][:, None], 0.03)
+        dets.append(det); Ts.append(gs["translations"]); Rs.append(gs["rotation_matrices"]); thrs.append(thr)
+    Td, Rd, thd = (T(np.ascontiguousarray(np.stack(a)), dev) for a in (Ts, Rs, thrs))
+    got = collision_counts_batched([d._scene_dev for d in dets], Td, Rd, thd)
+    assert got.shape == (4, 96, 6)
+    for s_, d in enumerate(dets):
+        assert torch.equal(got[s_], collision_counts(d._scene_dev, Td[s_].contiguous(), Rd[s_].contiguous(), thd[s_].contiguous()))
+    assert int(got[..., 0].sum()) > 0
+
+
 @pytest.mark.parametrize("n,voxel,kind", [(20000, 0.01, "tabletop"), (20000, 0.005, "tabletop"), (5000, 0.05, "uniform"), (1, 0.01, "uniform"),
                                            (3000, 1e-4, "uniform")])
 def test_voxel_down_sample_gpu_matches_the_host_restatement(dev, n, voxel, kind):
