@@ -41,6 +41,9 @@ def main():
             continue
         if re.search(HELPER, d["name"]):
             pending += nbytes
+            if "grid_build" in d["name"]:  # a new query call starts: the full-scan launches behind its grid query belong to it
+                for f in fams.values():
+                    f["_grid_pending"] = False
             continue
         for rx, fam in MAIN:
             if re.search(rx, d["name"]):
@@ -48,7 +51,7 @@ def main():
                 # the full-scan query kernel launched behind a grid query is the same entry-point call
                 if not (fam in ("gb_ball_query", "gb_cylinder_query") and "grid_query" not in d["name"] and f.get("_grid_pending")):
                     f["launches"] += 1
-                f["_grid_pending"] = "grid_query" in d["name"]
+                f["_grid_pending"] = f.get("_grid_pending", False) or "grid_query" in d["name"]
                 f["dram_bytes"] += nbytes + pending
                 pending = 0.0
                 break
