@@ -23,6 +23,7 @@ static int *tuning_slot(const char *key) {
   if (!strcmp(key, "group_split")) return &gb::g_tuning.group_split;
   if (!strcmp(key, "group_mode")) return &gb::g_tuning.group_mode;
   if (!strcmp(key, "group_target_kb")) return &gb::g_tuning.group_target_kb;
+  if (!strcmp(key, "group_ch")) return &gb::g_tuning.group_ch;
   if (!strcmp(key, "interp_mode")) return &gb::g_tuning.interp_mode;
   if (!strcmp(key, "query_qpw")) return &gb::g_tuning.query_qpw;
   if (!strcmp(key, "scatter_cc")) return &gb::g_tuning.scatter_cc;

@@ -41,6 +41,7 @@ struct Tuning {
   int fps_direct = 0;  // 1: CTA-level stage before the cluster exchange even when every warp could push directly
   int group_split = 0;
   int group_mode = 0;  // flags: 1 plain stores, 2 generic kernel, 4 no sorted backward, 8 no single-row TMA kernel, 16 flattened forward split
+  int group_ch = 0;         // forward: channels staged per CTA (multiple of the interleave), 0 = automatic
   int group_target_kb = 0;  // forward: output per CTA of the aligned partition (0 = 512)
   int interp_mode = 0;
   int query_qpw = 0;

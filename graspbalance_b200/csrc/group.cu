@@ -349,7 +349,7 @@ static int launch_group_fwd(const float *points, const int *idx, float *out, int
   const long long pairs = (long long)b * chunks;
   if (!(g_tuning.group_mode & 16) && pairs * 1 <= (1LL << 30)) {
     const long long pair_out_kb = (long long)per4 * 16 * CH / 1024;
-    const long long target_kb = g_tuning.group_target_kb > 0 ? g_tuning.group_target_kb : 384;
+    const long long target_kb = g_tuning.group_target_kb > 0 ? g_tuning.group_target_kb : (smem <= 64u * 1024u ? 512 : 384);
     long long r = (pair_out_kb + target_kb / 2) / target_kb;
     const long long max_r = per4 / min_w > 1 ? per4 / min_w : 1;
     r = r < 1 ? 1 : (r > max_r ? max_r : r);
@@ -411,6 +411,10 @@ static int group_fwd_impl(const float *points, const int *idx, float *out, int b
     CH -= CH % V;
     if (CH > ((c + V - 1) / V) * V) CH = ((c + V - 1) / V) * V;
     if (CH > 64) CH = 64;
+    // short rows (n <= 1024): 16 channels per fill -- more co-resident CTAs and shorter fills beat fewer idx re-reads
+    // (B200, 32 scenes, C = 256: n = 512: 72 -> 59 us, n = 1024: 218 -> 202 us with 512 KB ranges; tests/ubench/fwd_shapes.py)
+    if (row_bytes <= 4096 && CH > 16 && V == 4) CH = 16;
+    if (g_tuning.group_ch > 0 && g_tuning.group_ch % V == 0 && (size_t)g_tuning.group_ch * row_bytes <= big) CH = g_tuning.group_ch;
     if (V == 4) return launch_group_fwd<4>(points, idx, out, b, c, n, per, CH, ostride, s);
     if (V == 2) return launch_group_fwd<2>(points, idx, out, b, c, n, per, CH, ostride, s);
     return launch_group_fwd<1>(points, idx, out, b, c, n, per, CH, ostride, s);

@@ -37,10 +37,9 @@ for (label, n, m, ns, C, r) in (("irm0", 2048, 2048, 64, 128, 0.08), ("irm1", 10
     f = torch.randn((B, C, n), generator=g).to(dev)
     nbytes = B * (4 * C * n + 4 * m * ns + 4 * C * m * ns)
     row = {"op": f"group fwd {label}"}
-    for name, mode, kb in (("flattened", 16, 0), ("aligned512", 0, 512), ("aligned256", 0, 256), ("aligned384", 0, 384), ("aligned768", 0, 768),
-                           ("aligned1024", 0, 1024), ("aligned2048", 0, 2048)):
-        _lib.set_tuning("group_mode", mode); _lib.set_tuning("group_target_kb", kb)
+    for name, ch, kb in (("auto", 0, 0), ("old_ch24_kb384", 24, 384), ("old_ch48_kb384", 48, 384), ("ch16_kb384", 16, 384), ("ch16_kb768", 16, 768)):
+        _lib.set_tuning("group_ch", ch); _lib.set_tuning("group_target_kb", kb)
         us = timeit(lambda: A.group_points(f, idx))
         row[name] = (round(us, 1), round(nbytes / (us * 1e-6) / 1e9 / HBM, 3))
-    _lib.set_tuning("group_mode", 0); _lib.set_tuning("group_target_kb", 0)
+    _lib.set_tuning("group_ch", 0); _lib.set_tuning("group_target_kb", 0)
     print(json.dumps(row), flush=True)
