@@ -9,10 +9,15 @@
 // the whole kernel, so a round touches no global memory at all:
 //   1. every thread updates its P points against the last pick and keeps its best (distance, slot);
 //   2. warp argmax with two redux.sync instructions on integer keys (distance bits, then tie key);
-//   3. warp winners -> shared memory -> one __syncthreads -> every warp reduces them redundantly (no 2nd barrier);
-//   4. (C > 1) the CTA winner is PUSHED into the shared memory of all C CTAs with st.async, which completes a
-//      transaction count on the receiver's mbarrier; every CTA waits on its own mbarrier, reduces the C candidates
-//      and starts the next round.  One DSMEM hop and no cluster barrier per round.
+//   3. DIRECT mode (C > 1, at most 32 warps in the cluster): every warp PUSHES its own winner into the shared memory of
+//      all C CTAs with st.async, which completes a transaction count on the receiver's mbarrier; every warp waits on its
+//      CTA's mbarrier and reduces the <= 32 candidates, one per lane.  One DSMEM hop per round, no cluster barrier, no
+//      __syncthreads, no CTA-level reduction.
+//   3'. otherwise: warp winners -> shared memory -> one __syncthreads -> every warp reduces them redundantly, and (C > 1)
+//      the CTA winner is pushed to all CTAs the same way.
+// The picks are parked in shared memory during the rounds (the loop is latency-critical: a store or an index conversion
+// inside it is paid m - 1 times) and written out once at the end, optionally with their coordinates (gb_fps_xyz).
+// Segmented mode (gb_fps_segments): one CTA per segment of a packed point array, sizes from a device-side table.
 //
 // Bit-exact tie order.  The reference's result is determined by its block size BS = opt_n_threads(n): the per-thread
 // strided scan keeps the first strict maximum and the shared-memory tree keeps the lower slot on ties, i.e. among equal

@@ -11,8 +11,10 @@
 //     point, so that the random gather is one LDS.(32*V) per index instead of V sector-sized L2 reads;
 //   * each thread owns 4 consecutive output positions: one 128-bit load of idx (read once per channel CHUNK, not once
 //     per channel), 4 LDS gathers per channel group, one coalesced 128-bit streaming store per channel;
-//   * the (scene, chunk) x position work space is flattened and cut into equal contiguous ranges, one per resident CTA,
-//     so all 148 SMs finish together whatever the shape.
+//   * large launches: a CTA stages the rows of ONE (scene, chunk) pair and sweeps ~384-512 KB of its output (aligned
+//     partition: one fill per CTA, many short waves that hide each other's fills); small launches: the (scene, chunk) x
+//     position work space is flattened and cut into equal contiguous ranges, one per resident CTA, so all 148 SMs finish
+//     together whatever the shape.
 // Backward is a scatter-add.  With >= 4 channels it runs as the atomic-free sorted segmented sum of scatter.cu; the
 // kernels kept here serve few-channel calls (the xyz rows): coalesced 128-bit reads of grad_out and idx,
 // red.global.add.f32 into the (L2-resident) gradient rows, with WARP-AGGREGATION of runs of equal indices first --

@@ -19,6 +19,10 @@
 // ascending index, exactly the reference's sequential scan.  The per-candidate arithmetic is the same instruction
 // sequence as the full scan, and culling only removes points that cannot pass it, so results stay bit-exact.  When the
 // grid would not cull (radius comparable to the scene) the build kernel says so and the full-scan kernel runs instead.
+//
+// Multi mode (gb_cylinder_query_multi, gb_cylinder_query_multi_radius): the nested cylinders of a grasp crop -- up to four
+// depths (hmax) x four radii around the same seed, axis and hmin -- share ONE scan with the largest radius and depth; every
+// hit is then classified by radius and depth and the up to 16 index lists of the seed are compacted from one hit buffer.
 #include <float.h>
 
 #include "common.cuh"

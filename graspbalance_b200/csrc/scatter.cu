@@ -342,7 +342,8 @@ __global__ void __launch_bounds__(kSegThreads, 1) seg_accum_kernel(const float *
 // interpolation backward with <= 1024 known points), entry-parallel processing spends its time merging runs.  Here the
 // roles flip: a THREAD owns a target (TPT targets when n > 1024) and CT channels for the whole kernel and keeps their sums
 // in REGISTERS; per tile it walks its targets' slices of the sorted entry list and adds the staged source values.  No
-// accumulator in shared memory, no atomics, no run merging; the only barrier releases the stage.
+// accumulator in shared memory, no atomics, no run merging; the only barrier releases the stage.  Which thread owns
+// which target is decided per call from the targets' (sampled) degrees: see seg_perm_kernel.
 //
 // Sort output per tile ("blob", one bulk copy): tp[2048] u16 (tile-local entry of each sorted position) | start[NS] u16
 // (first sorted position of every target, start[n] = number of valid entries; NS = n + 1 rounded up to 8).
