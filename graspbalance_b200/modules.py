@@ -73,6 +73,25 @@ def multi_scale_group(width_groups, seed_xyz, pointcloud, vp_rot):
             .view(B, 3, num_seed * D, g0.nsample) for k in range(R)]
 
 
+def balance_plan(labels, counts, num_seed=1024):
+    """The sampling plan of one scene (modules.py:190-193,199-205): labels = the sorted unique segment labels, counts = their
+    point counts.  Every non-background object t gets num_seed // num_objects seeds, the last one the remainder as well, with
+    num_objects = len(labels) - 1 exactly as upstream (label 0 = background is assumed present).  Returns (first position in
+    the label-sorted point order, points, seeds) per object, in label order.  Host logic only."""
+    num_objects = len(labels) - 1
+    if num_objects <= 0:
+        raise ZeroDivisionError("ObjectBalanceSampling needs at least one object besides the background (as upstream)")
+    per_obj = [num_seed // num_objects] * num_objects
+    per_obj[-1] += num_seed % num_objects
+    plan, start, t = [], 0, 0
+    for lab, c in zip(labels, counts):
+        if lab != 0:
+            plan.append((start, c, per_obj[t]))  # IndexError when label 0 is absent, as upstream
+            t += 1
+        start += c
+    return plan
+
+
 def ObjectBalanceSampling(end_points, num_seed=1024):
     """TrainModel/modules.py:177-223: every segmented object of a scene contributes num_seed // num_objects seeds (the last
     one takes the remainder), chosen by FPS among the object's points; the seeds' indices, coordinates and up-sampled
@@ -87,19 +106,11 @@ def ObjectBalanceSampling(end_points, num_seed=1024):
     packed_src, counts, ks, scene_of_obj = [], [], [], []
     for i in range(B):
         labels, cnt = torch.unique(batch_seg_res[i], return_counts=True)  # sorted labels (one host sync per scene, as upstream)
-        labels, cnt = labels.tolist(), cnt.tolist()
-        num_objects = len(labels) - 1
-        per_obj = [num_seed // num_objects] * num_objects
-        per_obj[-1] += num_seed % num_objects
-        start, t = 0, 0
-        for lab, c in zip(labels, cnt):
-            if lab != 0:
-                packed_src.append(order[i, start:start + c])
-                counts.append(c)
-                ks.append(per_obj[t])
-                scene_of_obj.append(i)
-                t += 1
-            start += c
+        for start, c, k in balance_plan(labels.tolist(), cnt.tolist(), num_seed):
+            packed_src.append(order[i, start:start + c])
+            counts.append(c)
+            ks.append(k)
+            scene_of_obj.append(i)
     src = torch.cat(packed_src)                                         # scene-local index of every packed point
     scene_ids = torch.repeat_interleave(torch.tensor(scene_of_obj, device=src.device), torch.tensor(counts, device=src.device))
     packed_xyz = batch_points[scene_ids, src].contiguous().float()

@@ -58,16 +58,25 @@ def furthest_point_sample_segments(points, counts, nsamples):
     (TrainModel/modules.py:186-213).  points [total,3] f32 CUDA = the sets back to back; counts / nsamples = per-set sizes
     and sample counts (host sequences).  Returns the concatenated set-local indices ([sum(nsamples)] i32), each set sampled
     exactly as furthest_point_sample(set.unsqueeze(0), k)[0] samples it."""
+    rows, total_points, total_out = segment_table(counts, nsamples)
+    assert total_points <= points.shape[0]
+    seg = torch.tensor(rows, dtype=torch.int32).reshape(-1, 4).to(points.device)
+    return _ext.furthest_point_sampling_segments(points, seg, max((r[1] for r in rows), default=0), max((r[2] for r in rows), default=0),
+                                                 total_out)
+
+
+def segment_table(counts, nsamples):
+    """Rows (first point, points, samples, first output slot) of gb_fps_segments for point sets stored back to back; also
+    the number of points and of output slots they span.  Host logic only."""
     counts, nsamples = [int(c) for c in counts], [int(k) for k in nsamples]
-    assert len(counts) == len(nsamples)
+    if len(counts) != len(nsamples) or any(c < 0 for c in counts) or any(k < 0 for k in nsamples):
+        raise ValueError("counts and nsamples must be non-negative sequences of equal length")
     rows, first, slot = [], 0, 0
     for c, k in zip(counts, nsamples):
         rows.append((first, c, k, slot))
         first += c
         slot += k
-    assert first <= points.shape[0]
-    seg = torch.tensor(rows, dtype=torch.int32).reshape(-1, 4).to(points.device)
-    return _ext.furthest_point_sampling_segments(points, seg, max(counts, default=0), max(nsamples, default=0), slot)
+    return rows, first, slot
 
 
 class GatherOperation(Function):

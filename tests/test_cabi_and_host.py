@@ -174,3 +174,22 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["impl"] == "reference" and line["unit"] == "scenes/s" and line["higher_is_better"] is True
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and math.isfinite(line["value"]) and line["value"] > 0
+
+
+def test_segment_table_and_balance_plan_host_logic():
+    """Host logic of the segmented FPS behind ObjectBalanceSampling (TrainModel/modules.py:186-213), no GPU needed."""
+    from graspbalance_b200.modules import balance_plan
+    from graspbalance_b200.pointnet2_utils import segment_table
+    rows, npts, nout = segment_table([5, 0, 300, 64], [5, 0, 40, 80])
+    assert rows == [(0, 5, 5, 0), (5, 0, 0, 5), (5, 300, 40, 5), (305, 64, 80, 45)] and npts == 369 and nout == 125
+    assert segment_table([], []) == ([], 0, 0)
+    with pytest.raises(ValueError):
+        segment_table([1, 2], [1])
+    # labels sorted, 0 = background: 3 objects share 1024 seeds as 341, 341, 342 (modules.py:192-193)
+    plan = balance_plan([0, 2, 5, 9], [12000, 3000, 4000, 1000], 1024)
+    assert plan == [(12000, 3000, 341), (15000, 4000, 341), (19000, 1000, 342)]
+    assert sum(k for _, _, k in balance_plan([0, 1], [10, 90], 1024)) == 1024
+    with pytest.raises(ZeroDivisionError):  # upstream divides by zero objects as well
+        balance_plan([0], [20000], 1024)
+    with pytest.raises(IndexError):  # upstream assumes label 0 exists; without it its per-object list is one short
+        balance_plan([1, 2], [10, 10], 1024)
