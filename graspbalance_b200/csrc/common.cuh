@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "../../include/gbops.h"
 
 #ifndef __CUDA_ARCH__
@@ -14,42 +16,49 @@ namespace gb {
 constexpr int kNumSMsB200 = 148;
 
 // launch bookkeeping -------------------------------------------------------------------------------
-extern unsigned long long g_launch_count;
-inline void count_launch(int n = 1) { g_launch_count += (unsigned long long)n; }
+// Host state is per device and safe to touch from several host threads (autograd runs backward on its own thread; one
+// process may drive all eight GPUs): the counter is atomic, device facts are cached per device, tuning knobs are atomics.
+extern std::atomic<unsigned long long> g_launch_count;
+inline void count_launch(int n = 1) { g_launch_count.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
 inline int finish_launch() {
   cudaError_t e = cudaGetLastError();
   return (int)e;
 }
 
-inline int num_sms() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
-        sms <= 0)
-      sms = kNumSMsB200;
-  }
-  return sms;
+constexpr int kMaxDevices = 64;
+int num_sms();  // of the CURRENT device (api.cu)
+
+// Raise the dynamic shared-memory limit of `kernel` on the current device to the device maximum minus the kernel's static
+// usage -- once per (kernel, device), always to the same value, so concurrent launches never shrink each other's limit --
+// and check that `needed` bytes fit.  Returns a cudaError_t as int.
+int raise_smem_limit(const void *kernel, size_t needed);
+template <class K>
+inline int raise_smem_limit(K kernel, size_t needed) {
+  return raise_smem_limit(reinterpret_cast<const void *>(kernel), needed);
 }
 
 // tuning knobs (host side) ---------------------------------------------------------------------------
 struct Tuning {
-  int fps_cluster = 0;
-  int fps_threads = 0;
-  int fps_defer = 0;   // 1: store every pick to global memory inside the round loop
-  int fps_direct = 0;  // 1: CTA-level stage before the cluster exchange even when every warp could push directly
-  int group_split = 0;
-  int group_mode = 0;  // flags: 1 plain stores, 2 generic kernel, 4 no sorted backward, 8 no single-row TMA kernel, 16 flattened forward split
-  int group_ch = 0;         // forward: channels staged per CTA (multiple of the interleave), 0 = automatic
-  int group_target_kb = 0;  // forward: output per CTA of the aligned partition (0 = 512)
-  int interp_mode = 0;
-  int query_qpw = 0;
-  int scatter_cc = 0;
-  int scatter_nt = 0;  // dense backward: log2 of the target slots per CTA (8..10), 0 = smallest that holds n
-  int scatter_mode = 0;  // bit 0: never use the dense (thread-owned targets) backward; bit 2: targets in index order (no degree sort)
-  int query_mode = 0;  // 1: never use the cell grid, 2: always use it (when the shape allows)
-  int grid_cell_pct = 0;  // cell edge as a percentage of the query reach (0 = default 50)
+  std::atomic<int> fps_cluster{0};
+  std::atomic<int> fps_threads{0};
+  std::atomic<int> fps_defer{0};   // 1: store every pick to global memory inside the round loop
+  std::atomic<int> fps_direct{0};  // 1: CTA-level stage before the cluster exchange even when every warp could push directly
+  std::atomic<int> group_split{0};
+  std::atomic<int> group_mode{0};  // flags: 1 plain stores, 2 generic kernel, 4 no sorted backward, 8 no single-row TMA kernel, 16 flattened forward split
+  std::atomic<int> group_ch{0};         // forward: channels staged per CTA (multiple of the interleave), 0 = automatic
+  std::atomic<int> group_target_kb{0};  // forward: output per CTA of the aligned partition (0 = 512)
+  std::atomic<int> interp_mode{0};
+  std::atomic<int> query_qpw{0};
+  std::atomic<int> scatter_cc{0};
+  std::atomic<int> scatter_nt{0};  // dense backward: log2 of the target slots per CTA (8..10), 0 = smallest that holds n
+  std::atomic<int> scatter_mode{0};  // bit 0: never use the dense (thread-owned targets) backward; bit 2: targets in index order (no degree sort);
+                         // bit 3: never use the warp-private backward; bit 4: use it for any number of tasks
+  std::atomic<int> priv_vl{0};     // warp-private backward: positions per lane and load (1, 2, 4), 0 = automatic
+  std::atomic<int> priv_dry{0};    // experiment: 1 = the warp-private backward only streams its inputs (wrong results)
+  std::atomic<int> priv_cw{0};     // warp-private backward: channels per warp and plane (2, 4), 0 = automatic
+  std::atomic<int> query_mode{0};  // 1: never use the cell grid, 2: always use it (when the shape allows)
+  std::atomic<int> grid_cell_pct{0};  // cell edge as a percentage of the query reach (0 = default 50)
 };
 extern Tuning g_tuning;
 
@@ -60,6 +69,11 @@ cudaError_t scratch_alloc(void **p, size_t bytes, cudaStream_t s);
 bool seg_scatter_supported(int b, int c, int n, size_t entries, int div);
 int seg_scatter_add(const float *src, size_t src_stride, const int *key, const float *weight, float *grad, int b, int c, int n,
                     size_t entries, int div, int overwrite, cudaStream_t s);
+
+// scatter_private.cu: group backward with warp-private shared-memory accumulators (no sort, no atomics)
+bool scatter_private_supported(int b, int c, int n, int npoints, int nsample, size_t src_stride, const float *src, const int *idx);
+int scatter_private(const float *src, size_t src_stride, const int *idx, float *grad, int b, int c, int n, int npoints, int nsample,
+                    int overwrite, cudaStream_t s);
 
 // squared distance exactly as nvcc contracts the reference's (a-b)*(a-b)+(c-d)*(c-d)+(e-f)*(e-f):
 // FMUL on the y term, then FFMA x, then FFMA z (SASS of ball_query_gpu.cu / sampling_gpu.cu / interpolate_gpu.cu).

@@ -311,8 +311,8 @@ static int launch_fps(const float *xyz, float *temp, int *idx, float *new_xyz, i
   // defer mode parks the picks in shared memory (4 bytes each) when they fit beside the coordinate copy
   const int defer = ((size_t)3 * P * T * sizeof(float) + (size_t)m * 4 <= 200u * 1024u && g_tuning.fps_defer != 1) ? 1 : 0;
   const size_t dyn = (size_t)3 * P * T * sizeof(float) + (defer ? (size_t)m * 4 : 0);
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-  if (e != cudaSuccess) return (int)e;
+  if (int rc_ = raise_smem_limit(kern, dyn)) return rc_;
+  cudaError_t e = cudaSuccess;
   if (C > 8) {
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     if (e != cudaSuccess) return (int)e;

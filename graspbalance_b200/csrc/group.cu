@@ -328,8 +328,7 @@ static int launch_group_fwd(const float *points, const int *idx, float *out, int
                             cudaStream_t s) {
   auto kern = group_fwd_kernel<V>;
   const size_t smem = (size_t)CH * n * sizeof(float);
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return (int)e;
+  if (int rc_ = raise_smem_limit(kern, smem)) return rc_;
   const int chunks = (c + CH - 1) / CH;
   const int per4 = (int)(per / 4);
   const long long total = (long long)b * chunks * per4;
@@ -351,7 +350,7 @@ static int launch_group_fwd(const float *points, const int *idx, float *out, int
   const long long pairs = (long long)b * chunks;
   if (!(g_tuning.group_mode & 16) && pairs * 1 <= (1LL << 30)) {
     const long long pair_out_kb = (long long)per4 * 16 * CH / 1024;
-    const long long target_kb = g_tuning.group_target_kb > 0 ? g_tuning.group_target_kb : (smem <= 64u * 1024u ? 512 : 384);
+    const long long target_kb = g_tuning.group_target_kb > 0 ? (int)g_tuning.group_target_kb : (smem <= 64u * 1024u ? 512 : 384);
     long long r = (pair_out_kb + target_kb / 2) / target_kb;
     const long long max_r = per4 / min_w > 1 ? per4 / min_w : 1;
     r = r < 1 ? 1 : (r > max_r ? max_r : r);
@@ -398,8 +397,7 @@ static int group_fwd_impl(const float *points, const int *idx, float *out, int b
     const long long ctas = units < grid ? units : grid;
     const long long upc = (units + ctas - 1) / ctas;
     const size_t smem = 2 * row_bytes;
-    cudaError_t e = cudaFuncSetAttribute(group_fwd_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
+    if (int rc_ = raise_smem_limit(group_fwd_rows_kernel, smem)) return rc_;
     group_fwd_rows_kernel<<<(unsigned)((units + upc - 1) / upc), kGroupThreads, smem, s>>>(points, idx, out, c, n, per4, segs, seg_len4, units,
                                                                                       upc, ostride);
     count_launch();
@@ -448,6 +446,9 @@ static int group_bwd_impl(const float *grad_out, const int *idx, float *grad_poi
   if (b == 0 || c == 0) return 0;
   if (per == 0) return overwrite ? (int)cudaMemsetAsync(grad_points, 0, (size_t)b * c * n * sizeof(float), s) : 0;
 
+  // ---- warp-private accumulators (scatter_private.cu): the backbone's shapes, no sort pass at all ----
+  if (!(g_tuning.group_mode & 4) && scatter_private_supported(b, c, n, npoints, nsample, gstride, grad_out, idx))
+    return scatter_private(grad_out, gstride, idx, grad_points, b, c, n, npoints, nsample, overwrite, s);
   // ---- sorted, atomic-free path (scatter.cu): worth the one-off sort when there are enough channels to amortise it ----
   if (!(g_tuning.group_mode & 4) && gstride % 4 == 0 && seg_scatter_supported(b, c, n, per, 1))
     return seg_scatter_add(grad_out, gstride, idx, nullptr, grad_points, b, c, n, per, 1, overwrite, s);

@@ -142,8 +142,7 @@ extern "C" int gb_three_interp_fwd(const float *points, const int *idx, const fl
     if (CH > ((c + 3) / 4) * 4) CH = ((c + 3) / 4) * 4;
     if (CH > 64) CH = 64;
     const size_t smem = (size_t)CH * row_bytes;
-    cudaError_t e = cudaFuncSetAttribute(interp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
+    if (int rc_ = raise_smem_limit(interp_fwd_kernel, smem)) return rc_;
     const int chunks = (c + CH - 1) / CH;
     const int n4 = n / 4;
     const long long total = (long long)b * chunks * n4;

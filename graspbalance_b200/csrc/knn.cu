@@ -155,8 +155,7 @@ extern "C" int gb_knn(const float *ref, const float *query, int64_t *idx, int b,
   long long *o = reinterpret_cast<long long *>(idx);
 #define GB_KNN_LAUNCH(DT, K1)                                                                                   \
   do {                                                                                                          \
-    cudaError_t e = cudaFuncSetAttribute(knn_kernel<DT, K1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    if (e != cudaSuccess) return (int)e;                                                                        \
+    if (int rc_ = raise_smem_limit(knn_kernel<DT, K1>, smem)) return rc_;                                                                        \
     knn_kernel<DT, K1><<<grid, kKnnWarps * 32, smem, s>>>(ref, query, o, dim, nref, nquery, k, ts);             \
   } while (0)
   if (dim == 3) {

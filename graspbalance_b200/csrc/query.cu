@@ -603,7 +603,7 @@ static int launch_query(const float *new_xyz, const float *xyz, const float *rot
     count_launch();
     const size_t smem = ((size_t)words + (MULTI ? kMultiHitCap : 0)) * kGridQueryWarps * sizeof(unsigned);
     auto kern = grid_query_kernel<CYL, MULTI>;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = (cudaError_t)raise_smem_limit(kern, smem);
     if (e != cudaSuccess) {
       cudaFreeAsync(scratch, s);
       return (int)e;

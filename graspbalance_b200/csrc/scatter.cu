@@ -611,15 +611,15 @@ __global__ void __launch_bounds__(kSegThreads, 1) seg_dense_kernel(const float *
 // stream-ordered scratch from the device's default pool; the pool is told once to keep freed memory instead of
 // returning it to the driver at every synchronisation (the default), which would make every call pay a fresh allocation
 cudaError_t scratch_alloc(void **p, size_t bytes, cudaStream_t s) {
-  static bool configured = false;
-  if (!configured) {
-    int dev = 0;
+  static std::atomic<bool> configured[kMaxDevices];  // per device: one process may drive every GPU of the box
+  int dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < kMaxDevices && !configured[dev].load(std::memory_order_acquire)) {
     cudaMemPool_t pool;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
       unsigned long long keep = ~0ull;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);  // idempotent: a race sets it twice
     }
-    configured = true;
+    configured[dev].store(true, std::memory_order_release);
   }
   return cudaMallocAsync(p, bytes, s);
 }
@@ -637,8 +637,7 @@ static int launch_seg_accum(const float *src, size_t src_stride, const unsigned 
   if (!bulk_ok) stages = 1;
   const size_t smem = acc_bytes + stages * stage_bytes;
   auto kern = seg_accum_kernel<CC, DIV, WEIGHTED>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return (int)e;
+  if (int rc_ = raise_smem_limit(kern, smem)) return rc_;
   const int chunks = (c + CC - 1) / CC;
   kern<<<(unsigned)(b * chunks), kSegThreads, smem, s>>>(src, packed, wsorted, bnd, grad, c, n, per_src, tiles, chunks, stages, bulk_ok,
                                                          overwrite, src_stride);
@@ -659,8 +658,7 @@ static int launch_seg_dense(const float *src, size_t src_stride, const unsigned 
   if (!bulk_ok || stages < 1) stages = 1;
   const size_t smem = stages * stage_bytes;
   auto kern = seg_dense_kernel<CT, TPT, DIV, WEIGHTED, MUL>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return (int)e;
+  if (int rc_ = raise_smem_limit(kern, smem)) return rc_;
   const int chunks = (c + CC - 1) / CC;
   kern<<<(unsigned)(b * chunks), kSegThreads, smem, s>>>(src, blobs, weight, grad, c, n, per_src, tiles, chunks, nt_log2, stages,
                                                          (int)stage_bytes, bulk_ok, overwrite, src_stride, perm);
@@ -799,10 +797,10 @@ int seg_scatter_add(const float *src, size_t src_stride, const int *key, const f
   const size_t sort_smem = ((size_t)n + 32) * sizeof(int) + kSegTileStride * sizeof(unsigned short);
   int rc;
   if (weight) {
-    rc = (int)cudaFuncSetAttribute(seg_sort_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem);
+    rc = raise_smem_limit(seg_sort_kernel<true>, sort_smem);
     if (!rc) seg_sort_kernel<true><<<dim3((unsigned)tiles, b), kSegSortThreads, sort_smem, s>>>(key, weight, (int)entries, n, T, packed, wsorted, bnd);
   } else {
-    rc = (int)cudaFuncSetAttribute(seg_sort_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem);
+    rc = raise_smem_limit(seg_sort_kernel<false>, sort_smem);
     if (!rc) seg_sort_kernel<false><<<dim3((unsigned)tiles, b), kSegSortThreads, sort_smem, s>>>(key, nullptr, (int)entries, n, T, packed, nullptr, bnd);
   }
   if (!rc) {

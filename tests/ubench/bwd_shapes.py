@@ -56,17 +56,24 @@ def main():
     lv0 = torch.gather(xyz, 1, fidx[:, :, None].expand(-1, -1, 3)).contiguous()
     rows, all_ok = [], True
 
-    def run(label, fn, want, nbytes):
+    GROUP_VARIANTS = (("sorted", 8, 0), ("private", 0, 0))
+    INTERP_VARIANTS = (("index_order", 4, 0), ("degree_sorted", 0, 0))
+
+    def run(label, fn, want, nbytes, variants):
         nonlocal all_ok
         row = {"op": label}
-        for name, mode, cc in (("index_order", 4, 0), ("degree_sorted", 0, 0), ("degree_sorted_cc2", 0, 2), ("degree_sorted_cc4", 0, 4),
-                               ("degree_sorted_cc8", 0, 8)):
+        for name, mode, cc in variants:
             _lib.set_tuning("scatter_mode", mode)
             _lib.set_tuning("scatter_cc", cc)
             got = fn()[:2]
             err = (got.double() - want).abs().max().item()
             ok = err <= 1e-5 * max(want.abs().max().item(), 1.0)
             all_ok &= ok
+            if name == "private":  # fixed summation order: bit-reproducible
+                again = fn()[:2]
+                if not torch.equal(got, again):
+                    all_ok = False
+                    row[name + "_reproducible"] = False
             t = timeit(fn)
             row[name + "_us"] = round(t, 1)
             row[name + "_hbm_frac"] = round(nbytes / (t * 1e-6) / 1e9 / HBM, 3)
@@ -87,7 +94,7 @@ def main():
         want = torch.zeros((2, C, n), dtype=torch.float64, device=dev)
         want.scatter_add_(2, idx[:2].long().reshape(2, 1, m * ns).expand(-1, C, -1), gout[:2].double().reshape(2, C, m * ns))
         run(f"group bwd {label} n={n} m={m} ns={ns} C={C} B={B}", lambda: A.group_points_grad(gout, idx, n), want,
-            B * (4 * C * n + 4 * m * ns + 4 * C * m * ns))
+            B * (4 * C * n + 4 * m * ns + 4 * C * m * ns), GROUP_VARIANTS)
     for (nn, mm) in ((20000, 1024), (1024, 512), (512, 256)):
         unknown = xyz[:, :nn].contiguous() if nn == 20000 else lv0[:, :nn].contiguous()
         known = lv0[:, :mm].contiguous()
@@ -99,7 +106,7 @@ def main():
         src = (go[:2].double()[:, :, :, None] * w[:2].double()[:, None, :, :]).reshape(2, 256, nn * 3)
         want.scatter_add_(2, i3[:2].long().reshape(2, 1, nn * 3).expand(-1, 256, -1), src)
         run(f"interp bwd {nn}<-{mm} C=256 B={B}", lambda: A.three_interpolate_grad(go, i3, w, mm), want,
-            B * (4 * 256 * mm + 24 * nn + 4 * 256 * nn))
+            B * (4 * 256 * mm + 24 * nn + 4 * 256 * nn), INTERP_VARIANTS)
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     with open(args.out, "w") as f:
         json.dump({"B": B, "all_ok": bool(all_ok), "rows": rows}, f, indent=1)
