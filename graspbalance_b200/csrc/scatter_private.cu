@@ -82,61 +82,41 @@ struct PrivAcc<2> {
   static __device__ __forceinline__ float2 zero() { return make_float2(0.f, 0.f); }
 };
 
-// The rare rows of the warp-private backward, out of line so that the unrolled hot loop stays a few KB of code.
-//   cls 1: every row of the unit is an ascending run followed by copies of the row's first target t0 (how
-//          ball_query_gpu.cu:31-40 and cylinder_query_gpu.cu:68-75 fill rows with fewer than nsample hits): the copies are
-//          summed in registers across the row's LG lanes and added once;
-//   cls 2: anything else: per step, repeats among the active lanes' targets (match.any) are summed in registers first,
-//          then every target is updated once.
-// acc = this lane's plane; the unit is read from local memory (the caller's copy).
+// Padded rows (an ascending run followed by copies of the row's first target t0: how ball_query_gpu.cu:31-40 and
+// cylinder_query_gpu.cu:68-75 fill rows with fewer than nsample hits): every lane hands over the sum of its copies' values;
+// the LG lanes of a row (and plane) add them up and the row's first lane updates t0 once.  Out of line: scalar arguments
+// only, the unrolled hot loop stays small.
+template <int CW, int NRG, int LG>
+__device__ __noinline__ void priv_add_copies(typename PrivAcc<CW>::T *acc, int t0, float s0, float s1, float s2, float s3) {
+  float sum[CW];
+  sum[0] = s0, sum[1] = s1;
+  if (CW == 4) sum[CW - 2] = s2, sum[CW - 1] = s3;
+#pragma unroll
+  for (int d = LG / 2; d; d >>= 1) {
+#pragma unroll
+    for (int j = 0; j < CW; ++j) sum[j] += __shfl_xor_sync(0xffffffffu, sum[j], d);
+  }
+  const int lane = threadIdx.x & 31;
+#pragma unroll 1
+  for (int r = 0; r < NRG; ++r) {  // the rows of a unit one after the other: two of them may share their first target
+    if ((NRG == 1 || lane / LG == r) && (lane & (LG - 1)) == 0) {
+      typename PrivAcc<CW>::T a = acc[t0];
+      PrivAcc<CW>::add(a, sum);
+      acc[t0] = a;
+    }
+    __syncwarp();
+  }
+}
+
+// Rows that are neither ascending nor padded (kNN order, arbitrary caller tensors, out-of-range entries), out of line: per
+// step, repeats among the active lanes' targets (match.any) are summed in registers first, then every target is updated
+// once.  acc = this lane's plane; the unit is read from local memory (the caller's copy).
 template <int CW, int VL, int NRG, int LG>
-__device__ __noinline__ void priv_slow_unit(typename PrivAcc<CW>::T *acc, int n, int h, const PrivUnit<CW, VL> *up, int cls, int t0) {
+__device__ __noinline__ void priv_slow_unit(typename PrivAcc<CW>::T *acc, int n, int h, const PrivUnit<CW, VL> *up) {
   typedef typename PrivAcc<CW>::T AccT;
   const int lane = threadIdx.x & 31;
   const int rg = lane / LG;
   const PrivUnit<CW, VL> u = *up;
-  if (cls == 1) {
-    const bool first = (lane & (LG - 1)) == 0;
-    bool pad[VL];
-    float sum[CW];
-#pragma unroll
-    for (int j = 0; j < CW; ++j) sum[j] = 0.f;
-#pragma unroll
-    for (int q = 0; q < VL; ++q) {
-      pad[q] = u.t[q] == t0 && !(first && q == 0);
-#pragma unroll
-      for (int j = 0; j < CW; ++j) sum[j] += pad[q] ? u.v[j][q] : 0.f;
-    }
-#pragma unroll
-    for (int d = LG / 2; d; d >>= 1) {  // the lanes of one row (and plane) exchange among themselves
-#pragma unroll
-      for (int j = 0; j < CW; ++j) sum[j] += __shfl_xor_sync(0xffffffffu, sum[j], d);
-    }
-#pragma unroll 1
-    for (int r = 0; r < NRG; ++r) {
-      if (NRG == 1 || rg == r) {
-#pragma unroll
-        for (int q = 0; q < VL; ++q) {
-          if (!pad[q]) {
-            AccT a = acc[u.t[q]];
-            float x[CW];
-#pragma unroll
-            for (int j = 0; j < CW; ++j) x[j] = u.v[j][q];
-            PrivAcc<CW>::add(a, x);
-            acc[u.t[q]] = a;
-          }
-        }
-      }
-      __syncwarp();
-      if ((NRG == 1 || rg == r) && first) {  // the copies' total, once per row (and plane)
-        AccT a = acc[t0];
-        PrivAcc<CW>::add(a, sum);
-        acc[t0] = a;
-      }
-      __syncwarp();
-    }
-    return;
-  }
 #pragma unroll 1
   for (int r = 0; r < NRG; ++r) {
 #pragma unroll 1
@@ -256,6 +236,11 @@ __global__ void __launch_bounds__(MAXT, 1) scatter_private_kernel(const float *_
     }
     int t0 = 0;
     const int cls = classify(u, t0);
+    if (cls == 2) {
+      const PrivUnit<CW, VL> copy = u;  // addressable copy: the ring itself stays in registers
+      priv_slow_unit<CW, VL, NRG, LG>(acc, n, h, &copy);
+      return;
+    }
     if (cls == 0) {
 #pragma unroll
       for (int r = 0; r < NRG; ++r) {
@@ -274,9 +259,35 @@ __global__ void __launch_bounds__(MAXT, 1) scatter_private_kernel(const float *_
         }
         __syncwarp();  // the next row may name the same targets on other lanes
       }
-    } else {
-      const PrivUnit<CW, VL> copy = u;  // addressable copy: the ring itself stays in registers
-      priv_slow_unit<CW, VL, NRG, LG>(acc, n, h, &copy, cls, t0);
+      return;
+    }
+    // class 1: the copies of t0 leave the row (summed and added once, out of line); what is left is strictly ascending
+    const bool first = (lane & (LG - 1)) == 0;
+    bool pad[VL];
+    float sum[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int q = 0; q < VL; ++q) {
+      pad[q] = u.t[q] == t0 && !(first && q == 0);
+#pragma unroll
+      for (int j = 0; j < CW; ++j) sum[j] += pad[q] ? u.v[j][q] : 0.f;
+    }
+    priv_add_copies<CW, NRG, LG>(acc, t0, sum[0], sum[1], sum[2], sum[3]);
+#pragma unroll 1
+    for (int r = 0; r < NRG; ++r) {
+      if (NRG == 1 || rg == r) {
+#pragma unroll
+        for (int q = 0; q < VL; ++q) {
+          if (!pad[q]) {
+            AccT a = acc[u.t[q]];
+            float x[CW];
+#pragma unroll
+            for (int j = 0; j < CW; ++j) x[j] = u.v[j][q];
+            PrivAcc<CW>::add(a, x);
+            acc[u.t[q]] = a;
+          }
+        }
+      }
+      __syncwarp();
     }
   };
 
