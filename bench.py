@@ -133,14 +133,15 @@ class ClockSampler:
 def make_host_inputs(scene_ids, pin=True):
     import torch
     from graspbalance_b200 import pipeline, scenes
-    from graspbalance_b200.collision_detector import voxel_down_sample
+    from graspbalance_b200.collision_detector import voxel_down_sample_gpu
     B = len(scene_ids)
     xyz = scenes.scene_batch(scene_ids, N_POINTS, "tabletop")
     rot = pipeline.make_view_rotations(B, seed=int(scene_ids[0])).astype(np.float32)
     pts, Ts, Rs, thrs = [], [], [], []
     fw, fl, ad = 0.01, 0.06, 0.03
     for b, sid in enumerate(scene_ids):
-        p = voxel_down_sample(xyz[b].astype(np.float64), 0.01)  # what ModelFreeCollisionDetector.__init__ does (host)
+        # what ModelFreeCollisionDetector.__init__ does (the product's GPU down-sampling; input preparation, untimed)
+        p = voxel_down_sample_gpu(torch.from_numpy(xyz[b].astype(np.float64)).cuda(), 0.01).cpu().numpy()
         g = scenes.grasp_set(int(sid) + 1000, p, pipeline.NUM_GRASP)
         h, d, w = g["heights"][:, None], g["depths"][:, None], g["widths"][:, None]
         thr = np.concatenate([-h / 2, h / 2, d - fl, d, -(w / 2 + fw), -w / 2, (w / 2 + fw), w / 2, d - fl - fw, d - fl - fw - ad], axis=1)
@@ -260,6 +261,243 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+
+# ------------------------------------------------------------------------------------------------------------------
+# reported baselines beside the headline (rank 0, outside every timed region of the product)
+# ------------------------------------------------------------------------------------------------------------------
+def _event_ms(fn, iters, warm, dev):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize(dev)
+    ts = []
+    for _ in range(iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        e1.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def gpu_baseline_leg(args, dev):
+    """The reference's own kernels (oracle/_ref = PointNet/_ext_src + pointnet2_batch/src compiled unmodified for sm_100a) on
+    this GPU, driven op for op through the same chain with the reference's torch glue (oracle/ref_chain.py), and the
+    product on exactly those ops (no collision test: the reference has no GPU collision kernel) at the same batch."""
+    import torch
+    from graspbalance_b200 import pipeline
+    from oracle import ref_chain
+    ra, rb, _ = ref_chain.load_refs()
+    if ra is None or rb is None:
+        return {"unavailable": "oracle/_ref is not built (oracle/build_ref.py needs /root/reference)"}
+    Bb = max(1, min(args.batch, args.baseline_batch))
+    host, offs = make_host_inputs(list(range(Bb)), pin=False)
+    xyz, rot, _ = to_device(host, offs, dev)
+    pipe = pipeline.OpPipeline(Bb, N_POINTS, dev, seed=0, backward=not args.no_backward, overlap=not args.no_overlap,
+                               fused_crops=not args.unfused_crops)
+    with torch.no_grad():
+        ms_ref = _event_ms(lambda: ref_chain.run(pipe, xyz, rot, ra, rb, backward=not args.no_backward), 2, 1, dev)
+    ms_ours = _event_ms(lambda: pipe.run(xyz, rot, None), 5, 3, dev)
+    return {"value": Bb / (ms_ref * 1e-3), "unit": UNIT, "scenes": Bb, "ms_per_step": ms_ref,
+            "kind": "reference kernels, sm_100a (oracle/_ref: PointNet/_ext_src + pointnet2_batch/src, unmodified) with the reference's torch glue",
+            "product_same_ops": {"value": Bb / (ms_ours * 1e-3), "ms_per_step": ms_ours},
+            "excluded": "collision test (numpy on the CPU in the reference)"}
+
+
+def configs_leg(args, dev):
+    """BASELINE configs 1-4 as written (B = 4 scenes): product time, the reference's own implementation beside it."""
+    import torch
+    import oracle
+    from graspbalance_b200 import knn_modules, pipeline, scenes
+    from graspbalance_b200 import pointnet2_utils as pu
+    from graspbalance_b200.collision_detector import ModelFreeCollisionDetector
+    from oracle import ref_chain
+    ra, rb, rc = ref_chain.load_refs()
+    peak, _ = read_peaks()
+    B, N, m, ns = 4, N_POINTS, 1024, 64
+    out = {}
+    xyz_np = scenes.scene_batch(range(100, 100 + B), N, "tabletop")
+    xyz = torch.from_numpy(xyz_np).to(dev)
+    xyz_t = xyz.transpose(1, 2).contiguous()
+    gen = torch.Generator(device="cpu").manual_seed(7)
+
+    # cfg1: ModelFreeCollisionDetector(scene, voxel_size=0.01).detect(1024 grasps), host arrays in, bool mask out
+    pts64 = xyz_np[0].astype(np.float64)
+    det = ModelFreeCollisionDetector(pts64, voxel_size=0.01, device=dev)
+    gs = scenes.GraspGroupStandIn(**scenes.grasp_set(77, det.scene_points, pipeline.NUM_GRASP))
+
+    def cfg1():
+        d = ModelFreeCollisionDetector(pts64, voxel_size=0.01, device=dev)
+        return d.detect(gs, approach_dist=0.05, collision_thresh=0.01)
+    for _ in range(2):
+        cfg1()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        cfg1()
+    ms1 = (time.perf_counter() - t0) / 5 * 1e3
+    t0 = time.perf_counter()
+    det.detect(gs, approach_dist=0.05, collision_thresh=0.01)
+    ms1_detect = (time.perf_counter() - t0) * 1e3
+    oracle.build()
+    t0 = time.perf_counter()
+    p_cpu = oracle.voxel_down_sample(pts64, 0.01)
+    oracle.collision_detect_numpy(p_cpu, 0.01, gs.translations, gs.rotation_matrices, gs.heights, gs.depths, gs.widths,
+                                  approach_dist=0.05, collision_thresh=0.01)
+    out["cfg1"] = {"what": "constructor (voxel 0.01) + detect, 20k-point scene, 1024 grasps, host arrays in / mask out",
+                   "ms": ms1, "detect_only_ms": ms1_detect, "ref_cpu_ms": (time.perf_counter() - t0) * 1e3,
+                   "ref": "numpy restatement of collision_detector.py:16-64 on the host cores"}
+
+    # cfg2: SA chain, B = 4: FPS 20000 -> 1024, ball_query r = 0.05 ns = 64, group C = 3 + 128
+    feats = torch.randn((B, 128, N), generator=gen).to(dev)
+
+    def cfg2(mod_fps, mod_gather, mod_ball, mod_group):
+        inds = mod_fps(xyz, m)
+        new_xyz = mod_gather(xyz_t, inds).transpose(1, 2).contiguous()
+        idx = mod_ball(new_xyz, xyz, 0.05, ns)
+        return torch.cat([mod_group(xyz_t, idx), mod_group(feats, idx)], dim=1)
+    from graspbalance_b200 import _ext as A
+    ms2 = _event_ms(lambda: cfg2(A.furthest_point_sampling, A.gather_points, A.ball_query, A.group_points), 5, 2, dev)
+    algo2 = B * ((12 * N + 4 * m) + (12 * N + 16 * m) + (12 * N + 12 * m + 4 * m * ns) + 2 * 4 * m * ns + 4 * 131 * N + 4 * 131 * m * ns)
+    out["cfg2"] = {"what": "FPS 20000->1024 + gather + ball_query(0.05, 64) + group C=3 and C=128 + cat, B=4", "ms": ms2,
+                   "hbm_frac": algo2 / (ms2 * 1e-3) / 1e9 / peak}
+    if ra is not None:
+        out["cfg2"]["ref_gpu_ms"] = _event_ms(lambda: cfg2(ra.furthest_point_sampling, ra.gather_points, ra.ball_query, ra.group_points), 2, 1, dev)
+
+    # cfg3: FP chain, B = 4: three_nn + weights + three_interpolate forward / backward, 1024 -> 20000, C = 256
+    known = pu.gather_operation(xyz_t, pu.furthest_point_sample(xyz, m)).transpose(1, 2).contiguous()
+    kf = torch.randn((B, 256, m), generator=gen).to(dev)
+    go = torch.randn((B, 256, N), generator=gen).to(dev)
+
+    def cfg3_ours():
+        _, idx, w = pu.three_nn_weights(xyz, known)
+        A.three_interpolate(kf, idx, w)
+        return A.three_interpolate_grad(go, idx, w, m)
+
+    def cfg3_ref():
+        d2, idx = ra.three_nn(xyz, known)
+        r = 1.0 / (torch.sqrt(d2) + 1e-8)
+        w = r / torch.sum(r, dim=2, keepdim=True)
+        ra.three_interpolate(kf, idx, w)
+        return ra.three_interpolate_grad(go, idx, w, m)
+    ms3 = _event_ms(cfg3_ours, 5, 2, dev)
+    algo3 = B * ((12 * N + 12 * m + 36 * N) + 2 * (4 * 256 * m + 24 * N + 4 * 256 * N))
+    out["cfg3"] = {"what": "three_nn + weights + three_interpolate fwd + bwd, 1024 -> 20000, C=256, B=4", "ms": ms3,
+                   "hbm_frac": algo3 / (ms3 * 1e-3) / 1e9 / peak}
+    if ra is not None:
+        out["cfg3"]["ref_gpu_ms"] = _event_ms(cfg3_ref, 2, 1, dev)
+
+    # cfg4: grasp-crop stage, B = 4: 12 approach-view sets x 4 depths = 48 cylinder queries + grouped coordinates,
+    # KNN k = 1 and 64 (R = 20000, Q = 1024), and the batched collision test
+    seeds = known
+    rng = np.random.default_rng(3)
+    views = rng.normal(size=(B, m, 3)).astype(np.float32)
+    rots = [torch.from_numpy(np.ascontiguousarray(scenes.viewpoint_rotations(-views, np.full((B, m), i * np.pi / 12, np.float32))
+                                                  .reshape(B, m, 9))).to(dev) for i in range(12)]
+    ref_cf, qry_cf = xyz_t, seeds.transpose(1, 2).contiguous()
+
+    def crops(query, group, fused):
+        for rot in rots:
+            if fused:
+                idx = pu.cylinder_query_multi(0.05, -0.02, pipeline.CROP_HMAX, ns, xyz, seeds, rot)
+                pu._FusedQueryGroup.apply(xyz, seeds, idx.view(B, m, 4 * ns), rot, None, None)
+                continue
+            for hmax in pipeline.CROP_HMAX:
+                idx = query(seeds, xyz, rot, 0.05, -0.02, hmax, ns)
+                g = group(xyz_t, idx)
+                g -= seeds.transpose(1, 2).unsqueeze(-1)
+                torch.matmul(g.permute(0, 2, 3, 1).contiguous(), rot.view(B, m, 3, 3)).permute(0, 3, 1, 2).contiguous()
+
+    def crops_ours_unfused():
+        for rot in rots:
+            for hmax in pipeline.CROP_HMAX:
+                idx = A.cylinder_query(seeds, xyz, rot, 0.05, -0.02, hmax, ns)
+                pu._FusedQueryGroup.apply(xyz, seeds, idx, rot, None, None)
+
+    def knn_ours():
+        knn_modules.knn_k(ref_cf, qry_cf, 1)
+        knn_modules.knn_k(ref_cf, qry_cf, 64)
+
+    def knn_ref():
+        for k in (1, 64):
+            idx = torch.empty((B, k, m), dtype=torch.int64, device=dev)
+            rc.knn(ref_cf, qry_cf, idx)
+    ms4c = _event_ms(crops_ours_unfused, 3, 1, dev)
+    ms4f = _event_ms(lambda: crops(None, None, True), 3, 1, dev)
+    ms4k = _event_ms(knn_ours, 3, 1, dev)
+    out["cfg4"] = {"what": "48 cylinder_query(0.05, -0.02, hmax, 64) + grouped rotated coordinates; knn k=1 and k=64 (R=20000, Q=1024); B=4",
+                   "crops_48_calls_ms": ms4c, "crops_fused_depths_ms": ms4f, "knn_ms": ms4k, "ms": ms4f + ms4k}
+    if ra is not None:
+        out["cfg4"]["ref_gpu_crops_ms"] = _event_ms(lambda: crops(ra.cylinder_query, ra.group_points, False), 1, 1, dev)
+    if rc is not None:
+        out["cfg4"]["ref_gpu_knn_ms"] = _event_ms(knn_ref, 1, 1, dev)
+    if "ref_gpu_crops_ms" in out["cfg4"] and "ref_gpu_knn_ms" in out["cfg4"]:
+        out["cfg4"]["ref_gpu_ms"] = out["cfg4"]["ref_gpu_crops_ms"] + out["cfg4"]["ref_gpu_knn_ms"]
+    return out
+
+
+def arithmetic_peaks():
+    """Measured DFMA / FFMA lane-operations per second (tests/ubench/peaks.cu), or None when the helper is not built."""
+    import ctypes
+    path = os.path.join(ROOT, "tests", "ubench", "libgb_peaks.so")
+    if not os.path.exists(path):
+        return None
+    L = ctypes.CDLL(path)
+    L.ub_dfma_per_s.restype = L.ub_ffma_per_s.restype = ctypes.c_double
+    L.ub_dfma_per_s.argtypes = L.ub_ffma_per_s.argtypes = [ctypes.c_int]
+    return {"dfma_per_s": float(L.ub_dfma_per_s(4096)), "ffma_per_s": float(L.ub_ffma_per_s(8192)),
+            "how": "tests/ubench/peaks.cu: 8 independent FMA chains per thread, 2 x 1024 threads per SM, best of 3"}
+
+
+# lane instructions per candidate test of the scan kernels (sub/mul/fma/compare of the reference arithmetic, DESIGN.md 2)
+SCAN_INSTR = {"gb_ball_query": 8, "gb_cylinder_query": 17, "gb_three_nn": 12, "gb_three_nn_weights": 12, "gb_knn": 8}
+
+
+def kernel_notes(prof, peaks, steps):
+    """What bounds the kernels that are not HBM-bound (SURVEY 8d): FPS = latency of m - 1 dependent rounds (us per round);
+    scans = fp32 issue (full-scan-equivalent candidate tests per second against the measured FFMA rate: above 1 means the
+    cell grid culled candidates a full scan would test); collision = FP64 pipe against the measured DFMA rate."""
+    notes = {}
+    for name, evs in prof.items():
+        if name.startswith("gb_fps"):
+            best = max(evs, key=lambda e: e[2])
+            a = best[3]
+            mm = a[6] if name == "gb_fps_xyz" else a[5]
+            rows = [e for e in evs if e[3] == a]
+            us = sum(x.elapsed_time(y) for x, y, _, _ in rows) / len(rows) * 1e3
+            notes["fps"] = {"launch": f"b={a[4] if name == 'gb_fps_xyz' else a[3]} n={a[5] if name == 'gb_fps_xyz' else a[4]} m={mm}",
+                            "us": us, "us_per_round": us / max(mm - 1, 1),
+                            "sm": "ncu (profiles/r01e_ncu_full_summary.csv): 2 warps per scheduler, issue slots 45 % of a round, the rest is the cluster exchange latency"}
+    if peaks:
+        for name, evs in prof.items():
+            base = name.replace("_multi_radius", "").replace("_multi", "").replace("_batched", "")
+            if base in SCAN_INSTR:
+                tests = 0.0
+                for _, _, _, a in evs:
+                    if base in ("gb_ball_query",):
+                        tests += a[3] * a[4] * a[5]
+                    elif base == "gb_cylinder_query":
+                        tests += a[4] * a[5] * a[6]
+                    elif base in ("gb_three_nn",):
+                        tests += a[4] * a[5] * a[6]
+                    elif base == "gb_three_nn_weights":
+                        tests += a[5] * a[6] * a[7]
+                    elif base == "gb_knn":
+                        tests += a[3] * a[5] * a[6]
+                sec = sum(x.elapsed_time(y) for x, y, _, _ in evs) * 1e-3
+                n = notes.setdefault(base, {"tests_per_s": 0.0})
+                n["tests_per_s"] = tests / sec if sec > 0 else 0.0
+                n["fp32_issue_frac_full_scan_equiv"] = n["tests_per_s"] * SCAN_INSTR[base] / peaks["ffma_per_s"]
+            if name.startswith("gb_collision_counts"):
+                pairs = sum((a[2] * a[3] * a[7]) if name.endswith("batched") else (a[1] * a[5]) for _, _, _, a in evs)
+                sec = sum(x.elapsed_time(y) for x, y, _, _ in evs) * 1e-3
+                notes["collision"] = {"pairs_per_s": pairs / sec if sec > 0 else 0.0,
+                                      "fp64_pipe_frac": (pairs / sec) * 24 / peaks["dfma_per_s"] if sec > 0 else 0.0,
+                                      "ops_per_pair": "3 DADD + 9 DMUL/DFMA + 12 DSETP (collision_detector.py:23-41), upper bound: the height-slab reject skips most of them"}
+    return notes
+
+
 def workload_name(args):
     return (f"BASELINE config 5: full GraspBalance backbone op pipeline forward{'+backward' if not args.no_backward else ''} "
             f"(SA1-4 + 15 InvResMLP + FP1/2 + 20k up-sampling + 16 cylinder crops + 1024-grasp collision), "
@@ -277,6 +515,11 @@ def main():
     ap.add_argument("--no-backward", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling leg (32 scenes in total over the N GPUs)")
+    ap.add_argument("--strong-total", type=int, default=32, help="scenes in total of the strong-scaling leg")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the reference-kernels leg (oracle/_ref on this GPU)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE configs 1-4 leg")
+    ap.add_argument("--baseline-batch", type=int, default=8, help="scenes per step of the reference-kernels leg")
     ap.add_argument("--no-overlap", action="store_true", help="run the sampling chain and the collision tests on the main stream")
     ap.add_argument("--unfused-crops", action="store_true",
                     help="grasp crops as the reference's 16 separate CylinderQueryAndGroup calls instead of 4 multi-depth scans")
@@ -312,22 +555,64 @@ def main():
     gather_buf = torch.empty((world * B, pipeline.NUM_SEED + 6 * pipeline.NUM_GRASP), dtype=torch.int64, device=dev) if world > 1 else None
 
     def step(resident, inputs=None):
-        """One pipeline pass.  resident=True: inputs already on the device.  resident=False: the e2e path -- pinned host
-        buffers are copied in, the per-scene results are copied back to the host."""
-        if resident:
-            xyz, rot, grasps = inputs
-        else:
-            xyz, rot, grasps = to_device(host, offs, dev)
+        """One pipeline pass over device-resident inputs; returns the per-scene result tensor and the checksums."""
+        xyz, rot, grasps = inputs
         out = pipe.run(xyz, rot, grasps)
         result = torch.cat([out["seed_inds"].to(torch.int64), out["collision_counts"].reshape(B, -1)], dim=1)
         if world > 1:
             sharding.gather_scene_outputs(result, world, gather_buf)  # NCCL: gather per-scene outputs only
-        if not resident:
-            res_h = result.to("cpu", non_blocking=True)
-            chk_h = torch.stack([out["up_checksum"], out["crop_checksum"]] + ([out["grad_checksum"]] if "grad_checksum" in out else [])).to("cpu", non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            return res_h, chk_h
-        return result
+        if resident:
+            return result
+        chk = torch.stack([out["up_checksum"], out["crop_checksum"]] + ([out["grad_checksum"]] if "grad_checksum" in out else []))
+        return result, chk
+
+    # ---- e2e: every step copies its inputs from pinned host memory and its results back to pinned host memory.  The copies
+    # run on a copy stream one step ahead / behind the compute stream (two device input sets, two host result sets), so a
+    # step's H2D overlaps the previous step's kernels; every copy is inside the timed region and every step's result is on
+    # the host when the region closes.
+    copy_stream = torch.cuda.Stream(dev)
+    e2e_bufs = []
+
+    def e2e_prepare():
+        for _ in range(2):
+            d = {k: torch.empty_like(v, device=dev) for k, v in host.items()}
+            grasps = {"scene_points": [d["scene_points"][offs[b]:offs[b + 1]] for b in range(len(offs) - 1)],
+                      "T": d["T"], "R": d["R"], "thr": d["thr"]}
+            e2e_bufs.append({"dev": d, "inputs": (d["xyz"], d["rot"], grasps), "free": None, "res_h": None, "chk_h": None})
+
+    def e2e_steps(n_steps):
+        main = torch.cuda.current_stream(dev)
+
+        def upload(k):
+            buf = e2e_bufs[k % 2]
+            with torch.cuda.stream(copy_stream):
+                if buf["free"] is not None:
+                    copy_stream.wait_event(buf["free"])  # the step that last read this input set has finished
+                for name, v in host.items():
+                    buf["dev"][name].copy_(v, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            return ev
+
+        ready = upload(0)
+        for k in range(n_steps):
+            buf = e2e_bufs[k % 2]
+            main.wait_event(ready)
+            if k + 1 < n_steps:
+                ready = upload(k + 1)
+            result, chk = step(False, buf["inputs"])
+            done = torch.cuda.Event()
+            done.record(main)
+            buf["free"] = done
+            with torch.cuda.stream(copy_stream):  # results of step k leave while step k + 1 computes
+                copy_stream.wait_event(done)
+                if buf["res_h"] is None:
+                    buf["res_h"] = torch.empty(result.shape, dtype=result.dtype, pin_memory=True)
+                    buf["chk_h"] = torch.empty(chk.shape, dtype=chk.dtype, pin_memory=True)
+                buf["res_h"].copy_(result, non_blocking=True)
+                buf["chk_h"].copy_(chk, non_blocking=True)
+                result.record_stream(copy_stream), chk.record_stream(copy_stream)
+        main.wait_stream(copy_stream)  # the timed region ends when the last result is on the host
 
     def barrier():
         if world > 1:
@@ -340,14 +625,17 @@ def main():
         t_wall0 = time.time()
         e0.record()
         marks = []
-        for _ in range(n_steps):
-            step(resident, inputs)
-            marks.append(torch.cuda.Event(enable_timing=True))
-            marks[-1].record()  # per-step marks on the main stream: diagnostics only (the value is e0..e1 over all K steps)
+        if callable(resident):
+            resident(n_steps)  # a whole-loop runner (the e2e path, graph replays)
+        else:
+            for _ in range(n_steps):
+                step(resident, inputs)
+                marks.append(torch.cuda.Event(enable_timing=True))
+                marks[-1].record()  # per-step marks on the main stream: diagnostics only (the value is e0..e1 over all K steps)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
-        timed.per_step = [a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks)]
+        timed.per_step = [a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks)] if marks else [ms / n_steps]
         if world > 1:
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -417,13 +705,65 @@ def main():
     # ---- e2e: host buffers in, results out, every step ----
     e2e = None
     if not args.no_e2e:
-        for _ in range(2):
-            step(False)
-        ms_e2e, _, _ = timed(args.steps, False)
+        e2e_prepare()
+        e2e_steps(3)
+        ms_e2e, _, _ = timed(args.steps, e2e_steps)
         h2d = sum(v.numel() * v.element_size() for v in host.values())
         d2h = B * (pipeline.NUM_SEED + 6 * pipeline.NUM_GRASP) * 8 + 3 * 4
         e2e = {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / args.steps}
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / args.steps,
+               "copies": "pinned host -> device and results -> pinned host every step, on a copy stream one step ahead / behind"}
+
+
+    # ---- strong scaling (BASELINE config 5 as written: 32 scenes in total, sharded 32 / N per GPU) ----
+    # A small shard makes the step launch-bound on the host (about 170 launches from Python), so the whole step -- every
+    # stream, forward and backward -- is captured once in a CUDA graph and replayed; the all_gather stays an eager call.
+    strong = None
+    if not args.no_strong:
+        total = args.strong_total
+        lo, hi = sharding.shard_batch(total, world)[rank]
+        Bs = hi - lo
+        if Bs == B:
+            s_pipe, s_inputs = pipe, resident_inputs
+        else:
+            s_host, s_offs = make_host_inputs(list(range(lo, hi)), pin=False)
+            s_pipe = pipeline.OpPipeline(Bs, N_POINTS, dev, seed=rank, backward=not args.no_backward, overlap=not args.no_overlap,
+                                         fused_crops=not args.unfused_crops)
+            s_inputs = to_device(s_host, s_offs, dev)
+        s_gather = torch.empty((total, pipeline.NUM_SEED + 6 * pipeline.NUM_GRASP), dtype=torch.int64, device=dev) if world > 1 else None
+        equal_shards = all(e - b == Bs for b, e in sharding.shard_batch(total, world))
+
+        def s_step():
+            out = s_pipe.run(*s_inputs)
+            return torch.cat([out["seed_inds"].to(torch.int64), out["collision_counts"].reshape(Bs, -1)], dim=1)
+
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                s_step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        launches_g0 = _lib.launch_count()
+        with torch.cuda.graph(graph, stream=side):
+            s_result = s_step()
+        launches_graph = _lib.launch_count() - launches_g0
+        torch.cuda.synchronize()
+
+        def s_loop(n_steps):
+            for _ in range(n_steps):
+                graph.replay()
+                if world > 1 and equal_shards:
+                    sharding.gather_scene_outputs(s_result, world, s_gather)
+
+        s_loop(max(args.warmup, 3))
+        ms_s, _, _ = timed(args.steps, s_loop)
+        strong = {"scenes_total": total, "scenes_per_gpu": Bs, "ms_per_step": ms_s / args.steps,
+                  "value": total * args.steps / (ms_s * 1e-3), "unit": UNIT, "cuda_graph": True,
+                  "launches_per_step": int(launches_graph),
+                  "note": "same step as `value`, one CUDA-graph replay per step; efficiency = value(N) / value(1) across the driver's runs"}
+        del graph
 
     if rank != 0:
         if world > 1:
@@ -434,13 +774,13 @@ def main():
     peak, peak_src = read_peaks()
     fam = {}
     for name, evs in prof.items():
-        tot_ms = sum(a.elapsed_time(b) for a, b, _ in evs)
+        tot_ms = sum(a.elapsed_time(b) for a, b, _, _ in evs)
         base = name.replace("_set", "").replace("_strided", "").replace("_multi_radius", "").replace("_multi", "").replace("_batched", "")  # entry-point variants of one op share its kernels
         f = fam.setdefault(base, {"launches": 0, "ms": 0.0, "bytes": 0, "big": None})
         f["launches"] += len(evs)
         f["ms"] += tot_ms
-        f["bytes"] += sum(x for _, _, x in evs)
-        for a, b, x in evs:  # the launch that moves the most bytes: small launches of a family are latency-bound
+        f["bytes"] += sum(x for _, _, x, _ in evs)
+        for a, b, x, _ in evs:  # the launch that moves the most bytes: small launches of a family are latency-bound
             if f["big"] is None or x > f["big"][0]:
                 f["big"] = (x, a.elapsed_time(b))
     total_ms = sum(f["ms"] for f in fam.values()) or 1.0
@@ -480,17 +820,24 @@ def main():
         cpu = {"value": n_cpu / t_cpu, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port",
                "sample": f"{n_cpu} scenes (full op chain fwd+bwd each) of the {B}-scene batch, oracle/gb_oracle.c + numpy detect"}
 
+    peaks = arithmetic_peaks()
+    notes = kernel_notes(prof, peaks, args.steps)
+    gpu_base = None if args.no_gpu_baseline else gpu_baseline_leg(args, dev)
+    cfgs = None if args.no_configs else configs_leg(args, dev)
+
     algo = pipeline.algorithmic_bytes_per_scene(N_POINTS, not args.no_backward)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args), "scenes_per_gpu": B, "n_points": N_POINTS, "parallelism": f"scene-sharded x{world}",
+                       "headline": "`value` / `e2e` = 32 scenes per GPU (weak scaling: the configuration that fills a B200); `strong` = BASELINE config 5 as written, 32 scenes in total over the N GPUs",
                        "streams": "sampling chain + collision tests on side streams" if pipe.overlap else "single stream",
                        "l2": "per-step working set (>10 GB of grouped features) exceeds the 126 MB L2; no explicit flush",
                        "algorithmic_bytes_per_scene": int(sum(algo.values())),
                        "allocator_priming_steps": prime_steps, "device_allocs_in_timed_region": int(dev_allocs_timed),
                        "step_diagnostics": step_diag},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "strong": strong, "gpu_baseline": gpu_base, "configs": cfgs, "arithmetic_peaks": peaks, "kernel_notes": notes,
             "roofline_pass_ms_per_step": ms_prof / args.steps,
             "pipeline_hbm_frac": (sum(algo.values()) * world * B * args.steps / (ms * 1e-3) / 1e9) / (peak * world),
             "per_op": per_op}

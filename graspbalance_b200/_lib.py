@@ -45,6 +45,7 @@ SIGNATURES = {
     "gb_collision_counts": [_vp, _i, _vp, _vp, _vp, _i, _vp, _vp],
     "gb_collision_counts_host": [_vp, _i, _vp, _vp, _vp, _i, _vp],
     "gb_collision_counts_batched": [_vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _vp],
+    "gb_collision_detect": [_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, ctypes.POINTER(ctypes.c_double), _vp, _vp, _vp, _vp, _vp],
     "gb_voxel_means": [_vp, _vp, _vp, _vp, _i, _vp],
     "gb_set_tuning": [ctypes.c_char_p, _i],
     "gb_get_tuning": [ctypes.c_char_p, ctypes.POINTER(ctypes.c_int)],
@@ -123,6 +124,7 @@ ALGO_BYTES = {
     "gb_knn": lambda a: a[3] * (4 * a[4] * (a[5] + a[6]) + 8 * a[7] * a[6]),              # b*(4d(R+Q) + 8kQ)
     "gb_collision_counts": lambda a: 24 * a[1] + 176 * a[5] + 48 * a[5],
     "gb_collision_counts_batched": lambda a: a[2] * (24 * a[3] + 176 * a[7] + 48 * a[7]),
+    "gb_collision_detect": lambda a: 24 * a[1] + 8 * 15 * a[4] + a[4],                   # 24 N' + grasp rows + masks
     "gb_voxel_means": lambda a: 48 * a[4] * 4 + 24 * a[4],  # ~4 points per voxel read (24 B + 8 B index), 24 B written
 }
 
@@ -146,7 +148,7 @@ def call(name, ref_tensor, *args):
             e0.record(stream)
             err = fn(*args, stream.cuda_stream)
             e1.record(stream)
-            PROFILER.setdefault(name, []).append((e0, e1, ALGO_BYTES[name](args)))
+            PROFILER.setdefault(name, []).append((e0, e1, ALGO_BYTES[name](args), tuple(a if isinstance(a, (int, float)) else None for a in args)))
     finally:
         if prev is not None:
             torch.cuda.set_device(prev)

@@ -108,6 +108,85 @@ __global__ void voxel_means_kernel(const double *__restrict__ points, const long
   out[3 * (size_t)i] = sx / cnt, out[3 * (size_t)i + 1] = sy / cnt, out[3 * (size_t)i + 2] = sz / cnt;
 }
 
+
+// ---- detect() entirely on the device ------------------------------------------------------------------------
+// collision_detector.py:16-64 around the occupancy test is elementwise IEEE arithmetic on the grasp arrays: the ten
+// half-space thresholds (:26-35), the gripper volumes in voxels (:43-46,55) and count / (volume + 1e-6) > thresh (:47-48,
+// 56-63).  numpy evaluates them in the DTYPE OF THE GRASP ARRAYS -- float32 for a graspnetAPI GraspGroup built from network
+// output, float64 otherwise -- with the Python floats cast to that dtype first, left to right, no contraction; only the
+// comparisons against the fp64 transformed points and the final integer / float divisions are fp64.  F below is that dtype;
+// every operation is an explicit round-to-nearest intrinsic.
+template <typename F>
+struct ColArith;
+template <>
+struct ColArith<float> {
+  static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+  static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+  static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+  static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+};
+template <>
+struct ColArith<double> {
+  static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+  static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+  static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+  static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+};
+
+struct ColParams {
+  double fw, fl, ad, v3, two_fw, collision_thresh, empty_thresh;
+};
+
+// grasp rows: `stride` elements apart, translation / rotation (row-major 3x3) / height / depth / width at the given column
+// offsets -- [G,15] packed by the host wrapper, or the [Ns,17] array pred_decode emits (graspbalance.py:187-190).
+// Writes T64 [g,3], R64 [g,9], thr [g,10] and den [g,5] = {volume + 1e-6, lr + 1e-6, bottom + 1e-6, shifting + 1e-6, inner}.
+template <typename F>
+__global__ void collision_prepare_kernel(const F *__restrict__ rows, int g, int stride, int oT, int oR, int oH, int oD, int oW,
+                                         ColParams p, double *__restrict__ T64, double *__restrict__ R64, double *__restrict__ thr,
+                                         double *__restrict__ den) {
+  typedef ColArith<F> A;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g) return;
+  const F *r = rows + (size_t)i * stride;
+#pragma unroll
+  for (int e = 0; e < 3; ++e) T64[(size_t)i * 3 + e] = (double)r[oT + e];
+#pragma unroll
+  for (int e = 0; e < 9; ++e) R64[(size_t)i * 9 + e] = (double)r[oR + e];
+  const F h = r[oH], d = r[oD], w = r[oW];
+  const F fw = (F)p.fw, fl = (F)p.fl, ad = (F)p.ad, v3 = (F)p.v3, two_fw = (F)p.two_fw, eps = (F)1e-6, two = (F)2;
+  const F h2 = A::div(h, two), w2 = A::div(w, two);
+  const F w2fw = A::add(w2, fw), dfl = A::sub(d, fl), dflfw = A::sub(dfl, fw);
+  double *t = thr + (size_t)i * 10;
+  t[0] = (double)(-h2), t[1] = (double)h2, t[2] = (double)dfl, t[3] = (double)d, t[4] = (double)(-w2fw), t[5] = (double)(-w2),
+  t[6] = (double)w2fw, t[7] = (double)w2, t[8] = (double)dflfw, t[9] = (double)A::sub(dflfw, ad);
+  const F lr = A::div(A::mul(A::mul(h, fl), fw), v3);
+  const F wide = A::mul(h, A::add(w, two_fw));
+  const F bottom = A::div(A::mul(wide, fw), v3), shifting = A::div(A::mul(wide, ad), v3);
+  const F volume = A::add(A::add(A::mul(lr, two), bottom), shifting);
+  double *q = den + (size_t)i * 5;
+  q[0] = (double)A::add(volume, eps), q[1] = (double)A::add(lr, eps), q[2] = (double)A::add(bottom, eps),
+  q[3] = (double)A::add(shifting, eps), q[4] = (double)A::div(A::mul(A::mul(h, fl), w), v3);
+}
+
+// counts [g,6] -> collision mask, optional empty mask, optional IoUs [5,g] (global, left, right, bottom, shifting)
+__global__ void collision_finish_kernel(const unsigned long long *__restrict__ counts, const double *__restrict__ den, int g, ColParams p,
+                                        unsigned char *__restrict__ mask, unsigned char *__restrict__ empty, double *__restrict__ ious) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g) return;
+  const unsigned long long *c = counts + (size_t)i * 6;
+  const double *q = den + (size_t)i * 5;
+  const double giou = __ddiv_rn((double)(long long)c[0], q[0]);
+  mask[i] = giou > p.collision_thresh ? 1 : 0;
+  if (empty) empty[i] = __ddiv_rn((double)(long long)c[5], q[4]) < p.empty_thresh ? 1 : 0;
+  if (ious) {
+    ious[i] = giou;
+    ious[(size_t)g + i] = __ddiv_rn((double)(long long)c[1], q[1]);
+    ious[(size_t)2 * g + i] = __ddiv_rn((double)(long long)c[2], q[1]);
+    ious[(size_t)3 * g + i] = __ddiv_rn((double)(long long)c[3], q[2]);
+    ious[(size_t)4 * g + i] = __ddiv_rn((double)(long long)c[4], q[3]);
+  }
+}
+
 static int collision_launch(const double *points, int np, const double *T, const double *R, const double *thr, int g, int64_t *counts,
                             cudaStream_t s) {
   cudaError_t e = cudaMemsetAsync(counts, 0, (size_t)g * 6 * sizeof(int64_t), s);
@@ -161,6 +240,46 @@ extern "C" int gb_collision_counts_host(const double *points, int np, const doub
   if (!rc) rc = (int)cudaStreamSynchronize(s);
   cudaFree(d);
   cudaStreamDestroy(s);
+  return rc;
+}
+
+
+/* ModelFreeCollisionDetector.detect (collision_detector.py:16-64) without a host round trip.
+ * points [np,3] f64 = the detector's down-sampled scene; grasps = g rows of `dtype` (0 = f32, 1 = f64), row_stride elements
+ * apart, with the translation (3), row-major rotation (9), height, depth and width at column offsets oT, oR, oH, oD, oW
+ * (a packed [g,15] array, or pred_decode's [Ns,17] array: graspbalance.py:187-190).  params (HOST, 7 doubles) = finger_width,
+ * finger_length, max(approach_dist, finger_width), voxel_size**3, 2*finger_width, collision_thresh, empty_thresh -- the
+ * Python floats of the reference.  mask [g] u8 (required); empty [g] u8, ious [5,g] f64, counts [g,6] i64: optional outputs.
+ * Thresholds and volumes are evaluated in the grasp arrays' dtype exactly as numpy does; every output is bit-identical to
+ * the reference's for f32 and f64 grasp groups. */
+extern "C" int gb_collision_detect(const double *points, int np, const void *grasps, int dtype, int g, int row_stride, int oT, int oR,
+                                   int oH, int oD, int oW, const double *params, unsigned char *mask, unsigned char *empty, double *ious,
+                                   int64_t *counts, gb_stream_t stream) {
+  if (np < 0 || g < 0 || (dtype != 0 && dtype != 1) || !params) return (int)cudaErrorInvalidValue;
+  if (g == 0) return 0;
+  if (!grasps || !mask || (np > 0 && !points) || row_stride <= 0) return (int)cudaErrorInvalidValue;
+  cudaStream_t s = (cudaStream_t)stream;
+  gb::ColParams p = {params[0], params[1], params[2], params[3], params[4], params[5], params[6]};
+  const size_t nd = (size_t)g * (3 + 9 + 10 + 5);
+  double *scratch = nullptr;
+  cudaError_t e = gb::scratch_alloc((void **)&scratch, (nd + (counts ? 0 : (size_t)g * 6)) * sizeof(double), s);
+  if (e != cudaSuccess) return (int)e;
+  double *T64 = scratch, *R64 = T64 + (size_t)g * 3, *thr = R64 + (size_t)g * 9, *den = thr + (size_t)g * 10;
+  int64_t *cnt = counts ? counts : reinterpret_cast<int64_t *>(den + (size_t)g * 5);
+  const int blocks = (g + 127) / 128;
+  if (dtype == 0)
+    gb::collision_prepare_kernel<float><<<blocks, 128, 0, s>>>((const float *)grasps, g, row_stride, oT, oR, oH, oD, oW, p, T64, R64, thr, den);
+  else
+    gb::collision_prepare_kernel<double><<<blocks, 128, 0, s>>>((const double *)grasps, g, row_stride, oT, oR, oH, oD, oW, p, T64, R64, thr, den);
+  gb::count_launch();
+  int rc = gb::finish_launch();
+  if (!rc) rc = gb::collision_launch(points, np, T64, R64, thr, g, cnt, s);
+  if (!rc) {
+    gb::collision_finish_kernel<<<blocks, 128, 0, s>>>(reinterpret_cast<const unsigned long long *>(cnt), den, g, p, mask, empty, ious);
+    gb::count_launch();
+    rc = gb::finish_launch();
+  }
+  cudaFreeAsync(scratch, s);
   return rc;
 }
 

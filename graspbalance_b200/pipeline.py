@@ -83,39 +83,54 @@ class OpPipeline:
 
     # ------------------------------------------------------------------------------------------------------------
     @staticmethod
-    def _interp(unknown, known, feats, grad):
+    def _interp(unknown, known, feats, grad, collect=None, tag=""):
         # three_nn + weights of pointnet2_modules.py:413-416 (sqrt, +1e-8, reciprocal, sum, divide) in one launch
         _, idx, weight = pu.three_nn_weights(unknown, known)
         out = pu.three_interpolate(feats, idx, weight)
         if grad is not None:
             out.backward(grad)
+        if collect is not None:
+            collect[tag + "_idx"], collect[tag + "_weight"], collect[tag + "_out"] = idx, weight, out.detach()
         return out
 
-    def _crops(self, xyz, view_rot, sa2_xyz, out):
+    def _crops(self, xyz, view_rot, sa2_xyz, out, collect=None):
         # ---- grasp crop: 4 radii x 4 depths cylinder query + group (seeds = fp2_xyz: 1024 points, drp.py:301-303) ----
         parts = []  # small slices: the checksum only gives the step a result to return
         if self.fused_crops:
             # WidthGroup1..4 of graspbalance.py:104-107 differ in the radius only: one scan for all 4 x 4 cylinders
-            parts = [g[:, :, :16] for g in multi_scale_group(self.crop_modules, sa2_xyz, xyz, view_rot)]  # seeds 0..3 x 4 depths
+            groups = multi_scale_group(self.crop_modules, sa2_xyz, xyz, view_rot)
+            parts = [g[:, :, :16] for g in groups]  # seeds 0..3 x 4 depths
+            if collect is not None:  # [B,3,seed*D+d,ns] -> one [B,3,seed,ns] per (radius k, depth d)
+                for k, g in enumerate(groups):
+                    g5 = g.view(g.shape[0], 3, NUM_SEED, len(CROP_HMAX), g.shape[-1])
+                    for d in range(len(CROP_HMAX)):
+                        collect[f"crop{k}_{d}_xyz"] = g5[:, :, :, d, :]
         else:
-            for mod in self.crop_modules:
-                parts += [gq(xyz, sa2_xyz, view_rot)[:, :, :4] for gq in mod.groupers]  # 4 x [B,3,1024,64]
+            for k, mod in enumerate(self.crop_modules):
+                full = [gq(xyz, sa2_xyz, view_rot) for gq in mod.groupers]  # 4 x [B,3,1024,64]
+                parts += [g[:, :, :4] for g in full]
+                if collect is not None:
+                    for d, g in enumerate(full):
+                        collect[f"crop{k}_{d}_xyz"] = g
         out["crop_checksum"] = torch.cat([p.reshape(-1) for p in parts]).sum()
 
-    def _interpolation(self, xyz, sa2_xyz, sa3_xyz, sa4_xyz, out):
+    def _interpolation(self, xyz, sa2_xyz, sa3_xyz, sa4_xyz, out, collect=None):
         bw = self.backward
         # ---- FP modules + up-sampling of the seed features to the full cloud ----
-        self._interp(sa3_xyz, sa4_xyz, self.fp_feats[0], self.fp_grads[0] if bw else None)
-        self._interp(sa2_xyz, sa3_xyz, self.fp_feats[1], self.fp_grads[1] if bw else None)
-        up = self._interp(xyz, sa2_xyz, self.fp_feats[2], self.fp_grads[2] if bw else None)
+        self._interp(sa3_xyz, sa4_xyz, self.fp_feats[0], self.fp_grads[0] if bw else None, collect, "fp0")
+        self._interp(sa2_xyz, sa3_xyz, self.fp_feats[1], self.fp_grads[1] if bw else None, collect, "fp1")
+        up = self._interp(xyz, sa2_xyz, self.fp_feats[2], self.fp_grads[2] if bw else None, collect, "fp2")
         out["up_checksum"] = up[:, :4, :256].sum()
 
-    def run(self, xyz, view_rot, grasps=None):
+    def run(self, xyz, view_rot, grasps=None, collect=None):
         """xyz [B,N,3] f32 CUDA; view_rot [B,1024,3,3] f32 CUDA (approach frames of the seeds); grasps = optional dict of
         per-scene fp64 CUDA tensors {scene_points: list of [N'_b,3], T [B,G,3], R [B,G,3,3], thr [B,G,10]}.
-        Returns a dict of the per-scene outputs a caller would keep."""
+        Returns a dict of the per-scene outputs a caller would keep.  collect: optional dict that receives every index
+        tensor, forward tensor and gradient of the chain (parity tests; costs two extra query launches per level)."""
         bw = self.backward
         out = {}
+        if collect is not None and self.overlap:
+            raise ValueError("collect= needs the single-stream schedule (overlap=False)")
         main = torch.cuda.current_stream(self.device) if self.overlap else None
 
         def sample(cur, npoint):  # furthest_point_sample + gather_operation of one SA module (pointnet2_modules.py:151-158)
@@ -158,6 +173,9 @@ class OpPipeline:
             grouped, _ = self.sa_groupers[lvl](cur_xyz, new_xyz, feats)
             if bw and feats is not None:
                 grouped.backward(self.sa_grads[lvl])
+            if collect is not None:
+                collect[f"sa{lvl}_inds"], collect[f"sa{lvl}_xyz"], collect[f"sa{lvl}_grouped"] = inds, new_xyz, grouped.detach()
+                collect[f"sa{lvl}_idx"] = pu.ball_query(radius, nsample, cur_xyz, new_xyz)
             if lvl == 0:
                 out["sa1_inds"] = inds
             # ---- InvResMLP blocks (variant B) ----
@@ -167,6 +185,9 @@ class OpPipeline:
                 dp, fj = self.irm_groupers[lvl](new_xyz, new_xyz, f)
                 if bw:
                     fj.backward(self.irm_grads[lvl])
+            if collect is not None:
+                collect[f"irm{lvl}_dp"], collect[f"irm{lvl}_fj"] = dp, fj.detach()
+                collect[f"irm{lvl}_idx"] = gb_group.ball_query(IRM_SPECS[lvl][2], IRM_SPECS[lvl][3], new_xyz, new_xyz)
             cur_xyz = new_xyz
             level_xyz.append(new_xyz)
             if self.overlap and lvl == 0:
@@ -192,8 +213,8 @@ class OpPipeline:
         sa1_xyz, sa2_xyz, sa3_xyz, sa4_xyz = level_xyz
         out["seed_inds"] = out["sa1_inds"][:, :NUM_SEED]
         if not self.overlap:
-            self._interpolation(xyz, sa2_xyz, sa3_xyz, sa4_xyz, out)
-            self._crops(xyz, view_rot, sa2_xyz, out)
+            self._interpolation(xyz, sa2_xyz, sa3_xyz, sa4_xyz, out, collect)
+            self._crops(xyz, view_rot, sa2_xyz, out, collect)
         if aux_done is not None:
             main.wait_event(aux_done)
         # ---- collision test ----
@@ -204,6 +225,13 @@ class OpPipeline:
         if bw:
             out["grad_checksum"] = torch.cat([t.grad[:, :4, :64].reshape(-1) for t in
                                               self.sa_in_feats[1:] + self.irm_feats + self.fp_feats]).sum()
+            if collect is not None:
+                for lvl in range(1, 4):
+                    collect[f"sa{lvl}_grad"] = self.sa_in_feats[lvl].grad
+                for lvl in range(4):
+                    collect[f"irm{lvl}_grad"] = self.irm_feats[lvl].grad
+                for i in range(3):
+                    collect[f"fp{i}_grad"] = self.fp_feats[i].grad
             for t in self.sa_in_feats[1:] + self.irm_feats + self.fp_feats:
                 t.grad = None
         return out

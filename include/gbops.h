@@ -180,6 +180,22 @@ GB_API int gb_collision_counts_host(const double *points, int np, const double *
 GB_API int gb_collision_counts_batched(const double *points, const long long *scene_off, int nscenes, int max_np, const double *T,
                                 const double *R, const double *thr, int g, int64_t *counts, gb_stream_t stream);
 
+/* ModelFreeCollisionDetector.detect (collision_detector.py:16-64) without a host round trip: thresholds
+ * (:26-35), occupancy counts (:23-41,55), volumes and IoUs (:43-47,55-63) and the masks (:48,56) in one call.
+ * points [np,3] f64 = the detector's down-sampled scene.  grasps = g rows of `dtype` (0 = f32, 1 = f64) that lie
+ * row_stride elements apart and hold the translation (3), the row-major rotation (9), height, depth and width at column
+ * offsets oT, oR, oH, oD, oW: a packed [g,15] array, or the [Ns,17] array pred_decode emits (TrainModel/graspbalance.py:
+ * 187-190: score, width, height, depth, rotation, centre, object id) -- so network output feeds the test in place.
+ * params = 7 HOST doubles {finger_width, finger_length, max(approach_dist, finger_width), voxel_size**3, 2*finger_width,
+ * collision_thresh, empty_thresh}: the Python floats of the reference expressions.  Thresholds and volumes are evaluated in
+ * the grasp arrays' dtype with the constants cast to it first, left to right, as numpy does; compares and IoU divisions
+ * are fp64.  mask [g] u8 (required) = global_iou > collision_thresh; optional: empty [g] u8 = inner_count / inner_volume <
+ * empty_thresh, ious [5,g] f64 = {global, left, right, bottom, shifting}, counts [g,6] i64.  Bit-identical to the reference
+ * for f32 and f64 grasp groups. */
+GB_API int gb_collision_detect(const double *points, int np, const void *grasps, int dtype, int g, int row_stride, int oT, int oR,
+                        int oH, int oD, int oW, const double *params, unsigned char *mask, unsigned char *empty, double *ious,
+                        int64_t *counts, gb_stream_t stream);
+
 /* The per-voxel means of the voxel down-sampling in ModelFreeCollisionDetector.__init__ (collision_detector.py:11-14, open3d
  * PointCloud.voxel_down_sample).  points [n,3] f64; order [n] i64 = point indices grouped by voxel, input order
  * kept inside a voxel; seg [v+1] i64 = first position of every voxel in `order`.  out [v,3] f64 = the sequential fp64 sum

@@ -220,9 +220,11 @@ FINGER_LENGTH = 0.06  # collision_detector.py:9
 def collision_thresholds(heights, depths, widths, approach_dist):
     """The ten per-grasp half-space thresholds, evaluated with the reference's own numpy expressions
     (collision_detector.py:26-35) so that they are bit-identical to what `detect` compares against."""
-    heights = np.asarray(heights, dtype=np.float64)[:, np.newaxis]
-    depths = np.asarray(depths, dtype=np.float64)[:, np.newaxis]
-    widths = np.asarray(widths, dtype=np.float64)[:, np.newaxis]
+    # the arrays keep their dtype (float32 for a graspnetAPI GraspGroup built from network output): numpy then evaluates the
+    # expressions in that dtype, as it does for the reference; the results widen to float64 exactly
+    heights = np.asarray(heights)[:, np.newaxis]
+    depths = np.asarray(depths)[:, np.newaxis]
+    widths = np.asarray(widths)[:, np.newaxis]
     fw, fl = FINGER_WIDTH, FINGER_LENGTH
     thr = np.concatenate([
         -heights / 2, heights / 2,
@@ -249,8 +251,8 @@ def collision_finish(counts, heights, depths, widths, voxel_size, approach_dist,
                      return_empty_grasp=False, empty_thresh=0.01, return_ious=False):
     """collision_detector.py:43-64: volumes, IoUs, thresholds and the return-shape convention, from the counts."""
     fw, fl = FINGER_WIDTH, FINGER_LENGTH
-    heights = np.asarray(heights, dtype=np.float64)[:, np.newaxis]
-    widths = np.asarray(widths, dtype=np.float64)[:, np.newaxis]
+    heights = np.asarray(heights)[:, np.newaxis]  # dtype kept: the reference's volumes are float32 for float32 grasp groups
+    widths = np.asarray(widths)[:, np.newaxis]
     left_right_volume = (heights * fl * fw / (voxel_size ** 3)).reshape(-1)
     bottom_volume = (heights * (widths + 2 * fw) * fw / (voxel_size ** 3)).reshape(-1)
     shifting_volume = (heights * (widths + 2 * fw) * approach_dist / (voxel_size ** 3)).reshape(-1)

@@ -40,10 +40,13 @@ from graspbalance_b200 import scenes  # noqa: E402
 
 def main():
     out = {}
-    for tag, (seed, n, g, voxel) in {"a": (11, 6000, 192, 0.01), "b": (12, 4000, 128, 0.005)}.items():
+    # a, b: small; c: BASELINE config 1 as written (20k-point scene, voxel 0.01, 1024 grasps); d: a float32 grasp group (what
+    # graspnetAPI builds from network output: the reference then evaluates thresholds and volumes in float32)
+    for tag, (seed, n, g, voxel, dtype) in {"a": (11, 6000, 192, 0.01, np.float64), "b": (12, 4000, 128, 0.005, np.float64),
+                                            "c": (13, 20000, 1024, 0.01, np.float64), "d": (14, 8000, 256, 0.01, np.float32)}.items():
         raw = scenes.tabletop_scene(seed, n).astype(np.float64)
         pts = oracle.voxel_down_sample(raw, voxel)
-        gs = scenes.grasp_set(seed + 100, pts, g)
+        gs = {k: np.ascontiguousarray(v.astype(dtype)) for k, v in scenes.grasp_set(seed + 100, pts, g).items()}
         det = ref_cd.ModelFreeCollisionDetector(pts, voxel_size=voxel)
         assert det.scene_points.shape == pts.shape
         gg = scenes.GraspGroupStandIn(**gs)
@@ -51,7 +54,12 @@ def main():
         full = det.detect(gg, approach_dist=0.05, collision_thresh=0.01, return_empty_grasp=True,
                           empty_thresh=0.01, return_ious=True)
         assert (plain == full[0]).all()
-        out.update({f"{tag}_points": pts, f"{tag}_voxel": np.float64(voxel),
+        if tag in "cd":  # keep the fixture small: the scene is regenerated from its seed by the test
+            out.update({f"{tag}_seed": np.int64(seed), f"{tag}_n": np.int64(n), f"{tag}_points_shape": np.array(pts.shape),
+                        f"{tag}_points_sum": pts.sum(0)})
+        else:
+            out[f"{tag}_points"] = pts
+        out.update({f"{tag}_voxel": np.float64(voxel),
                     **{f"{tag}_{k}": v for k, v in gs.items()},
                     f"{tag}_collision": full[0], f"{tag}_empty": full[1], f"{tag}_ious": np.stack(full[2])})
         print(tag, pts.shape, "collisions", int(full[0].sum()), "empty", int(full[1].sum()))

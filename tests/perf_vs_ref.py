@@ -195,7 +195,8 @@ def main():
     det = ModelFreeCollisionDetector(raw, voxel_size=0.01, device=dev)
     gs = scenes.grasp_set(4, det.scene_points, 1024)
     gg = scenes.GraspGroupStandIn(**gs)
-    thr = det._thresholds(gs["heights"][:, None], gs["depths"][:, None], gs["widths"][:, None], 0.03)
+    import oracle
+    thr = oracle.collision_thresholds(gs["heights"], gs["depths"], gs["widths"], 0.03)
     Td, Rd, thd = (torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (gs["translations"], gs["rotation_matrices"], thr))
     npts = det.scene_points.shape[0]
     add(f"collision counts G=1024 N'={npts} (kernel)", lambda: collision_counts(det._scene_dev, Td, Rd, thd), scenes_n=1,
@@ -206,7 +207,8 @@ def main():
     rows.append({"op": "collision detect() e2e host->host", "us": round((time.perf_counter() - t0) / 5 * 1e6, 1)})
     print(json.dumps(rows[-1]), flush=True)
     # BASELINE config 1 end to end: constructor (voxel down-sample of the raw 20k-point scene) + detect, host arrays in, mask out
-    from graspbalance_b200.collision_detector import voxel_down_sample
+    import oracle
+    voxel_down_sample = oracle.voxel_down_sample
     for _ in range(2):
         ModelFreeCollisionDetector(raw, voxel_size=0.01, device=dev).detect(gg)
     t0 = time.perf_counter()

@@ -541,23 +541,56 @@ def test_knn_full_size_vs_reference(dev, ref_c):
 
 
 # ---------------------------------------------------------------------------------------------------------- collision
-def test_collision_vs_golden_and_oracle(dev):
+def _detector_on(pts, voxel, dev):
+    """A detector whose (already down-sampled) scene is given: what the goldens pin is `detect` itself."""
+    det = ModelFreeCollisionDetector.__new__(ModelFreeCollisionDetector)
+    det.finger_width, det.finger_length, det.voxel_size, det.device = 0.01, 0.06, voxel, dev
+    det._scene_dev, det._scene_host = T(pts, dev), pts
+    return det
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c", "d"])
+def test_collision_vs_golden_and_oracle(dev, tag):
+    """detect() against the outputs of the reference's own collision_detector.py (tests/golden/make_golden_collision.py):
+    a, b small scenes; c = BASELINE config 1 as written (20k-point scene, voxel 0.01, 1024 grasps); d = a float32 grasp group,
+    for which the reference evaluates thresholds and volumes in float32.  Masks and all five IoU arrays bit-identical, through
+    the duck-typed attributes, through a graspnetAPI-style [G,17] grasp_group_array, and with the arrays on the device."""
     import os
+    from test_oracle_cpu import golden_scene
     z = np.load(os.path.join(os.path.dirname(__file__), "golden", "collision_ref.npz"))
-    for tag in "ab":
-        pts, voxel = z[tag + "_points"], float(z[tag + "_voxel"])
-        det = ModelFreeCollisionDetector.__new__(ModelFreeCollisionDetector)
-        det.finger_width, det.finger_length, det.voxel_size = 0.01, 0.06, voxel
-        det.scene_points, det.device = pts, dev
-        det._scene_dev = T(pts, dev)
-        gg = scenes.GraspGroupStandIn(z[tag + "_translations"], z[tag + "_rotation_matrices"], z[tag + "_heights"],
-                                      z[tag + "_depths"], z[tag + "_widths"])
-        plain = det.detect(gg, approach_dist=0.05, collision_thresh=0.01)
-        full = det.detect(gg, approach_dist=0.05, collision_thresh=0.01, return_empty_grasp=True, return_ious=True)
-        assert plain.dtype == np.bool_ and (plain == z[tag + "_collision"]).all()
-        assert (full[0] == z[tag + "_collision"]).all() and (full[1] == z[tag + "_empty"]).all()
+    pts, voxel = golden_scene(z, tag), float(z[tag + "_voxel"])
+    det = _detector_on(pts, voxel, dev)
+    Tr, Rm, h, d, w = (z[tag + k] for k in ("_translations", "_rotation_matrices", "_heights", "_depths", "_widths"))
+    gg = scenes.GraspGroupStandIn(Tr, Rm, h, d, w)
+    plain = det.detect(gg, approach_dist=0.05, collision_thresh=0.01)
+    assert isinstance(plain, np.ndarray) and plain.dtype == np.bool_ and (plain == z[tag + "_collision"]).all()
+
+    def check(full):
+        assert (np.asarray(full[0]) == z[tag + "_collision"]).all() and (np.asarray(full[1]) == z[tag + "_empty"]).all()
+        assert full[0].dtype == np.bool_ and full[1].dtype == np.bool_
         for a, b in zip(full[2], z[tag + "_ious"]):
+            assert a.dtype == np.float64
             np.testing.assert_array_equal(a, b)
+    check(det.detect(gg, approach_dist=0.05, collision_thresh=0.01, return_empty_grasp=True, return_ious=True))
+    # graspnetAPI layout: [score, width, height, depth, R(9), T(3), object id], uploaded as it is
+    G = Tr.shape[0]
+    arr = np.zeros((G, 17), dtype=Tr.dtype)
+    arr[:, 1], arr[:, 2], arr[:, 3], arr[:, 4:13], arr[:, 13:16], arr[:, 16] = w, h, d, Rm.reshape(G, 9), Tr, -1
+    gg17 = scenes.GraspGroupStandIn(Tr, Rm, h, d, w)
+    gg17.grasp_group_array = arr
+    check(det.detect(gg17, approach_dist=0.05, collision_thresh=0.01, return_empty_grasp=True, return_ious=True))
+    # network output that never leaves the device (modules.pred_decode emits this array): CUDA tensors in, CUDA tensors out
+    on_dev = det.detect_device(T(arr, dev), approach_dist=0.05, collision_thresh=0.01, return_empty_grasp=True, return_ious=True)
+    assert on_dev[0].is_cuda and on_dev[0].dtype == torch.bool
+    check([on_dev[0].cpu().numpy(), on_dev[1].cpu().numpy(), [x.cpu().numpy() for x in on_dev[2]]])
+    ggd = scenes.GraspGroupStandIn(T(Tr, dev), T(Rm, dev), T(h, dev), T(d, dev), T(w, dev))
+    on_dev = det.detect(ggd, approach_dist=0.05, collision_thresh=0.01, return_empty_grasp=True, return_ious=True)
+    check([on_dev[0].cpu().numpy(), on_dev[1].cpu().numpy(), [x.cpu().numpy() for x in on_dev[2]]])
+
+
+def test_collision_detector_refuses_cpu_devices():
+    with pytest.raises(RuntimeError, match="CPU not supported"):
+        ModelFreeCollisionDetector(np.zeros((10, 3)), voxel_size=0.01, device="cpu")
 
 
 def test_collision_full_size_vs_oracle(dev):
@@ -581,7 +614,7 @@ def test_collision_counts_batched_equals_one_launch_per_scene(dev):
     for sid, n in ((3, 20000), (4, 6000), (5, 300), (6, 20000)):  # scenes of different sizes after down-sampling
         det = ModelFreeCollisionDetector(scenes.tabletop_scene(sid, n).astype(np.float64), voxel_size=0.01, device=dev)
         gs = scenes.grasp_set(sid, det.scene_points, 96)
-        thr = det._thresholds(gs["heights"][:, None], gs["depths"][:, None], gs["widths"][:, None], 0.03)
+        thr = oracle.collision_thresholds(gs["heights"], gs["depths"], gs["widths"], 0.03)
         dets.append(det); Ts.append(gs["translations"]); Rs.append(gs["rotation_matrices"]); thrs.append(thr)
     Td, Rd, thd = (T(np.ascontiguousarray(np.stack(a)), dev) for a in (Ts, Rs, thrs))
     got = collision_counts_batched([d._scene_dev for d in dets], Td, Rd, thd)
@@ -594,9 +627,10 @@ def test_collision_counts_batched_equals_one_launch_per_scene(dev):
 @pytest.mark.parametrize("n,voxel,kind", [(20000, 0.01, "tabletop"), (20000, 0.005, "tabletop"), (5000, 0.05, "uniform"), (1, 0.01, "uniform"),
                                            (3000, 1e-4, "uniform")])
 def test_voxel_down_sample_gpu_matches_the_host_restatement(dev, n, voxel, kind):
-    """voxel_down_sample_gpu (torch sort + gb_voxel_means) == the numpy restatement of open3d's voxel_down_sample: the same
-    set of voxel means, bit for bit (sequential fp64 sums in input order); only the order of the voxels differs."""
-    from graspbalance_b200.collision_detector import voxel_down_sample, voxel_down_sample_gpu
+    """voxel_down_sample_gpu (torch sort + gb_voxel_means) == the oracle's numpy restatement of open3d's voxel_down_sample: the
+    same set of voxel means, bit for bit (sequential fp64 sums in input order); only the order of the voxels differs."""
+    from graspbalance_b200.collision_detector import voxel_down_sample_gpu
+    voxel_down_sample = oracle.voxel_down_sample
     pts = scenes.scene_batch([9], n, kind)[0].astype(np.float64)
     pts[n // 2:n // 2 + min(50, n // 3)] = pts[:min(50, n // 3)]  # duplicates share a voxel
     got = voxel_down_sample_gpu(T(pts, dev), voxel).cpu().numpy()

@@ -42,3 +42,44 @@ def test_fused_grasp_crops_match_the_sixteen_separate_calls(dev):
     assert abs(sums[0][0] - sums[1][0]) <= 1e-4 * max(1.0, abs(sums[0][0]))
     np.testing.assert_array_equal(sums[0][1], sums[1][1])  # FPS + gather in one launch: same samples
     assert abs(sums[0][2] - sums[1][2]) <= 1e-4 * max(1.0, abs(sums[0][2]))
+
+
+def test_whole_chain_matches_the_reference_extensions_tensor_by_tensor(dev, ref_a, ref_b):
+    """BASELINE config 5's op chain (SA1-4, 15 InvResMLP groupings, FP1/FP2/up-sampling, 16 grasp crops; forward + backward)
+    through OpPipeline and through the UNMODIFIED reference extensions with the reference's own torch glue
+    (oracle/ref_chain.py), on the same scenes and the same stand-in features / gradients: every index tensor and forward
+    tensor bit-equal (rotated crop coordinates to 1e-6: cuBLAS owns that sum), every gradient within 1e-5 relative."""
+    import bench
+    from graspbalance_b200 import pipeline
+    from oracle import ref_chain
+    B = 2
+    host, offs = bench.make_host_inputs([11, 12], pin=False)
+    xyz, rot, _ = bench.to_device(host, offs, dev)
+    want = {}
+    pipe = pipeline.OpPipeline(B, bench.N_POINTS, dev, seed=5, backward=True, overlap=False)
+    ref_chain.run(pipe, xyz, rot, ref_a, ref_b, collect=want)
+    for fused in (True, False):
+        pipe.fused_crops = pipe.fused_sampling = fused
+        got = {}
+        pipe.run(xyz, rot, None, collect=got)
+        torch.cuda.synchronize()
+        assert set(want) - set(got) <= {k for k in want if k.startswith("crop") and k.endswith("_idx")}, sorted(set(want) - set(got))
+        for k, w in want.items():
+            if k not in got:
+                continue
+            g = got[k]
+            assert g.shape == w.shape and g.dtype == w.dtype, (k, g.shape, w.shape, g.dtype, w.dtype)
+            if k.endswith("_grad"):
+                scale = max(float(w.abs().max()), 1e-30)
+                assert float((g - w).abs().max()) <= 1e-5 * scale, (k, float((g - w).abs().max()), scale)
+            elif k.startswith("crop"):
+                assert float((g - w).abs().max()) <= 1e-6, (k, float((g - w).abs().max()))
+            else:
+                assert torch.equal(g, w), k
+    # the crops' index lists, which the fused path does not return: the product's own cylinder_query against the reference's
+    from graspbalance_b200 import pointnet2_utils as pu
+    seed = want["sa1_xyz"]
+    rot9 = rot.reshape(B, -1, 9).contiguous()
+    for k, radius in enumerate(pipeline.CROP_RADII):
+        for d, hmax in enumerate(pipeline.CROP_HMAX):
+            assert torch.equal(pu.cylinder_query(radius, pipeline.CROP_HMIN, hmax, 64, xyz, seed, rot9), want[f"crop{k}_{d}_idx"])

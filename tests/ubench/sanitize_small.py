@@ -6,6 +6,8 @@ means, the degree-sorted backward, the aligned forward partition, three_nn + wei
 import os, sys
 import numpy as np
 import torch
+
+import oracle  # noqa: E402 (test infrastructure)
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from graspbalance_b200 import _ext as A, pointnet2_utils as pu, scenes
@@ -34,7 +36,7 @@ g = pu.grouping_operation(feats, idx)
 g.backward(torch.randn_like(g))
 dets = [ModelFreeCollisionDetector(xyz[b].double().cpu().numpy(), voxel_size=0.01, device=dev) for b in range(B)]
 gs = [scenes.grasp_set(b, dets[b].scene_points, 32) for b in range(B)]
-thr = [dets[b]._thresholds(gs[b]["heights"][:, None], gs[b]["depths"][:, None], gs[b]["widths"][:, None], 0.03) for b in range(B)]
+thr = [oracle.collision_thresholds(gs[b]["heights"], gs[b]["depths"], gs[b]["widths"], 0.03) for b in range(B)]
 T_, R_, H_ = (torch.from_numpy(np.ascontiguousarray(np.stack(a))).to(dev) for a in ([x["translations"] for x in gs], [x["rotation_matrices"] for x in gs], thr))
 cnt = collision_counts_batched([d._scene_dev for d in dets], T_, R_, H_)
 torch.cuda.synchronize()
