@@ -515,6 +515,7 @@ def main():
     ap.add_argument("--no-backward", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-prefetch", action="store_true", help="every step runs its own sampling chain first (no cross-step pipelining)")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling leg (32 scenes in total over the N GPUs)")
     ap.add_argument("--strong-total", type=int, default=32, help="scenes in total of the strong-scaling leg")
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the reference-kernels leg (oracle/_ref on this GPU)")
@@ -554,10 +555,25 @@ def main():
                                fused_crops=not args.unfused_crops)
     gather_buf = torch.empty((world * B, pipeline.NUM_SEED + 6 * pipeline.NUM_GRASP), dtype=torch.int64, device=dev) if world > 1 else None
 
-    def step(resident, inputs=None):
+    # cross-step pipelining of the sampling chain (4 x FPS + gather: ~2 ms of dependent rounds that every other operator of a
+    # step waits for, but which needs the coordinates only): step k launches the chain of step k + 1 on the sampling stream
+    # beside its own grouping work, into the other of two sample-buffer sets.  Every step still runs exactly one chain.
+    pf = {"on": not args.no_prefetch, "k": 0, "bufs": [pipe.alloc_samples(), pipe.alloc_samples()]}
+
+    def prime_prefetch(xyz):
+        pf["k"] = 0
+        pipe.sampling_chain(xyz, pf["bufs"][0])
+
+    def step(resident, inputs=None, next_xyz=None, next_ready=None):
         """One pipeline pass over device-resident inputs; returns the per-scene result tensor and the checksums."""
         xyz, rot, grasps = inputs
-        out = pipe.run(xyz, rot, grasps)
+        if pf["on"]:
+            k = pf["k"]
+            pf["k"] = k + 1
+            out = pipe.run(xyz, rot, grasps, samples=pf["bufs"][k % 2],
+                           prefetch=(xyz if next_xyz is None else next_xyz, pf["bufs"][(k + 1) % 2], next_ready))
+        else:
+            out = pipe.run(xyz, rot, grasps)
         result = torch.cat([out["seed_inds"].to(torch.int64), out["collision_counts"].reshape(B, -1)], dim=1)
         if world > 1:
             sharding.gather_scene_outputs(result, world, gather_buf)  # NCCL: gather per-scene outputs only
@@ -595,12 +611,17 @@ def main():
             return ev
 
         ready = upload(0)
+        if pf["on"]:
+            main.wait_event(ready)
+            prime_prefetch(e2e_bufs[0]["inputs"][0])  # the first step's chain (every later one is launched a step ahead)
         for k in range(n_steps):
             buf = e2e_bufs[k % 2]
             main.wait_event(ready)
+            nxt = None
             if k + 1 < n_steps:
                 ready = upload(k + 1)
-            result, chk = step(False, buf["inputs"])
+                nxt = e2e_bufs[(k + 1) % 2]["inputs"][0]
+            result, chk = step(False, buf["inputs"], nxt, ready if nxt is not None else None)
             done = torch.cuda.Event()
             done.record(main)
             buf["free"] = done
@@ -644,6 +665,7 @@ def main():
 
     resident_inputs = to_device(host, offs, dev)
     torch.cuda.synchronize()
+    prime_prefetch(resident_inputs[0])
     for _ in range(args.warmup):
         step(True, resident_inputs)
     # allocator priming (untimed, on top of the W warm-up steps): the caching allocator keeps growing its pools for a few
@@ -694,13 +716,24 @@ def main():
     clocks = sampler.stop(tw0, tw1) if rank == 0 else None
     value = world * B * args.steps / (ms * 1e-3)
 
+    # ---- the same K steps without the cross-step pipelining (every step runs its own sampling chain first) ----
+    no_pf = None
+    if pf["on"]:
+        pf["on"] = False
+        for _ in range(2):
+            step(True, resident_inputs)
+        ms_np, _, _ = timed(args.steps, True, resident_inputs)
+        no_pf = {"ms_per_step": ms_np / args.steps, "value": world * B * args.steps / (ms_np * 1e-3), "unit": UNIT}
+        pf["on"] = True
+
     # ---- roofline pass: the same K steps again with CUDA events around every libgbops call, on ONE stream (the side
     # streams of the overlapped schedule would make the bracketed durations overlap each other) ----
     _lib.PROFILER = {}
-    overlap, pipe.overlap = pipe.overlap, False
+    overlap, pipe.overlap, pf_on, pf["on"] = pipe.overlap, False, pf["on"], False
     ms_prof, _, _ = timed(args.steps, True, resident_inputs)
-    pipe.overlap = overlap
+    pipe.overlap, pf["on"] = overlap, pf_on
     prof, _lib.PROFILER = _lib.PROFILER, None
+    prime_prefetch(resident_inputs[0])
 
     # ---- e2e: host buffers in, results out, every step ----
     e2e = None
@@ -733,29 +766,38 @@ def main():
         s_gather = torch.empty((total, pipeline.NUM_SEED + 6 * pipeline.NUM_GRASP), dtype=torch.int64, device=dev) if world > 1 else None
         equal_shards = all(e - b == Bs for b, e in sharding.shard_batch(total, world))
 
-        def s_step():
-            out = s_pipe.run(*s_inputs)
+        s_bufs = [s_pipe.alloc_samples(), s_pipe.alloc_samples()]
+
+        def s_step(k):
+            if args.no_prefetch:
+                out = s_pipe.run(*s_inputs)
+            else:  # graph k % 2 consumes sample set k % 2 and fills the other one for the next replay
+                out = s_pipe.run(*s_inputs, samples=s_bufs[k % 2], prefetch=(s_inputs[0], s_bufs[(k + 1) % 2]))
             return torch.cat([out["seed_inds"].to(torch.int64), out["collision_counts"].reshape(Bs, -1)], dim=1)
 
         side = torch.cuda.Stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
-            for _ in range(3):
-                s_step()
+            s_pipe.sampling_chain(s_inputs[0], s_bufs[0])
+            for k in range(4):
+                s_step(k)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize()
-        graph = torch.cuda.CUDAGraph()
+        graphs, s_results = [], []
         launches_g0 = _lib.launch_count()
-        with torch.cuda.graph(graph, stream=side):
-            s_result = s_step()
-        launches_graph = _lib.launch_count() - launches_g0
+        for k in range(1 if args.no_prefetch else 2):
+            g_ = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_, stream=side):
+                s_results.append(s_step(k))
+            graphs.append(g_)
+        launches_graph = (_lib.launch_count() - launches_g0) // len(graphs)
         torch.cuda.synchronize()
 
         def s_loop(n_steps):
-            for _ in range(n_steps):
-                graph.replay()
+            for k in range(n_steps):
+                graphs[k % len(graphs)].replay()
                 if world > 1 and equal_shards:
-                    sharding.gather_scene_outputs(s_result, world, s_gather)
+                    sharding.gather_scene_outputs(s_results[k % len(graphs)], world, s_gather)
 
         s_loop(max(args.warmup, 3))
         ms_s, _, _ = timed(args.steps, s_loop)
@@ -763,7 +805,8 @@ def main():
                   "value": total * args.steps / (ms_s * 1e-3), "unit": UNIT, "cuda_graph": True,
                   "launches_per_step": int(launches_graph),
                   "note": "same step as `value`, one CUDA-graph replay per step; efficiency = value(N) / value(1) across the driver's runs"}
-        del graph
+        strong["prefetch"] = not args.no_prefetch
+        del graphs
 
     if rank != 0:
         if world > 1:
@@ -832,12 +875,14 @@ def main():
             "config": {"workload": workload_name(args), "scenes_per_gpu": B, "n_points": N_POINTS, "parallelism": f"scene-sharded x{world}",
                        "headline": "`value` / `e2e` = 32 scenes per GPU (weak scaling: the configuration that fills a B200); `strong` = BASELINE config 5 as written, 32 scenes in total over the N GPUs",
                        "streams": "sampling chain + collision tests on side streams" if pipe.overlap else "single stream",
+                       "sampling": ("the sampling chain of step k + 1 runs beside step k (it needs the coordinates only); `no_prefetch` = every step samples first"
+                                    if pf["on"] else "every step runs its own sampling chain first"),
                        "l2": "per-step working set (>10 GB of grouped features) exceeds the 126 MB L2; no explicit flush",
                        "algorithmic_bytes_per_scene": int(sum(algo.values())),
                        "allocator_priming_steps": prime_steps, "device_allocs_in_timed_region": int(dev_allocs_timed),
                        "step_diagnostics": step_diag},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-            "strong": strong, "gpu_baseline": gpu_base, "configs": cfgs, "arithmetic_peaks": peaks, "kernel_notes": notes,
+            "no_prefetch": no_pf, "strong": strong, "gpu_baseline": gpu_base, "configs": cfgs, "arithmetic_peaks": peaks, "kernel_notes": notes,
             "roofline_pass_ms_per_step": ms_prof / args.steps,
             "pipeline_hbm_frac": (sum(algo.values()) * world * B * args.steps / (ms * 1e-3) / 1e9) / (peak * world),
             "per_op": per_op}

@@ -122,11 +122,30 @@ class OpPipeline:
         up = self._interp(xyz, sa2_xyz, self.fp_feats[2], self.fp_grads[2] if bw else None, collect, "fp2")
         out["up_checksum"] = up[:, :4, :256].sum()
 
-    def run(self, xyz, view_rot, grasps=None, collect=None):
+    def alloc_samples(self):
+        """Static buffers for one sampling chain: [(inds [B,npoint] i32, new_xyz [B,npoint,3] f32)] per SA level."""
+        return [(torch.empty((self.B, m), dtype=torch.int32, device=self.device),
+                 torch.empty((self.B, m, 3), dtype=torch.float32, device=self.device)) for (m, _, _, _) in SA_SPECS]
+
+    def sampling_chain(self, xyz, into):
+        """The four furthest_point_sample + gather_operation calls of a step (pointnet2_modules.py:151-158), which depend on
+        the coordinates only, on the CURRENT stream, results written into the buffers of alloc_samples()."""
+        cur = xyz
+        for (inds_buf, xyz_buf), (npoint, _, _, _) in zip(into, SA_SPECS):
+            inds, new_xyz = pu.furthest_point_sample_xyz(cur, npoint)
+            inds_buf.copy_(inds)
+            xyz_buf.copy_(new_xyz)
+            cur = xyz_buf
+
+    def run(self, xyz, view_rot, grasps=None, collect=None, samples=None, prefetch=None):
         """xyz [B,N,3] f32 CUDA; view_rot [B,1024,3,3] f32 CUDA (approach frames of the seeds); grasps = optional dict of
         per-scene fp64 CUDA tensors {scene_points: list of [N'_b,3], T [B,G,3], R [B,G,3,3], thr [B,G,10]}.
         Returns a dict of the per-scene outputs a caller would keep.  collect: optional dict that receives every index
-        tensor, forward tensor and gradient of the chain (parity tests; costs two extra query launches per level)."""
+        tensor, forward tensor and gradient of the chain (parity tests; costs two extra query launches per level).
+        Cross-step pipelining of the latency-bound sampling chain (it depends on the coordinates only, which a data loader
+        has one step ahead): samples = buffers a previous call filled (then this step launches no FPS of its own);
+        prefetch = (next_xyz, buffers[, event that next_xyz is ready]): the NEXT step's chain runs on the sampling stream
+        beside this step's work."""
         bw = self.backward
         out = {}
         if collect is not None and self.overlap:
@@ -145,28 +164,35 @@ class OpPipeline:
             return torch.stack([collision_counts(grasps["scene_points"][b], grasps["T"][b], grasps["R"][b], grasps["thr"][b])
                                 for b in range(len(grasps["scene_points"]))])
 
-        samples, col_done = [], None
+        col_done, prefetch_done = None, None
+        given = samples is not None
+        if given:  # filled by an earlier call that has finished on this stream's timeline: nothing to wait for
+            samples = [(i, x, None) for (i, x) in samples]
+        else:
+            samples = []
         if self.overlap:
             start = torch.cuda.Event()
             start.record(main)
             self._fps_stream.wait_event(start)
-            with torch.cuda.stream(self._fps_stream):
-                cur = xyz
-                for (npoint, _, _, _) in SA_SPECS:
-                    inds, new_xyz = sample(cur, npoint)
-                    ev = torch.cuda.Event()
-                    ev.record(self._fps_stream)
-                    inds.record_stream(main), new_xyz.record_stream(main)
-                    samples.append((inds, new_xyz, ev))
-                    cur = new_xyz
+            if not given:
+                with torch.cuda.stream(self._fps_stream):
+                    cur = xyz
+                    for (npoint, _, _, _) in SA_SPECS:
+                        inds, new_xyz = sample(cur, npoint)
+                        ev = torch.cuda.Event()
+                        ev.record(self._fps_stream)
+                        inds.record_stream(main), new_xyz.record_stream(main)
+                        samples.append((inds, new_xyz, ev))
+                        cur = new_xyz
 
         aux_done = None
         cur_xyz, level_xyz = xyz, []
         for lvl, (npoint, radius, nsample, c_in) in enumerate(SA_SPECS):
             # ---- SA module (variant A) ----
-            if self.overlap:
+            if self.overlap or given:
                 inds, new_xyz, ev = samples[lvl]
-                main.wait_event(ev)
+                if ev is not None:
+                    main.wait_event(ev)
             else:
                 inds, new_xyz = sample(cur_xyz, npoint)
             feats = self.sa_in_feats[lvl]
@@ -201,10 +227,20 @@ class OpPipeline:
                         out["collision_counts"].record_stream(main)
                         col_done = torch.cuda.Event()
                         col_done.record(self._col_stream)
-                self._aux_stream.wait_event(samples[1][2])
+                if prefetch is not None:  # the next step's sampling chain: enqueued behind this step's critical path
+                    with torch.cuda.stream(self._fps_stream):
+                        if len(prefetch) > 2 and prefetch[2] is not None:
+                            self._fps_stream.wait_event(prefetch[2])  # the next step's coordinates have arrived
+                        self.sampling_chain(prefetch[0], prefetch[1])
+                        prefetch_done = torch.cuda.Event()
+                        prefetch_done.record(self._fps_stream)
+                self._aux_stream.wait_event(start)
+                if samples[1][2] is not None:
+                    self._aux_stream.wait_event(samples[1][2])
                 with torch.cuda.stream(self._aux_stream):
                     self._crops(xyz, view_rot, samples[1][1], out)
-                    self._aux_stream.wait_event(samples[3][2])
+                    if samples[3][2] is not None:
+                        self._aux_stream.wait_event(samples[3][2])
                     self._interpolation(xyz, samples[1][1], samples[2][1], samples[3][1], out)
                     for k in ("up_checksum", "crop_checksum"):
                         out[k].record_stream(main)
@@ -217,6 +253,12 @@ class OpPipeline:
             self._crops(xyz, view_rot, sa2_xyz, out, collect)
         if aux_done is not None:
             main.wait_event(aux_done)
+        if prefetch_done is not None:
+            main.wait_event(prefetch_done)
+        elif prefetch is not None:  # single-stream schedule
+            if len(prefetch) > 2 and prefetch[2] is not None:
+                torch.cuda.current_stream(self.device).wait_event(prefetch[2])
+            self.sampling_chain(prefetch[0], prefetch[1])
         # ---- collision test ----
         if col_done is not None:
             main.wait_event(col_done)

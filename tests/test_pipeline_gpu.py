@@ -83,3 +83,33 @@ def test_whole_chain_matches_the_reference_extensions_tensor_by_tensor(dev, ref_
     for k, radius in enumerate(pipeline.CROP_RADII):
         for d, hmax in enumerate(pipeline.CROP_HMAX):
             assert torch.equal(pu.cylinder_query(radius, pipeline.CROP_HMIN, hmax, 64, xyz, seed, rot9), want[f"crop{k}_{d}_idx"])
+
+
+def test_cross_step_sampling_prefetch_returns_the_same_results(dev):
+    """Step k launching step k + 1's sampling chain on the side stream (OpPipeline.run(samples=, prefetch=)) changes the
+    schedule only: seeds, collision counts and checksums equal the plain run's, step after step, with different scenes in
+    consecutive steps."""
+    import bench
+    from graspbalance_b200 import pipeline
+    B = 2
+    batches = []
+    for ids in ([21, 22], [23, 24], [25, 26]):
+        host, offs = bench.make_host_inputs(ids, pin=False)
+        batches.append(bench.to_device(host, offs, dev))
+    pipe = pipeline.OpPipeline(B, bench.N_POINTS, dev, seed=1, backward=True, overlap=True)
+    plain = []
+    for inp in batches:
+        o = pipe.run(*inp)
+        torch.cuda.synchronize()
+        plain.append({k: v.detach().cpu().numpy() for k, v in o.items()})
+    bufs = [pipe.alloc_samples(), pipe.alloc_samples()]
+    pipe.sampling_chain(batches[0][0], bufs[0])
+    for k, inp in enumerate(batches):
+        nxt = batches[(k + 1) % len(batches)][0]
+        o = pipe.run(*inp, samples=bufs[k % 2], prefetch=(nxt, bufs[(k + 1) % 2]))
+        torch.cuda.synchronize()
+        got = {key: v.detach().cpu().numpy() for key, v in o.items()}
+        for key in ("sa1_inds", "seed_inds", "collision_counts"):
+            np.testing.assert_array_equal(got[key], plain[k][key])
+        for key in ("up_checksum", "crop_checksum", "grad_checksum"):
+            assert abs(float(got[key]) - float(plain[k][key])) <= 1e-4 * max(1.0, abs(float(plain[k][key]))), key
