@@ -356,13 +356,13 @@ static int floor_log2(int v) {
 using namespace gb;
 
 static int fps_impl(const float *xyz, float *temp, int *idx, float *new_xyz, int b, int n, int m, int variant, gb_stream_t stream) {
-  if (b < 0 || n <= 0 || m < 0 || (variant != GB_FPS_A && variant != GB_FPS_B)) return (int)cudaErrorInvalidValue;
+  if (b < 0 || n < 0 || m < 0 || (variant != GB_FPS_A && variant != GB_FPS_B)) return (int)cudaErrorInvalidValue;
   if (b == 0 || m == 0) return 0;  // nothing to do (empty tensors have null data pointers)
-  if (!xyz || !idx) return (int)cudaErrorInvalidValue;
+  if (n == 0 || !xyz || !idx) return (int)cudaErrorInvalidValue;  // samples of an empty cloud are undefined (the reference reads out of bounds)
   cudaStream_t s = (cudaStream_t)stream;
   // BS = opt_n_threads(n): cuda_utils.h:21-27 (cap 512) / pointnet2_batch/src/cuda_utils.h:10-14 (cap 1024).
   // floor(log2 n) computed in integers (the reference's double log() agrees for every n < 2^31 that is not within
-  // 1 ulp of a power of two from below -- checked for all n <= 2^22 in tests/test_host_logic.py).
+  // 1 ulp of a power of two from below -- checked around every power of two <= 2^22 in tests/test_cabi_and_host.py::test_block_size_formula_matches_the_reference_expression).
   const int cap = variant == GB_FPS_A ? 512 : 1024;
   int bs = 1 << floor_log2(n);
   if (bs > cap) bs = cap;

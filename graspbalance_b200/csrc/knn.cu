@@ -141,10 +141,18 @@ using namespace gb;
 
 extern "C" int gb_knn(const float *ref, const float *query, int64_t *idx, int b, int dim, int nref, int nquery, int k,
                       gb_stream_t stream) {
-  if (b < 0 || dim <= 0 || nref <= 0 || nquery < 0 || k <= 0 || k > nref || k > 1024 || dim > 256 || !ref || !query || !idx)
-    return (int)cudaErrorInvalidValue;
-  if (b == 0 || nquery == 0) return 0;
-  if (b > 65535) return (int)cudaErrorInvalidValue;
+  if (b < 0 || nquery < 0) return (int)cudaErrorInvalidValue;
+  if (b == 0 || nquery == 0) return 0;  // nothing to do (empty tensors have null data pointers)
+  if (dim <= 0 || nref <= 0 || k <= 0 || k > nref || k > 1024 || dim > 256 || !ref || !query || !idx) return (int)cudaErrorInvalidValue;
+  if (b > 65535) {  // the batch rides on gridDim.y: slabs of 65535 scenes
+    for (int b0 = 0; b0 < b; b0 += 65535) {
+      const int bb = b - b0 < 65535 ? b - b0 : 65535;
+      const int rc = gb_knn(ref + (size_t)b0 * dim * nref, query + (size_t)b0 * dim * nquery, idx + (size_t)b0 * k * nquery, bb, dim, nref,
+                            nquery, k, stream);
+      if (rc) return rc;
+    }
+    return 0;
+  }
   cudaStream_t s = (cudaStream_t)stream;
   int ts = (kKnnTileFloats / dim) & ~31;
   if (ts > 2048) ts = 2048;

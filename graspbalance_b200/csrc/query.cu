@@ -568,12 +568,24 @@ template <bool CYL, bool MULTI = false>
 static int launch_query(const float *new_xyz, const float *xyz, const float *rot, int *idx, int b, int n, int m, float radius,
                         float hmin, float hmax, int nsample, cudaStream_t s, HMax4 hm = HMax4{{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}, 1, 0ull},
                         int nd = 0) {
-  if (b < 0 || n <= 0 || m < 0 || nsample <= 0) return (int)cudaErrorInvalidValue;
-  if (b == 0 || m == 0) return 0;  // nothing to do (empty tensors have null data pointers)
-  if (!new_xyz || !xyz || !idx || (CYL && !rot)) return (int)cudaErrorInvalidValue;
+  if (b < 0 || n < 0 || m < 0 || nsample < 0) return (int)cudaErrorInvalidValue;
+  if (b == 0 || m == 0 || nsample == 0) return 0;  // nothing to do (empty tensors have null data pointers)
+  if (!idx) return (int)cudaErrorInvalidValue;
+  if (n == 0)  // an empty cloud has no hit: every slot keeps the zero the reference's zero-filled output holds
+    return (int)cudaMemsetAsync(idx, 0, (size_t)b * m * (nd > 0 ? nd : 1) * (MULTI ? hm.nr : 1) * nsample * sizeof(int), s);
+  if (!new_xyz || !xyz || (CYL && !rot)) return (int)cudaErrorInvalidValue;
+  if (b > 65535) {  // the batch rides on gridDim.y: larger batches go slab by slab
+    if (MULTI) return (int)cudaErrorInvalidValue;  // the multi-radius layout [radii, b, ...] is not contiguous per slab
+    for (int b0 = 0; b0 < b; b0 += 65535) {
+      const int bb = b - b0 < 65535 ? b - b0 : 65535;
+      const int rc = launch_query<CYL, MULTI>(new_xyz + (size_t)b0 * m * 3, xyz + (size_t)b0 * n * 3, rot ? rot + (size_t)b0 * m * 9 : nullptr,
+                                              idx + (size_t)b0 * m * nsample, bb, n, m, radius, hmin, hmax, nsample, s, hm, nd);
+      if (rc) return rc;
+    }
+    return 0;
+  }
   const float radius2 = radius * radius;  // fp32 product, as ball_query_gpu.cu:22
   const int use_bulk = (n % 4 == 0) && (((uintptr_t)xyz & 15u) == 0);
-  if (b > 65535) return (int)cudaErrorInvalidValue;
 
   // ---- cell-grid path for large clouds; the build kernel decides per scene whether the grid culls enough ----
   GridHeader *hdr = nullptr;

@@ -78,11 +78,15 @@ extern "C" int gb_three_nn(const float *unknown, const float *known, float *dist
   if (b < 0 || n < 0 || m < 0) return (int)cudaErrorInvalidValue;
   if (b == 0 || n == 0) return 0;  // nothing to do (empty tensors have null data pointers)
   if (!unknown || (m > 0 && !known) || !dist2 || !idx) return (int)cudaErrorInvalidValue;
-  if (b > 65535) return (int)cudaErrorInvalidValue;
-  dim3 grid((n + gb::kNNThreads - 1) / gb::kNNThreads, b);
-  gb::three_nn_kernel<false><<<grid, gb::kNNThreads, 0, (cudaStream_t)stream>>>(unknown, known, dist2, idx, nullptr, n, m);
-  gb::count_launch();
-  return gb::finish_launch();
+  for (int b0 = 0; b0 < b; b0 += 65535) {  // the batch rides on gridDim.y: slabs of 65535 scenes
+    const int bb = b - b0 < 65535 ? b - b0 : 65535;
+    dim3 grid((n + gb::kNNThreads - 1) / gb::kNNThreads, bb);
+    gb::three_nn_kernel<false><<<grid, gb::kNNThreads, 0, (cudaStream_t)stream>>>(unknown + (size_t)b0 * n * 3, known + (size_t)b0 * m * 3,
+                                                                                 dist2 + (size_t)b0 * n * 3, idx + (size_t)b0 * n * 3, nullptr, n, m);
+    gb::count_launch();
+    if (int rc = gb::finish_launch()) return rc;
+  }
+  return 0;
 }
 
 /* three_nn followed by the inverse-distance weights of its callers, one launch:
@@ -92,9 +96,14 @@ extern "C" int gb_three_nn_weights(const float *unknown, const float *known, flo
   if (b < 0 || n < 0 || m < 0) return (int)cudaErrorInvalidValue;
   if (b == 0 || n == 0) return 0;
   if (!unknown || (m > 0 && !known) || !dist || !idx || !weight) return (int)cudaErrorInvalidValue;
-  if (b > 65535) return (int)cudaErrorInvalidValue;
-  dim3 grid((n + gb::kNNThreads - 1) / gb::kNNThreads, b);
-  gb::three_nn_kernel<true><<<grid, gb::kNNThreads, 0, (cudaStream_t)stream>>>(unknown, known, dist, idx, weight, n, m);
-  gb::count_launch();
-  return gb::finish_launch();
+  for (int b0 = 0; b0 < b; b0 += 65535) {
+    const int bb = b - b0 < 65535 ? b - b0 : 65535;
+    dim3 grid((n + gb::kNNThreads - 1) / gb::kNNThreads, bb);
+    gb::three_nn_kernel<true><<<grid, gb::kNNThreads, 0, (cudaStream_t)stream>>>(unknown + (size_t)b0 * n * 3, known + (size_t)b0 * m * 3,
+                                                                                dist + (size_t)b0 * n * 3, idx + (size_t)b0 * n * 3,
+                                                                                weight + (size_t)b0 * n * 3, n, m);
+    gb::count_launch();
+    if (int rc = gb::finish_launch()) return rc;
+  }
+  return 0;
 }

@@ -60,9 +60,19 @@ def furthest_point_sample_segments(points, counts, nsamples):
     exactly as furthest_point_sample(set.unsqueeze(0), k)[0] samples it."""
     rows, total_points, total_out = segment_table(counts, nsamples)
     assert total_points <= points.shape[0]
-    seg = torch.tensor(rows, dtype=torch.int32).reshape(-1, 4).to(points.device)
-    return _ext.furthest_point_sampling_segments(points, seg, max((r[1] for r in rows), default=0), max((r[2] for r in rows), default=0),
-                                                 total_out)
+    # one CTA holds a segment in registers (up to SEGMENT_MAX_POINTS points); an object that owns more of the cloud than that
+    # is sampled by the cluster kernel on its own, as the reference's per-object call does (modules.py:207)
+    small = [r for r in rows if r[1] <= SEGMENT_MAX_POINTS]
+    seg = torch.tensor(small, dtype=torch.int32).reshape(-1, 4).to(points.device)
+    out = _ext.furthest_point_sampling_segments(points, seg, max((r[1] for r in small), default=0), max((r[2] for r in small), default=0),
+                                                total_out)
+    for first, c, k, slot in rows:
+        if c > SEGMENT_MAX_POINTS and k > 0:
+            out[slot:slot + k] = _ext.furthest_point_sampling(points[first:first + c].unsqueeze(0).contiguous(), k)[0]
+    return out
+
+
+SEGMENT_MAX_POINTS = 10240  # gb_fps_segments: 512 threads x 20 points
 
 
 def segment_table(counts, nsamples):

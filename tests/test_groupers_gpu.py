@@ -257,3 +257,21 @@ def test_multi_scale_group_matches_the_four_modules(dev):
     got = multi_scale_group(mods, q, x, R)
     for g, mod in zip(got, mods):
         assert torch.equal(g, mod.group(q, x, R))
+
+
+def test_empty_batches_and_empty_clouds(dev):
+    """Shapes the reference accepts: an empty batch (even with N = 0) is a no-op; a query against an empty cloud finds nothing,
+    so every slot keeps the zero of the reference's zero-filled output (ball_query.cpp:25-27, cylinder_query.cpp:27-29)."""
+    from graspbalance_b200 import _ext as gb_a, knn_modules
+    e3 = torch.zeros((0, 0, 3), device=dev)
+    assert tuple(pu.furthest_point_sample(e3, 0).shape) == (0, 0)
+    assert tuple(gb_a.ball_query(e3, e3, 0.1, 8).shape) == (0, 0, 8)
+    assert tuple(gb_a.three_nn(e3, e3)[1].shape) == (0, 0, 3)
+    assert tuple(knn_modules.knn_k(torch.zeros((0, 3, 5), device=dev), torch.zeros((0, 3, 0), device=dev), 1).shape) == (0, 1, 0)
+    new = torch.rand((2, 5, 3), device=dev)
+    none = torch.zeros((2, 0, 3), device=dev)
+    rot = torch.eye(3, device=dev).reshape(1, 1, 9).repeat(2, 5, 1).contiguous()
+    for idx in (gb_a.ball_query(new, none, 0.1, 8), gb_a.cylinder_query(new, none, rot, 0.1, -0.02, 0.04, 8)):
+        assert tuple(idx.shape) == (2, 5, 8) and idx.dtype == torch.int32 and int(idx.abs().sum()) == 0
+    with pytest.raises(RuntimeError):  # samples of an empty cloud are undefined
+        pu.furthest_point_sample(none, 4)

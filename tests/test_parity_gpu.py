@@ -379,8 +379,22 @@ def test_fps_segments_match_one_call_per_segment(dev):
             np.testing.assert_array_equal(got[slot:slot + k], alone)
         first += c
         slot += k
-    with pytest.raises(RuntimeError):  # a segment that does not fit the registers of one CTA is refused, not mis-sampled
-        pu.furthest_point_sample_segments(T(np.zeros((20000, 3), np.float32), dev), [20000], [8])
+    # the C entry point refuses a segment that does not fit the registers of one CTA (it never mis-samples) ...
+    with pytest.raises(RuntimeError):
+        seg = torch.tensor([[0, 20000, 8, 0]], dtype=torch.int32, device=dev)
+        gb_a.furthest_point_sampling_segments(T(np.zeros((20000, 3), np.float32), dev), seg, 20000, 8, 8)
+
+
+def test_fps_segments_with_an_object_larger_than_one_cta_holds(dev):
+    """... and the Python entry routes such a segment through the cluster kernel: an object that owns more than half of a
+    20k-point cloud (> 10240 points) is sampled like every other one (the reference's per-object call has no size limit,
+    TrainModel/modules.py:207)."""
+    rng = np.random.default_rng(9)
+    counts, ks = [300, 12000, 40, 15000, 0, 1024], [17, 600, 40, 424, 0, 100]
+    packed = (rng.uniform(-0.3, 0.3, (sum(counts), 3)).astype(np.float32) + np.array([0, 0, 0.5], np.float32))
+    packed[400:420] = packed[5000:5020]  # ties inside the oversize segment
+    got = pu.furthest_point_sample_segments(T(packed, dev), counts, ks).cpu().numpy()
+    np.testing.assert_array_equal(got, oracle.furthest_point_sample_segments(packed, counts, ks))
 
 
 def reference_object_balance_sampling(end_points):
