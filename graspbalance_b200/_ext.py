@@ -123,6 +123,27 @@ def three_nn_weights(unknowns, knows):
     return dist, idx, weight
 
 
+def three_interpolation(unknowns, knows, points, keep_for_backward):
+    """three_nn + weights + three_interpolate in one launch (gb_three_interpolation): unknowns [B,n,3], knows
+    [B,m,3], points [B,C,m] -> out [B,C,n]; idx and weight [B,n,3] are written only when keep_for_backward (else None).
+    Returns None when the fused kernel does not take the shape (the caller runs the two launches)."""
+    for t, name in ((unknowns, "unknowns"), (knows, "knows"), (points, "points")):
+        _contig(t, name); _is_float(t, name)
+    if unknowns.is_cuda:
+        _cuda(knows, "knows"); _cuda(points, "points")
+    _need_cuda(unknowns)
+    B, n, m = unknowns.shape[0], unknowns.shape[1], knows.shape[1]
+    C = points.shape[1]
+    if m < 1 or m > 4096 or n == 0 or B == 0:
+        return None
+    out = torch.empty((B, C, n), dtype=torch.float32, device=points.device)
+    idx = torch.empty((B, n, 3), dtype=torch.int32, device=points.device) if keep_for_backward else None
+    weight = torch.empty((B, n, 3), dtype=torch.float32, device=points.device) if keep_for_backward else None
+    _lib.call("gb_three_interpolation", points, unknowns.data_ptr(), knows.data_ptr(), points.data_ptr(), out.data_ptr(),
+              None if idx is None else idx.data_ptr(), None if weight is None else weight.data_ptr(), B, C, n, m)
+    return out, idx, weight
+
+
 def three_interpolate(points, idx, weight):
     """interpolate.cpp:47-75.  points [B,C,m], idx/weight [B,n,3] -> [B,C,n]."""
     _contig(points, "points"); _contig(idx, "idx"); _contig(weight, "weight")

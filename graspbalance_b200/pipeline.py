@@ -46,6 +46,10 @@ def _randn(shape, gen, device):
 
 class OpPipeline:
     """Holds the stand-in feature / gradient tensors (allocated once, outside any timed region) and runs the chain."""
+    # FP modules as one launch (gb_three_interpolation).  Off: measured 1.24 ms per step against 0.83 ms for three_nn_weights +
+    # three_interpolate (B200, 32 scenes) -- the brute-force search inside a 2-CTA-per-SM kernel loses more than the saved
+    # 36 bytes per point of idx / weight traffic; it stays the path that writes nothing but the output (inference).
+    fused_fp = False
 
     def __init__(self, batch, n_points=20000, device="cuda", seed=0, backward=True, overlap=True, fused_crops=True, fused_sampling=True, batched_collision=True):
         self.B, self.N, self.device, self.backward = batch, n_points, torch.device(device), backward
@@ -84,9 +88,12 @@ class OpPipeline:
     # ------------------------------------------------------------------------------------------------------------
     @staticmethod
     def _interp(unknown, known, feats, grad, collect=None, tag=""):
-        # three_nn + weights of pointnet2_modules.py:413-416 (sqrt, +1e-8, reciprocal, sum, divide) in one launch
-        _, idx, weight = pu.three_nn_weights(unknown, known)
-        out = pu.three_interpolate(feats, idx, weight)
+        # three_nn + weights of pointnet2_modules.py:413-416 (sqrt, +1e-8, reciprocal, sum, divide) + three_interpolate: one launch
+        if collect is None and OpPipeline.fused_fp:
+            out = pu.three_interpolation(unknown, known, feats)
+        else:
+            _, idx, weight = pu.three_nn_weights(unknown, known)
+            out = pu.three_interpolate(feats, idx, weight)
         if grad is not None:
             out.backward(grad)
         if collect is not None:

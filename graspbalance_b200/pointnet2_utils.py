@@ -154,6 +154,40 @@ class ThreeInterpolate(Function):
 three_interpolate = ThreeInterpolate.apply
 
 
+class ThreeInterpolation(Function):
+    """three_nn -> inverse-distance weights -> three_interpolate as ONE launch: PointnetFPModule.forward
+    (pointnet2_modules.py:413-420), upsampling.three_interpolation (upsampling.py:67-74), graspbalance.py:37-41.  dist / idx /
+    weight [B,n,3] are not materialised; idx and weight are kept (written by the same launch) only when the features need a
+    gradient.  Values are bit-identical to the three separate steps; coordinates get no gradient, as in the reference
+    (three_nn's outputs are non-differentiable there too)."""
+
+    @staticmethod
+    def forward(ctx, unknown, known, features):
+        need = features.requires_grad
+        res = _ext.three_interpolation(unknown, known, features, need)
+        if res is None:  # shape the fused kernel does not take: the two launches
+            _, idx, weight = _ext.three_nn_weights(unknown, known)
+            res = (_ext.three_interpolate(features, idx, weight), idx, weight)
+        out, idx, weight = res
+        ctx.three_interpolate_for_backward = (idx, weight, features.size(2))
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        idx, weight, m = ctx.three_interpolate_for_backward
+        return None, None, _ext.three_interpolate_grad(grad_out.contiguous(), idx, weight, m)
+
+
+def three_interpolation(unknown, known, features):
+    """Fused feature propagation; falls back to the unfused reference expression for inputs the kernels do not take."""
+    if _fusable(unknown, known) and features.is_cuda and features.dtype == torch.float32 and features.is_contiguous():
+        return ThreeInterpolation.apply(unknown, known, features)
+    dist, idx = three_nn(unknown, known)
+    dist_recip = 1.0 / (dist + 1e-8)
+    weight = dist_recip / torch.sum(dist_recip, dim=2, keepdim=True)
+    return three_interpolate(features, idx, weight)
+
+
 class GroupingOperation(Function):
     @staticmethod
     def forward(ctx, features, idx):

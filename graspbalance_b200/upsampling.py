@@ -58,7 +58,8 @@ three_interpolate = ThreeInterpolate.apply
 def three_interpolation(unknown_xyz, known_xyz, know_feat):
     """upsampling.py:67-74: inverse-distance weights over the three nearest known points.  The neighbour search and the
     weight arithmetic (sqrt, +1e-8, reciprocal, sum, divide -- five elementwise passes in the reference) are one launch
-    (gb_three_nn_weights, bit-identical values); three_nn's outputs carry no gradient in the reference either."""
+    (gb_three_nn_weights, bit-identical values); three_nn's outputs carry no gradient in the reference either.
+    pointnet2_utils.three_interpolation is the single-launch variant that writes nothing but the output."""
     from . import pointnet2_utils as pu
     if (unknown_xyz.is_cuda and unknown_xyz.dtype == torch.float32 and known_xyz.dtype == torch.float32 and unknown_xyz.is_contiguous()
             and known_xyz.is_contiguous()):

@@ -161,6 +161,16 @@ GB_API int gb_three_interp_bwd_set(const float *grad_out, const int *idx, const 
 GB_API int gb_knn(const float *ref, const float *query, int64_t *idx, int b, int dim, int nref, int nquery, int k,
            gb_stream_t stream);
 
+/* three_nn + inverse-distance weights + three_interpolate in ONE launch -- what PointnetFPModule.forward
+ * (PointNet/pointnet2_modules.py:413-420), upsampling.three_interpolation (ModifiedNetTools/upsampling.py:67-74) and the seed
+ * up-sampling of TrainModel/graspbalance.py:37-41 compute with a neighbour search, five elementwise passes and a gather.
+ * unknown [b,n,3], known [b,m,3] (1 <= m <= 4096), feats [b,c,m] -> out [b,c,n] (16-byte aligned).  idx_out / weight_out
+ * [b,n,3]: both NULL (nothing but `out` is written) or both given (three_interpolate's backward reads them).  Returns
+ * cudaErrorNotSupported (801) for shapes it does not take (callers use the two-launch path).  Bit-identical to
+ * gb_three_nn_weights followed by gb_three_interp_fwd. */
+GB_API int gb_three_interpolation(const float *unknown, const float *known, const float *feats, float *out, int *idx_out,
+                           float *weight_out, int b, int c, int n, int m, gb_stream_t stream);
+
 /* collision_detector.ModelFreeCollisionDetector.detect's grasp x point occupancy test (collision_detector.py:23-41,55),
  * all fp64.  points [np,3]; T [g,3]; R [g,3,3] row-major; thr [g,10] = the per-grasp half-space thresholds
  *   {-h/2, h/2, d-fl, d, -(w/2+fw), -w/2, w/2+fw, w/2, d-fl-fw, d-fl-fw-approach}

@@ -710,3 +710,30 @@ def test_non_contiguous_and_wrong_dtype_inputs_raise(dev):
         pu.furthest_point_sample(xyz.double(), 8)
     with pytest.raises((RuntimeError, AssertionError)):
         pu.grouping_operation(torch.randn((2, 3, 300), device=dev), torch.zeros((2, 4, 4), dtype=torch.int64, device=dev))
+
+
+@pytest.mark.parametrize("B,n,m,C", [(2, 20000, 1024, 256), (3, 1024, 512, 256), (2, 512, 256, 64), (1, 777, 5, 7), (2, 2050, 1, 4),
+                                     (1, 3, 2, 1), (2, 5000, 3000, 12)])
+def test_fused_feature_propagation_equals_the_three_steps(dev, ref_a, B, n, m, C):
+    """gb_three_interpolation (search + weights + gather in one launch) == the reference's three_nn, the weight arithmetic
+    of pointnet2_modules.py:413-416 and three_interpolate, bit for bit (values, and the idx / weight it keeps for backward);
+    gradient == three_interpolate_grad of the reference within 1e-5."""
+    unknown = T(scenes.scene_batch(range(B), n, "tabletop" if n >= 1000 else "uniform"), dev)
+    known = T(scenes.scene_batch(range(50, 50 + B), m, "tabletop" if m >= 1000 else "uniform"), dev)
+    g = torch.Generator(device="cpu").manual_seed(4)
+    feats = torch.randn((B, C, m), generator=g).to(dev)
+    d2, idx = ref_a.three_nn(unknown, known)
+    r = 1.0 / (torch.sqrt(d2) + 1e-8)
+    w = r / torch.sum(r, dim=2, keepdim=True)
+    want = ref_a.three_interpolate(feats, idx, w)
+    got_inf = pu.three_interpolation(unknown, known, feats)  # inference: nothing but the output is written
+    assert torch.equal(got_inf, want)
+    f = feats.clone().requires_grad_(True)
+    l0 = _lib.launch_count()
+    got = pu.three_interpolation(unknown, known, f)
+    assert _lib.launch_count() - l0 == 1
+    assert torch.equal(got.detach(), want)
+    go = torch.randn(want.shape, generator=g).to(dev)
+    got.backward(go)
+    assert_grad_close(f.grad.cpu().numpy(), ref_a.three_interpolate_grad(go, idx, w, m).cpu().numpy())
+    assert torch.equal(gb_up.three_interpolation(unknown, known, feats), want)  # the ModifiedNetTools entry point (two launches)
