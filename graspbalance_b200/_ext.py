@@ -254,6 +254,35 @@ def group_points(points, idx):
     return out
 
 
+def group_points_max(points, idx, need_arg=True):
+    """group_points followed by the max over nsample in one pass (gb_group_max_fwd): points [B,C,N], idx [B,npoint,nsample]
+    -> (out [B,C,npoint], arg [B,C,npoint] i32 source index of each maximum, or None).  Returns None for rows too long for
+    the kernel's shared-memory staging (the caller runs group_points + max_pool2d)."""
+    _contig(points, "points"); _contig(idx, "idx"); _is_float(points, "points"); _is_int(idx, "idx")
+    if points.is_cuda:
+        _cuda(idx, "idx")
+    _need_cuda(points)
+    B, C, N = points.shape
+    npoint, nsample = idx.shape[1], idx.shape[2]
+    if N * 16 > 200 * 1024 or nsample < 1:
+        return None
+    out = torch.empty((B, C, npoint), dtype=torch.float32, device=points.device)
+    arg = torch.empty((B, C, npoint), dtype=torch.int32, device=points.device) if need_arg else None
+    _lib.call("gb_group_max_fwd", points, points.data_ptr(), idx.data_ptr(), out.data_ptr(), None if arg is None else arg.data_ptr(),
+              B, C, N, npoint, nsample)
+    return out, arg
+
+
+def group_points_max_grad(grad_out, arg, n):
+    """Backward of group_points_max: grad_out [B,C,npoint] scattered to the winning sources -> [B,C,n]."""
+    _contig(grad_out, "grad_out"); _contig(arg, "arg"); _is_float(grad_out, "grad_out"); _is_int(arg, "arg")
+    _need_cuda(grad_out)
+    B, C, npoint = grad_out.shape
+    out = torch.zeros((B, C, int(n)), dtype=torch.float32, device=grad_out.device)
+    _lib.call("gb_group_max_bwd", grad_out, grad_out.data_ptr(), arg.data_ptr(), out.data_ptr(), B, C, int(n), npoint)
+    return out
+
+
 def group_points_grad(grad_out, idx, n):
     """group_points.cpp:49-75.  grad_out [B,C,npoints,nsample] -> [B,C,n]."""
     _contig(grad_out, "grad_out"); _contig(idx, "idx"); _is_float(grad_out, "grad_out"); _is_int(idx, "idx")

@@ -42,6 +42,8 @@ SIGNATURES = {
     "gb_three_interp_bwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "gb_three_interp_bwd_set": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "gb_knn": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "gb_group_max_fwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "gb_group_max_bwd": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "gb_three_interpolation": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "gb_collision_counts": [_vp, _i, _vp, _vp, _vp, _i, _vp, _vp],
     "gb_collision_counts_host": [_vp, _i, _vp, _vp, _vp, _i, _vp],
@@ -123,6 +125,8 @@ ALGO_BYTES = {
     "gb_group_bwd_strided": lambda a: a[3] * (4 * a[4] * a[5] + 4 * a[6] * a[7] + 4 * a[4] * a[6] * a[7]),
     "gb_group_xyz": lambda a: a[5] * (12 * a[6] + 12 * a[7] + (36 * a[7] if a[3] else 0) + 16 * a[7] * a[8]),  # b*(12n+12m(+36m)+(4+12) m ns)
     "gb_knn": lambda a: a[3] * (4 * a[4] * (a[5] + a[6]) + 8 * a[7] * a[6]),              # b*(4d(R+Q) + 8kQ)
+    "gb_group_max_fwd": lambda a: a[4] * (4 * a[5] * a[6] + 4 * a[7] * a[8] + (8 if a[3] else 4) * a[5] * a[7]),
+    "gb_group_max_bwd": lambda a: a[3] * (8 * a[4] * a[6] + 4 * a[4] * a[5]),
     "gb_three_interpolation": lambda a: a[6] * (12 * a[8] + 12 * a[9] + 4 * a[7] * a[9] + 4 * a[7] * a[8] + (24 * a[8] if a[4] else 0)),
     "gb_collision_counts": lambda a: 24 * a[1] + 176 * a[5] + 48 * a[5],
     "gb_collision_counts_batched": lambda a: a[2] * (24 * a[3] + 176 * a[7] + 48 * a[7]),

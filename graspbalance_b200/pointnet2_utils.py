@@ -203,6 +203,55 @@ class GroupingOperation(Function):
 grouping_operation = GroupingOperation.apply
 
 
+class GroupingMax(Function):
+    """grouping_operation + max over nsample as one pass: what the 'max' pooling of PointnetSAModuleVotes(_WOMLP)
+    (pointnet2_modules.py:173-175, 324-335) computes from the grouped tensor when no MLP sits in between --
+    F.max_pool2d(grouping_operation(features, idx), kernel_size=[1, nsample]).squeeze(-1), bit for bit, without the
+    [B,C,npoint,nsample] tensor.  Backward sends each gradient to the source that won the maximum (max_pool2d's backward
+    followed by GroupingOperation's)."""
+
+    @staticmethod
+    def forward(ctx, features, idx):
+        res = _ext.group_points_max(features, idx, features.requires_grad)
+        if res is None:
+            raise RuntimeError("grouping_max: rows of more than 12800 points are not taken; use grouping_operation + max_pool2d")
+        out, arg = res
+        ctx.for_backwards = (arg, features.size(2))
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        arg, N = ctx.for_backwards
+        return _ext.group_points_max_grad(grad_out.contiguous(), arg, N), None
+
+
+grouping_max = GroupingMax.apply
+
+
+class QueryGroupMaxPool(nn.Module):
+    """QueryAndGroup(radius, nsample, use_xyz, normalize_xyz) followed by max pooling over the samples, as
+    PointnetSAModuleVotes_WOMLP.forward runs them (pointnet2_modules.py:310-335), in three small launches: ball_query and one
+    grouping_max each for coordinates and features.  The maximum of the centred (and scaled) coordinates is taken on the raw
+    coordinates first -- subtracting the centre and multiplying by 1/radius are monotone, so the values are bit-identical.
+    Returns [B, 3+C, npoint] (or [B, C, npoint] without use_xyz)."""
+
+    def __init__(self, radius, nsample, use_xyz=True, normalize_xyz=False):
+        super().__init__()
+        self.radius, self.nsample, self.use_xyz, self.normalize_xyz = radius, nsample, use_xyz, normalize_xyz
+
+    def forward(self, xyz, new_xyz, features=None):
+        idx = ball_query(self.radius, self.nsample, xyz, new_xyz)
+        parts = []
+        if self.use_xyz or features is None:
+            pooled = grouping_max(xyz.transpose(1, 2).contiguous(), idx) - new_xyz.transpose(1, 2)
+            if self.normalize_xyz:
+                pooled = pooled / self.radius
+            parts.append(pooled)
+        if features is not None:
+            parts.append(grouping_max(features, idx))
+        return parts[0] if len(parts) == 1 else torch.cat(parts, dim=1)
+
+
 class BallQuery(Function):
     @staticmethod
     def forward(ctx, radius, nsample, xyz, new_xyz):

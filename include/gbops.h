@@ -129,6 +129,18 @@ GB_API int gb_group_bwd_strided(const float *grad_out, const int *idx, float *gr
 GB_API int gb_group_xyz(const float *xyz, const float *new_xyz, const int *idx, const float *rot, float *out, int b, int n, int m,
                  int nsample, float scale, int use_scale, long long out_scene_stride, gb_stream_t stream);
 
+/* grouping_operation + max over nsample in one pass: PointnetSAModuleVotes_WOMLP.forward (PointNet/
+ * pointnet2_modules.py:324-335) and the 'max' pooling of PointnetSAModuleVotes (:173-175) when no MLP sits between the
+ * grouping and the pooling -- group_points_kernel (group_points_gpu.cu:17-36) + F.max_pool2d without the [b,c,npoints,nsample]
+ * tensor.  points [b,c,n], idx [b,npoints,nsample] -> out [b,c,npoints] = max_k points[b,c,idx[b,j,k]] (ATen's rule: first
+ * maximum in k order, NaN propagates); arg [b,c,npoints] i32 = source index of the maximum, or NULL.  Returns
+ * cudaErrorNotSupported (801) for rows that do not fit shared memory four at a time (callers run the two steps). */
+GB_API int gb_group_max_fwd(const float *points, const int *idx, float *out, int *arg, int b, int c, int n, int npoints, int nsample,
+                     gb_stream_t stream);
+/* Its backward: ACCUMULATES grad_out [b,c,npoints] into grad_points [b,c,n] at arg. */
+GB_API int gb_group_max_bwd(const float *grad_out, const int *arg, float *grad_points, int b, int c, int n, int npoints,
+                     gb_stream_t stream);
+
 /* A: three_nn_kernel_wrapper (interpolate_gpu.cu:66-73); B: three_nn_kernel_launcher_fast (:62-81).
  * unknown [b,n,3], known [b,m,3] -> dist2 [b,n,3] f32 (SQUARED), idx [b,n,3] i32. */
 GB_API int gb_three_nn(const float *unknown, const float *known, float *dist2, int *idx, int b, int n, int m,

@@ -275,3 +275,105 @@ def test_empty_batches_and_empty_clouds(dev):
         assert tuple(idx.shape) == (2, 5, 8) and idx.dtype == torch.int32 and int(idx.abs().sum()) == 0
     with pytest.raises(RuntimeError):  # samples of an empty cloud are undefined
         pu.furthest_point_sample(none, 4)
+
+
+def _reference_pred_decode(end_points):
+    """TrainModel/graspbalance.py:139-192 and loss_utils.py:33-49, literally (per-scene loop), as the check of decode.pred_decode."""
+    def to_matrix(batch_towards, batch_angle):
+        axis_x = batch_towards
+        ones = torch.ones(axis_x.shape[0], dtype=axis_x.dtype, device=axis_x.device)
+        zeros = torch.zeros(axis_x.shape[0], dtype=axis_x.dtype, device=axis_x.device)
+        axis_y = torch.stack([-axis_x[:, 1], axis_x[:, 0], zeros], dim=-1)
+        mask_y = (torch.norm(axis_y, dim=-1) == 0)
+        axis_y[mask_y, 1] = 1
+        axis_x = axis_x / torch.norm(axis_x, dim=-1, keepdim=True)
+        axis_y = axis_y / torch.norm(axis_y, dim=-1, keepdim=True)
+        axis_z = torch.cross(axis_x, axis_y, dim=-1)
+        sin, cos = torch.sin(batch_angle), torch.cos(batch_angle)
+        R1 = torch.stack([ones, zeros, zeros, zeros, cos, -sin, zeros, sin, cos], dim=-1).reshape([-1, 3, 3])
+        return torch.matmul(torch.stack([axis_x, axis_y, axis_z], dim=-1), R1)
+    preds = []
+    for i in range(len(end_points['point_clouds'])):
+        objectness_score = end_points['objectness_score'][i].float()
+        grasp_score = end_points['grasp_score_pred'][i].float()
+        grasp_center = end_points['fp2_xyz'][i].float()
+        approaching = -end_points['grasp_top_view_xyz'][i].float()
+        grasp_width = torch.clamp(1.2 * end_points['grasp_width_pred'][i], min=0, max=0.1)
+        grasp_tolerance = end_points['grasp_tolerance_pred'][i]
+        cls = torch.argmax(end_points['grasp_angle_cls_pred'][i], 0)
+        grasp_angle = cls.float() / 12 * np.pi
+        cls_ = cls.unsqueeze(0)
+        grasp_score = torch.gather(grasp_score, 0, cls_).squeeze(0)
+        grasp_width = torch.gather(grasp_width, 0, cls_).squeeze(0)
+        grasp_tolerance = torch.gather(grasp_tolerance, 0, cls_).squeeze(0)
+        dcls = torch.argmax(grasp_score, 1, keepdims=True)
+        grasp_depth = (dcls.float() + 1) * 0.01
+        grasp_score, grasp_angle = torch.gather(grasp_score, 1, dcls), torch.gather(grasp_angle, 1, dcls)
+        grasp_width, grasp_tolerance = torch.gather(grasp_width, 1, dcls), torch.gather(grasp_tolerance, 1, dcls)
+        mask = torch.argmax(objectness_score, 0) == 1
+        grasp_score = grasp_score * torch.softmax(objectness_score, dim=0)[1, :].unsqueeze(1)
+        grasp_score, grasp_width, grasp_depth = grasp_score[mask], grasp_width[mask], grasp_depth[mask]
+        approaching, grasp_angle, grasp_center, grasp_tolerance = approaching[mask], grasp_angle[mask], grasp_center[mask], grasp_tolerance[mask]
+        grasp_score = grasp_score * grasp_tolerance / 0.05
+        Ns = grasp_angle.size(0)
+        rot = to_matrix(approaching.view(Ns, 3), grasp_angle.view(Ns)).view(Ns, 9)
+        preds.append(torch.cat([grasp_score, grasp_width, 0.02 * torch.ones_like(grasp_score), grasp_depth, rot, grasp_center,
+                                -1 * torch.ones_like(grasp_score)], axis=-1))
+    return preds
+
+
+def test_pred_decode_and_on_device_collision_masks(dev):
+    """decode.pred_decode == the reference's per-scene loop (graspbalance.py:139-192) on random head outputs, and its float32
+    rows fed to the collision test on the device give the masks the reference flow gives (rows -> host -> GraspGroup arrays ->
+    numpy detect, here the dtype-faithful oracle)."""
+    from graspbalance_b200 import decode
+    from graspbalance_b200.collision_detector import ModelFreeCollisionDetector
+    B, Ns, A, D = 2, 1024, 12, 4
+    g = torch.Generator(device="cpu").manual_seed(6)
+    xyz_np = scenes.scene_batch([31, 32], 20000, "tabletop")
+    seeds = torch.from_numpy(xyz_np[:, :Ns].copy()).to(dev)
+    views = torch.randn((B, Ns, 3), generator=g).to(dev)
+    views[0, :3] = torch.tensor([0.0, 0.0, 1.0])  # approach along z: the degenerate y axis of loss_utils.py:38-39
+    ep = {"point_clouds": torch.from_numpy(xyz_np).to(dev), "objectness_score": torch.randn((B, 2, Ns), generator=g).to(dev),
+          "grasp_score_pred": torch.rand((B, A, Ns, D), generator=g).to(dev), "fp2_xyz": seeds, "grasp_top_view_xyz": views,
+          "grasp_angle_cls_pred": torch.randn((B, A, Ns, D), generator=g).to(dev),
+          "grasp_width_pred": (0.1 * torch.rand((B, A, Ns, D), generator=g)).to(dev),
+          "grasp_tolerance_pred": (0.05 * torch.rand((B, A, Ns, D), generator=g)).to(dev)}
+    got, want = decode.pred_decode(ep), _reference_pred_decode(ep)
+    for a, b in zip(got, want):
+        assert a.shape == b.shape and a.dtype == torch.float32 and 100 < a.shape[0] < Ns
+        assert torch.equal(a, b)
+    masks = decode.collision_masks(got, [xyz_np[b].astype(np.float64) for b in range(B)], voxel_size=0.01)
+    for b in range(B):
+        rows = got[b].cpu().numpy()  # float32, as the arrays of the GraspGroup the reference builds from them
+        det = ModelFreeCollisionDetector(xyz_np[b].astype(np.float64), voxel_size=0.01, device=dev)
+        ref = oracle.collision_detect(det.scene_points, 0.01, rows[:, 13:16], rows[:, 4:13].reshape(-1, 3, 3), rows[:, 2], rows[:, 3],
+                                      rows[:, 1], approach_dist=0.05, collision_thresh=0.01)
+        assert masks[b].is_cuda and masks[b].dtype == torch.bool
+        np.testing.assert_array_equal(masks[b].cpu().numpy(), ref)
+        assert 0 < int(ref.sum()) < ref.shape[0]
+
+
+@pytest.mark.parametrize("B,N,m,ns,C,r", [(2, 20000, 1024, 64, 35, 0.05), (3, 2048, 1024, 32, 128, 0.1), (2, 1024, 300, 16, 7, 0.3), (1, 500, 64, 5, 4, 0.2)])
+def test_grouping_max_equals_group_then_max_pool(dev, B, N, m, ns, C, r):
+    """gb_group_max_fwd / bwd == grouping_operation + F.max_pool2d over the samples (pointnet2_modules.py:173-175, 324-335):
+    values bit for bit, gradients equal those autograd sends through max_pool2d and GroupingOperation (padded neighbourhoods
+    repeat their first index: the first maximum wins in both), and the fused WOMLP-style module equals QueryAndGroup + pooling."""
+    import torch.nn.functional as F
+    xyz = torch.from_numpy(scenes.scene_batch(range(B), N, "tabletop" if N >= 1000 else "uniform")).to(dev)
+    new_xyz = xyz[:, :m].contiguous()
+    idx = pu.ball_query(r, ns, xyz, new_xyz)
+    g = torch.Generator(device="cpu").manual_seed(8)
+    feats = torch.randn((B, C, N), generator=g).to(dev)
+    feats[:, :, ::7] = feats[:, :, 1::7][:, :, :feats[:, :, ::7].shape[2]]  # equal values at different sources: ties
+    f1, f2 = feats.clone().requires_grad_(True), feats.clone().requires_grad_(True)
+    want = F.max_pool2d(pu.grouping_operation(f1, idx), kernel_size=[1, ns]).squeeze(-1)
+    got = pu.grouping_max(f2, idx)
+    assert torch.equal(got, want)
+    go = torch.randn(want.shape, generator=g).to(dev)
+    want.backward(go), got.backward(go)
+    np.testing.assert_allclose(f2.grad.cpu().numpy(), f1.grad.cpu().numpy(), rtol=1e-5, atol=1e-6)
+    for norm in (False, True):
+        ref = pu.QueryAndGroup(r, ns, use_xyz=True, normalize_xyz=norm)(xyz, new_xyz, feats)
+        ref = F.max_pool2d(ref, kernel_size=[1, ns]).squeeze(-1)
+        assert torch.equal(pu.QueryGroupMaxPool(r, ns, use_xyz=True, normalize_xyz=norm)(xyz, new_xyz, feats), ref)

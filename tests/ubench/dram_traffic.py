@@ -16,7 +16,7 @@ import sys
 _I, _B0, _B1 = r"(\(int\))?", r"(\(bool\))?(0|false)", r"(\(bool\))?(1|true)"
 MAIN = [  # (regex on the kernel name, family); seg_dense_kernel<CT, TPT, DIV, WEIGHTED, MUL>, seg_accum_kernel<CC, DIV, WEIGHTED>
     (r"group_fwd_kernel|group_fwd_generic", "gb_group_fwd"),
-    (rf"seg_dense_kernel<[^>]*, ?{_I}1, ?{_B0}, ?{_I}\d+>|seg_accum_kernel<[^>]*, ?{_I}1, ?{_B0}>|group_bwd_kernel|group_bwd_generic", "gb_group_bwd"),
+    (rf"scatter_private_kernel|seg_dense_kernel<[^>]*, ?{_I}1, ?{_B0}, ?{_I}\d+>|seg_accum_kernel<[^>]*, ?{_I}1, ?{_B0}>|group_bwd_kernel|group_bwd_generic", "gb_group_bwd"),
     (rf"seg_dense_kernel<[^>]*, ?{_I}3, ?{_B1}, ?{_I}\d+>|seg_accum_kernel<[^>]*, ?{_I}3, ?{_B1}>|interp_bwd_kernel", "gb_three_interp_bwd"),
     (r"interp_fwd", "gb_three_interp_fwd"),
     (rf"grid_query_kernel<{_B1}[,>]|query_kernel<{_B1}[,>]", "gb_cylinder_query"),
