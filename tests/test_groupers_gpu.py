@@ -365,14 +365,16 @@ def test_grouping_max_equals_group_then_max_pool(dev, B, N, m, ns, C, r):
     idx = pu.ball_query(r, ns, xyz, new_xyz)
     g = torch.Generator(device="cpu").manual_seed(8)
     feats = torch.randn((B, C, N), generator=g).to(dev)
-    feats[:, :, ::7] = feats[:, :, 1::7][:, :, :feats[:, :, ::7].shape[2]]  # equal values at different sources: ties
+    k7 = (N - 1) // 7
+    feats[:, :, 0:7 * k7:7] = feats[:, :, 1:7 * k7 + 1:7]  # equal values at different sources: ties
     f1, f2 = feats.clone().requires_grad_(True), feats.clone().requires_grad_(True)
     want = F.max_pool2d(pu.grouping_operation(f1, idx), kernel_size=[1, ns]).squeeze(-1)
     got = pu.grouping_max(f2, idx)
     assert torch.equal(got, want)
     go = torch.randn(want.shape, generator=g).to(dev)
     want.backward(go), got.backward(go)
-    np.testing.assert_allclose(f2.grad.cpu().numpy(), f1.grad.cpu().numpy(), rtol=1e-5, atol=1e-6)
+    scale = float(f1.grad.abs().max())
+    assert float((f2.grad - f1.grad).abs().max()) <= 1e-5 * scale  # float atomics on both sides: summation order differs
     for norm in (False, True):
         ref = pu.QueryAndGroup(r, ns, use_xyz=True, normalize_xyz=norm)(xyz, new_xyz, feats)
         ref = F.max_pool2d(ref, kernel_size=[1, ns]).squeeze(-1)
