@@ -2,9 +2,10 @@
 //
 // Replaces the numpy body of ModelFreeCollisionDetector.detect (collision_detector.py:23-41,55), which materialises a
 // [G,N,3] fp64 array of transformed points (491 MB at G=1024, N=20000) and ten [G,N] boolean masks on the host.  Here one
-// WARP owns a grasp (translation, rotation and the ten half-space thresholds live in registers), the scene is staged tile
-// by tile in shared memory, every lane transforms one point per step and keeps six integer counters that are warp-reduced
-// at the end.  Nothing but the six counts per grasp ever leaves the SM.
+// WARP owns a grasp (translation, rotation and the ten half-space thresholds live in registers); the scene is cut into
+// packs of 32 consecutive points with precomputed bounds, the warp skips the packs its gripper cannot reach and, for the
+// others, every lane transforms one point and keeps six integer counters that are warp-reduced at the end.  Nothing but the
+// six counts per grasp ever leaves the SM.
 //
 // Arithmetic (SURVEY.md A.7 and DESIGN.md "collision rounding"): d = p - T in fp64; t_j = fma(d2,R[2][j], fma(d1,R[1][j],
 // d0*R[0][j])) -- the evaluation order of the OpenBLAS dgemm kernel numpy.matmul dispatches to (bit-identical on 9.6e5
@@ -15,45 +16,103 @@
 namespace gb {
 
 constexpr int kColWarps = 4;
-constexpr int kColTile = 1024;  // points per tile: 24 KB
+constexpr int kColPack = 32;  // points per pack: one per lane
 
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+  for (int d = 16; d; d >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, d));
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int d = 16; d; d >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, d));
+  return v;
+}
+
+// Axis-aligned bounds of every pack of 32 consecutive points: bounds [nscenes, pps, 6] = {min x,y,z, max x,y,z}.  One warp per
+// pack.  scene_off = nullptr: one scene of np points.  (fmin / fmax skip NaN coordinates: such points satisfy no mask.)
+__global__ void collision_bounds_kernel(const double *__restrict__ points, int np, const long long *__restrict__ scene_off, int pps,
+                                        double *__restrict__ bounds) {
+  const int lane = threadIdx.x & 31;
+  const int pack = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (scene_off) {
+    const long long o0 = scene_off[blockIdx.y];
+    points += 3 * o0;
+    np = (int)(scene_off[blockIdx.y + 1] - o0);
+  }
+  if (pack * kColPack >= np) return;
+  const int e = pack * kColPack + lane;
+  const bool ok = e < np;
+  const double inf = __longlong_as_double(0x7ff0000000000000LL);
+  const double x = ok ? points[(size_t)e * 3] : inf, y = ok ? points[(size_t)e * 3 + 1] : inf, z = ok ? points[(size_t)e * 3 + 2] : inf;
+  const double lo0 = warp_min(x), lo1 = warp_min(y), lo2 = warp_min(z);
+  const double hi0 = warp_max(ok ? x : -inf), hi1 = warp_max(ok ? y : -inf), hi2 = warp_max(ok ? z : -inf);
+  if (lane < 6) {
+    const double v = lane == 0 ? lo0 : lane == 1 ? lo1 : lane == 2 ? lo2 : lane == 3 ? hi0 : lane == 4 ? hi1 : hi2;
+    bounds[((size_t)blockIdx.y * pps + pack) * 6 + lane] = v;
+  }
+}
+
+// One warp per grasp.  A point can only count when its gripper-frame coordinates lie inside the box the ten thresholds
+// span; for an orthonormal rotation that puts it inside a sphere around the grasp centre, so packs whose bounds miss the
+// sphere (with a 2e-4 relative margin, far above the rounding of either side) are skipped without touching their points:
+// a gripper reaches ~0.1 m in a scene of ~0.7 m, and the detector's down-sampled cloud is stored in voxel-key order
+// (voxel_down_sample_gpu), so consecutive points are neighbours and most packs are skipped.  Rotations that are not
+// orthonormal to 1e-6 (or contain NaN) test every pack.  The arithmetic per tested point is unchanged, so the counts are
+// those of the exhaustive test.
 __global__ void __launch_bounds__(kColWarps * 32) collision_kernel(const double *__restrict__ points, int np, const double *__restrict__ T,
                                                                    const double *__restrict__ R, const double *__restrict__ thr, int g,
-                                                                   unsigned long long *__restrict__ counts, int pts_per_split,
-                                                                   const long long *__restrict__ scene_off) {
-  __shared__ double tile[kColTile * 3];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (scene_off) {  // batched: blockIdx.z = scene; its points are rows scene_off[z] .. scene_off[z+1] of the packed array
-    const long long o0 = scene_off[blockIdx.z];
+                                                                   unsigned long long *__restrict__ counts,
+                                                                   const long long *__restrict__ scene_off, const double *__restrict__ bounds,
+                                                                   int pps) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (scene_off) {  // batched: blockIdx.y = scene; its points are rows scene_off[y] .. scene_off[y+1] of the packed array
+    const long long o0 = scene_off[blockIdx.y];
     points += 3 * o0;
-    np = (int)(scene_off[blockIdx.z + 1] - o0);
-    const size_t go = (size_t)blockIdx.z * g;
+    np = (int)(scene_off[blockIdx.y + 1] - o0);
+    const size_t go = (size_t)blockIdx.y * g;
     T += go * 3, R += go * 9, thr += go * 10, counts += go * 6;
   }
+  bounds += (size_t)blockIdx.y * pps * 6;
   const int gi = blockIdx.x * kColWarps + warp;
-  const bool gok = gi < g;
-  const size_t gs = gok ? gi : 0;
-  const double t0 = T[gs * 3], t1 = T[gs * 3 + 1], t2 = T[gs * 3 + 2];
+  if (gi >= g) return;  // warps are independent
+  const double t0 = T[(size_t)gi * 3], t1 = T[(size_t)gi * 3 + 1], t2 = T[(size_t)gi * 3 + 2];
   double r[9], h[10];
 #pragma unroll
-  for (int e = 0; e < 9; ++e) r[e] = R[gs * 9 + e];
+  for (int e = 0; e < 9; ++e) r[e] = R[(size_t)gi * 9 + e];
 #pragma unroll
-  for (int e = 0; e < 10; ++e) h[e] = thr[gs * 10 + e];
+  for (int e = 0; e < 10; ++e) h[e] = thr[(size_t)gi * 10 + e];
+  // reach of the gripper box: x in (h9, h3), |y| < h6 (= w/2 + fw), |z| < h1 (= height / 2)
+  const double xr = fmax(fabs(h[9]), fabs(h[3])), yr = fmax(fabs(h[4]), fabs(h[6])), zr = fmax(fabs(h[0]), fabs(h[1]));
+  double rho2 = (xr * xr + yr * yr + zr * zr) * 1.0002 + 1e-12;
+  bool ortho = true;
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = a; b < 3; ++b) {
+      const double dot = r[a] * r[b] + r[3 + a] * r[3 + b] + r[6 + a] * r[6 + b];  // (R^T R)_{ab}
+      ortho = ortho && fabs(dot - (a == b ? 1.0 : 0.0)) < 1e-6;
+    }
+  if (!ortho || !(rho2 == rho2)) rho2 = __longlong_as_double(0x7ff0000000000000LL);  // test every pack
 
-  const int p_begin = blockIdx.y * pts_per_split;
-  const int p_end = min(np, p_begin + pts_per_split);
   int cg = 0, cl = 0, cr = 0, cb = 0, cs = 0, ci = 0;
-  for (int base = p_begin; base < p_end; base += kColTile) {
-    const int tc = min(kColTile, p_end - base);
-    __syncthreads();
-    for (int e = tid; e < tc * 3; e += kColWarps * 32) tile[e] = points[(size_t)base * 3 + e];
-    __syncthreads();
-    if (!gok) continue;
-    for (int off = 0; off < tc; off += 32) {
-      const int e = off + lane;
-      const bool valid = e < tc;
-      const int es = valid ? e : 0;
-      const double d0 = tile[es * 3] - t0, d1 = tile[es * 3 + 1] - t1, d2 = tile[es * 3 + 2] - t2;
+  const int npacks = (np + kColPack - 1) / kColPack;
+  for (int pbase = 0; pbase < npacks; pbase += 32) {
+    const int pk = pbase + lane;
+    bool hit = false;
+    if (pk < npacks) {
+      const double *bb = bounds + (size_t)pk * 6;
+      const double dx = fmax(fmax(bb[0] - t0, t0 - bb[3]), 0.0), dy = fmax(fmax(bb[1] - t1, t1 - bb[4]), 0.0),
+                   dz = fmax(fmax(bb[2] - t2, t2 - bb[5]), 0.0);
+      hit = !(dx * dx + dy * dy + dz * dz > rho2);  // NaN bounds or a NaN centre count as a hit
+    }
+    unsigned hits = __ballot_sync(0xffffffffu, hit);
+    while (hits) {
+      const int e = (pbase + __ffs(hits) - 1) * kColPack + lane;
+      hits &= hits - 1;
+      const bool valid = e < np;
+      const size_t es = valid ? e : 0;
+      const double d0 = points[es * 3] - t0, d1 = points[es * 3 + 1] - t1, d2 = points[es * 3 + 2] - t2;
       const double tz = __fma_rn(d2, r[8], __fma_rn(d1, r[5], __dmul_rn(d0, r[2])));
       const bool m1 = valid && (tz > h[0]) && (tz < h[1]);
       if (!__any_sync(0xffffffffu, m1)) continue;  // every mask needs m1
@@ -76,7 +135,6 @@ __global__ void __launch_bounds__(kColWarps * 32) collision_kernel(const double 
       ci += (m1 && m2 && !m4 && !m6) ? 1 : 0;
     }
   }
-  if (!gok) return;
   cg = __reduce_add_sync(0xffffffffu, cg);
   cl = __reduce_add_sync(0xffffffffu, cl);
   cr = __reduce_add_sync(0xffffffffu, cr);
@@ -85,7 +143,7 @@ __global__ void __launch_bounds__(kColWarps * 32) collision_kernel(const double 
   ci = __reduce_add_sync(0xffffffffu, ci);
   if (lane < 6) {
     const int v = lane == 0 ? cg : lane == 1 ? cl : lane == 2 ? cr : lane == 3 ? cb : lane == 4 ? cs : ci;
-    if (v) atomicAdd(counts + (size_t)gi * 6 + lane, (unsigned long long)v);
+    counts[(size_t)gi * 6 + lane] = (unsigned long long)v;
   }
 }
 
@@ -187,23 +245,25 @@ __global__ void collision_finish_kernel(const unsigned long long *__restrict__ c
   }
 }
 
-static int collision_launch(const double *points, int np, const double *T, const double *R, const double *thr, int g, int64_t *counts,
-                            cudaStream_t s) {
-  cudaError_t e = cudaMemsetAsync(counts, 0, (size_t)g * 6 * sizeof(int64_t), s);
+// scene_off = nullptr: one scene of np points; else nscenes scenes of at most np points each
+static int collision_launch(const double *points, int np, const long long *scene_off, int nscenes, const double *T, const double *R,
+                            const double *thr, int g, int64_t *counts, cudaStream_t s) {
+  if (np == 0) return (int)cudaMemsetAsync(counts, 0, (size_t)nscenes * g * 6 * sizeof(int64_t), s);
+  const int pps = (np + kColPack - 1) / kColPack;
+  double *bounds = nullptr;
+  cudaError_t e = scratch_alloc((void **)&bounds, (size_t)nscenes * pps * 6 * sizeof(double), s);
   if (e != cudaSuccess) return (int)e;
-  if (np == 0) return 0;
-  const int gx = (g + kColWarps - 1) / kColWarps;
-  int splits = (4 * num_sms() + gx - 1) / gx;  // aim at ~4 CTAs per SM
-  const int max_splits = (np + kColTile - 1) / kColTile;
-  if (splits > max_splits) splits = max_splits;
-  if (splits < 1) splits = 1;
-  int pps = (np + splits - 1) / splits;
-  pps = ((pps + kColTile - 1) / kColTile) * kColTile;
-  splits = (np + pps - 1) / pps;
-  dim3 grid(gx, splits);
-  collision_kernel<<<grid, kColWarps * 32, 0, s>>>(points, np, T, R, thr, g, reinterpret_cast<unsigned long long *>(counts), pps, nullptr);
+  collision_bounds_kernel<<<dim3((pps + 7) / 8, nscenes), 256, 0, s>>>(points, np, scene_off, pps, bounds);
   count_launch();
-  return finish_launch();
+  int rc = finish_launch();
+  if (!rc) {
+    collision_kernel<<<dim3((g + kColWarps - 1) / kColWarps, nscenes), kColWarps * 32, 0, s>>>(
+        points, np, T, R, thr, g, reinterpret_cast<unsigned long long *>(counts), scene_off, bounds, pps);
+    count_launch();
+    rc = finish_launch();
+  }
+  cudaFreeAsync(bounds, s);
+  return rc;
 }
 
 }  // namespace gb
@@ -212,7 +272,7 @@ extern "C" int gb_collision_counts(const double *points, int np, const double *T
                                    int64_t *counts, gb_stream_t stream) {
   if (np < 0 || g < 0 || !T || !R || !thr || !counts || (np > 0 && !points)) return (int)cudaErrorInvalidValue;
   if (g == 0) return 0;
-  return gb::collision_launch(points, np, T, R, thr, g, counts, (cudaStream_t)stream);
+  return gb::collision_launch(points, np, nullptr, 1, T, R, thr, g, counts, (cudaStream_t)stream);
 }
 
 extern "C" int gb_collision_counts_host(const double *points, int np, const double *T, const double *R, const double *thr, int g,
@@ -235,7 +295,7 @@ extern "C" int gb_collision_counts_host(const double *points, int np, const doub
   if (!rc) rc = (int)cudaMemcpyAsync(dt, T, bt, cudaMemcpyHostToDevice, s);
   if (!rc) rc = (int)cudaMemcpyAsync(dr, R, br, cudaMemcpyHostToDevice, s);
   if (!rc) rc = (int)cudaMemcpyAsync(dh, thr, bh, cudaMemcpyHostToDevice, s);
-  if (!rc) rc = gb::collision_launch((const double *)dp, np, (const double *)dt, (const double *)dr, (const double *)dh, g, (int64_t *)dc, s);
+  if (!rc) rc = gb::collision_launch((const double *)dp, np, nullptr, 1, (const double *)dt, (const double *)dr, (const double *)dh, g, (int64_t *)dc, s);
   if (!rc) rc = (int)cudaMemcpyAsync(counts, dc, bc, cudaMemcpyDeviceToHost, s);
   if (!rc) rc = (int)cudaStreamSynchronize(s);
   cudaFree(d);
@@ -273,7 +333,7 @@ extern "C" int gb_collision_detect(const double *points, int np, const void *gra
     gb::collision_prepare_kernel<double><<<blocks, 128, 0, s>>>((const double *)grasps, g, row_stride, oT, oR, oH, oD, oW, p, T64, R64, thr, den);
   gb::count_launch();
   int rc = gb::finish_launch();
-  if (!rc) rc = gb::collision_launch(points, np, T64, R64, thr, g, cnt, s);
+  if (!rc) rc = gb::collision_launch(points, np, nullptr, 1, T64, R64, thr, g, cnt, s);
   if (!rc) {
     gb::collision_finish_kernel<<<blocks, 128, 0, s>>>(reinterpret_cast<const unsigned long long *>(cnt), den, g, p, mask, empty, ious);
     gb::count_launch();
@@ -305,20 +365,5 @@ extern "C" int gb_collision_counts_batched(const double *points, const long long
   if (nscenes < 0 || max_np < 0 || g < 0) return (int)cudaErrorInvalidValue;
   if (nscenes == 0 || g == 0) return 0;
   if (!scene_off || !T || !R || !thr || !counts || (max_np > 0 && !points) || nscenes > 65535) return (int)cudaErrorInvalidValue;
-  cudaStream_t s = (cudaStream_t)stream;
-  cudaError_t e = cudaMemsetAsync(counts, 0, (size_t)nscenes * g * 6 * sizeof(int64_t), s);
-  if (e != cudaSuccess) return (int)e;
-  if (max_np == 0) return 0;
-  const int gx = (g + gb::kColWarps - 1) / gb::kColWarps;
-  int splits = (4 * gb::num_sms() + gx * nscenes - 1) / (gx * nscenes);
-  const int max_splits = (max_np + gb::kColTile - 1) / gb::kColTile;
-  splits = splits > max_splits ? max_splits : (splits < 1 ? 1 : splits);
-  int pps = (max_np + splits - 1) / splits;
-  pps = ((pps + gb::kColTile - 1) / gb::kColTile) * gb::kColTile;
-  splits = (max_np + pps - 1) / pps;
-  dim3 grid(gx, splits, nscenes);
-  gb::collision_kernel<<<grid, gb::kColWarps * 32, 0, s>>>(points, 0, T, R, thr, g, reinterpret_cast<unsigned long long *>(counts), pps,
-                                                           scene_off);
-  gb::count_launch();
-  return gb::finish_launch();
+  return gb::collision_launch(points, max_np, scene_off, nscenes, T, R, thr, g, counts, (cudaStream_t)stream);
 }

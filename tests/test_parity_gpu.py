@@ -737,3 +737,26 @@ def test_fused_feature_propagation_equals_the_three_steps(dev, ref_a, B, n, m, C
     got.backward(go)
     assert_grad_close(f.grad.cpu().numpy(), ref_a.three_interpolate_grad(go, idx, w, m).cpu().numpy())
     assert torch.equal(gb_up.three_interpolation(unknown, known, feats), want)  # the ModifiedNetTools entry point (two launches)
+
+
+def test_collision_pack_culling_never_changes_the_counts(dev):
+    """The collision kernel skips packs of 32 points whose bounds the gripper cannot reach.  Counts must equal the exhaustive
+    test (the C oracle) for clouds in any order (voxel-key order, shuffled), for rotations that are not orthonormal (scaled,
+    sheared: every pack is tested then), for grasps far outside the cloud, and for NaN / inf in centres and points."""
+    from graspbalance_b200.collision_detector import collision_counts
+    rng = np.random.default_rng(21)
+    det = ModelFreeCollisionDetector(scenes.tabletop_scene(15, 20000).astype(np.float64), voxel_size=0.01, device=dev)
+    pts_sorted = det.scene_points
+    G = 256
+    gs = scenes.grasp_set(16, pts_sorted, G)
+    Tm, Rm = gs["translations"].copy(), gs["rotation_matrices"].copy()
+    Rm[10:40] *= 1.7                                          # scaled
+    Rm[40:70] += rng.normal(scale=0.2, size=(30, 3, 3))       # sheared
+    Tm[70:90] += 5.0                                          # far outside the cloud
+    Tm[90, 0], Tm[91, 1], Rm[92, 1, 1] = np.nan, np.inf, np.nan
+    thr = oracle.collision_thresholds(gs["heights"], gs["depths"], gs["widths"], 0.05)
+    for pts in (pts_sorted, pts_sorted[rng.permutation(pts_sorted.shape[0])], np.concatenate([pts_sorted[:777], [[np.nan, 0.1, 0.5], [np.inf, 0.0, 0.5]]])):
+        got = collision_counts(T(pts, dev), T(Tm, dev), T(Rm, dev), T(thr, dev)).cpu().numpy()
+        want = oracle.collision_counts(pts, Tm, Rm, gs["heights"], gs["depths"], gs["widths"], 0.05)
+        np.testing.assert_array_equal(got, want)
+    assert int(want[:, 0].sum()) > 0
