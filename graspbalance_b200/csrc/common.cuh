@@ -56,6 +56,7 @@ struct Tuning {
                          // bit 3: never use the warp-private backward; bit 4: use it for any number of tasks
   std::atomic<int> priv_vl{0};     // warp-private backward: positions per lane and load (1, 2, 4), 0 = automatic
   std::atomic<int> priv_dry{0};    // experiment: 1 = the warp-private backward only streams its inputs (wrong results)
+  std::atomic<int> priv_split{0};  // warp-private backward: warps that share a task (1, 2, 4), 0 = automatic
   std::atomic<int> priv_cw{0};     // warp-private backward: channels per warp and plane (2, 4), 0 = automatic
   std::atomic<int> query_mode{0};  // 1: never use the cell grid, 2: always use it (when the shape allows)
   std::atomic<int> grid_cell_pct{0};  // cell edge as a percentage of the query reach (0 = default 50)

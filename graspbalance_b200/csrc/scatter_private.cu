@@ -167,15 +167,20 @@ __device__ __noinline__ void priv_slow_unit(typename PrivAcc<CW>::T *acc, int n,
 template <int CW, int S, int VL, int NRG, int R, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1) scatter_private_kernel(const float *__restrict__ src, const int *__restrict__ idx,
                                                                   float *__restrict__ grad, int c, int n, int per, int groups,
-                                                                  int tasks, int overwrite, size_t src_stride, int ns, int dry) {
+                                                                  int tasks, int overwrite, size_t src_stride, int ns, int split,
+                                                                  int dry) {
   constexpr int H = 32 / S, PU = S * VL, LG = S == 32 ? 32 / NRG : S;  // LG lanes hold one row (piece)
   static_assert(S == 32 || (VL == 1 && NRG == 1), "planes take one position per lane");
   typedef typename PrivAcc<CW>::T AccT;
   extern __shared__ __align__(16) unsigned char s_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int task = blockIdx.x * (blockDim.x >> 5) + warp;
-  if (task >= tasks) return;  // warps are independent: no block-level barrier anywhere below
-  const int scene = task / groups, grp = task - scene * groups;
+  // task = (scene, channel group); `split` consecutive warps of a block share a task and take every split-th unit of its
+  // rows (small launches: twice or four times the warps per SM); their accumulators are added up at the write-out
+  const int wtask = blockIdx.x * (blockDim.x >> 5) + warp;
+  const int task = wtask / split, part = wtask - task * split;
+  const bool live = task < tasks;
+  if (!live && split == 1) return;  // unsplit: warps are independent, no block-level barrier anywhere below
+  const int scene = live ? task / groups : 0, grp = live ? task - scene * groups : 0;
   const int k = lane & (S - 1), h = lane / S;
   const int rg = lane / LG;  // row of the unit this lane works on (0 when NRG == 1)
   const bool row_end = (lane & (LG - 1)) == LG - 1;
@@ -292,16 +297,21 @@ __global__ void __launch_bounds__(MAXT, 1) scatter_private_kernel(const float *_
   };
 
   PrivUnit<CW, VL> ring[R];
+  const int my_units = live ? (units - part + split - 1) / split : 0;  // units part, part + split, ...
 #pragma unroll
-  for (int r = 0; r < R; ++r) load(ring[r], r);
-  for (int u0 = 0; u0 < units; u0 += R) {
+  for (int r = 0; r < R; ++r) load(ring[r], part + r * split);
+  for (int u0 = 0; u0 < my_units; u0 += R) {
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      if (u0 + r < units) process(ring[r]);  // warp-uniform
-      load(ring[r], u0 + R + r);
+      if (u0 + r < my_units) process(ring[r]);  // warp-uniform
+      load(ring[r], part + (u0 + R + r) * split);
     }
   }
   __syncwarp();
+  if (split > 1) {
+    __syncthreads();  // the partners' accumulators are complete
+    if (!live || part != 0) return;
+  }
   if (dry) acc[lane] = acc[lane], grad[(size_t)scene * c * n + lane] = dry_sum;
 
   // rows of the warp's channels, written once (coalesced along the targets)
@@ -310,7 +320,14 @@ __global__ void __launch_bounds__(MAXT, 1) scatter_private_kernel(const float *_
     const int cbase = grp * CW * H + CW * hh;
     const AccT *a = acc_w + (size_t)hh * n;
     for (int t = lane; t < n; t += 32) {
-      const AccT x = a[t];
+      AccT x = a[t];
+      for (int p = 1; p < split; ++p) {  // partners' slices lie behind this warp's, in part order: a fixed summation order
+        const AccT y = a[(size_t)p * H * n + t];
+        float ys[CW];
+#pragma unroll
+        for (int j = 0; j < CW; ++j) ys[j] = PrivAcc<CW>::get(y, j);
+        PrivAcc<CW>::add(x, ys);
+      }
 #pragma unroll
       for (int j = 0; j < CW; ++j) {
         if (cbase + j < c) {
@@ -348,13 +365,14 @@ bool scatter_private_supported(int b, int c, int n, int npoints, int nsample, si
 
 template <int CW, int S, int VL, int NRG, int R, int MAXT>
 static int launch_private(const float *src, size_t src_stride, const int *idx, float *grad, int c, int n, int per, int groups, int tasks,
-                          int W, int overwrite, int nsample, cudaStream_t s) {
+                          int W, int split, int overwrite, int nsample, cudaStream_t s) {
   constexpr int H = 32 / S;
   const size_t smem = (size_t)W * H * n * 4 * CW;
   auto kern = scatter_private_kernel<CW, S, VL, NRG, R, MAXT>;
   if (int rc_ = raise_smem_limit(kern, smem)) return rc_;
-  kern<<<(unsigned)((tasks + W - 1) / W), W * 32, smem, s>>>(src, idx, grad, c, n, per, groups, tasks, overwrite, src_stride,
-                                                            nsample, g_tuning.priv_dry);
+  const long long warps = (long long)tasks * split;
+  kern<<<(unsigned)((warps + W - 1) / W), W * 32, smem, s>>>(src, idx, grad, c, n, per, groups, tasks, overwrite, src_stride, nsample, split,
+                                                            g_tuning.priv_dry);
   count_launch();
   return finish_launch();
 }
@@ -368,22 +386,32 @@ static int scatter_private_cw(const float *src, size_t src_stride, const int *id
   const int tasks = b * groups;
   int wmax = (int)(kPrivSmemBudget / ((size_t)H * n * 4 * CW));
   wmax = wmax > 16 ? 16 : wmax;
-  // warps per block: all that fit when the launch fills the GPU anyway, else spread the tasks over the SMs
+  // warps per block: all that fit when the launch fills the GPU anyway, else spread the tasks over the SMs ...
   int W = (tasks + num_sms() - 1) / num_sms();
   W = W > wmax ? wmax : (W < 1 ? 1 : W);
   if (g_tuning.scatter_cc > 0 && g_tuning.scatter_cc <= wmax) W = g_tuning.scatter_cc;
+  // ... and when fewer warps than fit would be busy, 2 or 4 warps share a task (every split-th unit of its rows each)
+  int split = 1;
+  while (split < 4 && W * split * 2 <= wmax && (long long)npoints * nsample / (32 * 2 * split) >= 64) split *= 2;
+  if (g_tuning.priv_split == 1 || g_tuning.priv_split == 2 || g_tuning.priv_split == 4) {
+    split = g_tuning.priv_split;
+    while (split > 1 && W * split > wmax) split >>= 1;
+  }
+  W *= split;
   // positions per lane and load; a unit of 32 * VL positions holds NRG = 32 * VL / nsample whole rows (or a piece of one)
   int VL = 1;
   if (S == 32) {
-    VL = W <= 8 ? 4 : 2;  // few warps per SM (large n): wider loads keep more bytes in flight
+    VL = nsample >= 64 ? 4 : 2;  // a unit of two rows either way (B200 sweep: profiles/r02_bwd_private_sweep.json)
     const int knob = g_tuning.priv_vl;
     if ((knob == 1 || knob == 2 || knob == 4) && (nsample % (32 * knob) == 0 || (32 * knob) % nsample == 0)) VL = knob;
     while (VL > 1 && per % (32 * VL) != 0) VL >>= 1;  // units are whole: an odd number of short rows takes narrower loads
   }
   const int NRG = S == 32 && nsample < 32 * VL ? 32 * VL / nsample : 1;
-#define GB_PRIV(SV, VV, NV, R8, R16)                                                                                                \
-  return W <= 8 ? launch_private<CW, SV, VV, NV, R8, 256>(src, src_stride, idx, grad, c, n, per, groups, tasks, W, overwrite, nsample, s)    \
-                : launch_private<CW, SV, VV, NV, R16, 512>(src, src_stride, idx, grad, c, n, per, groups, tasks, W, overwrite, nsample, s)
+  // ring depths (units in flight per warp): as deep as the register budget of the block size allows; two-channel units are
+  // half as large, so their rings are deeper
+#define GB_PRIV(SV, VV, NV, R8, R16_)                                                                                                \
+  return W <= 8 ? launch_private<CW, SV, VV, NV, R8, 256>(src, src_stride, idx, grad, c, n, per, groups, tasks, W, split, overwrite, nsample, s)    \
+                : launch_private<CW, SV, VV, NV, (CW == 2 ? (R16_ * 3) / 2 : R16_), 512>(src, src_stride, idx, grad, c, n, per, groups, tasks, W, split, overwrite, nsample, s)
   if (S == 32 && VL == 4 && NRG == 4) GB_PRIV(32, 4, 4, 8, 4);
   if (S == 32 && VL == 4 && NRG == 2) GB_PRIV(32, 4, 2, 8, 4);
   if (S == 32 && VL == 4) GB_PRIV(32, 4, 1, 8, 4);

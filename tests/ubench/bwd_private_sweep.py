@@ -28,7 +28,8 @@ def main():
     fidx = A.furthest_point_sampling(xyz, 2048).long()
     lv0 = torch.gather(xyz, 1, fidx[:, :, None].expand(-1, -1, 3)).contiguous()
     shapes = {"irm0": (2048, 2048, 64, 128, 0.08), "irm1": (1024, 1024, 32, 256, 0.2), "irm2": (512, 512, 16, 256, 0.4),
-              "sa2": (2048, 1024, 32, 128, 0.1), "sa3": (1024, 512, 16, 256, 0.2)}
+              "sa2": (2048, 1024, 32, 128, 0.1), "sa3": (1024, 512, 16, 256, 0.2), "irm3": (256, 256, 16, 256, 0.6),
+              "sa4": (512, 256, 16, 256, 0.3)}
     rows = []
     a = torch.empty(1 << 28, dtype=torch.float32, device=dev)
     b = torch.empty_like(a)
@@ -51,20 +52,19 @@ def main():
         vls = (1, 2, 4) if ns >= 32 else (1,)
         for vl in vls:
             for cw in (4, 2):
-                for w in (0, -1):  # -1: dry run (loads only)
-                    _lib.set_tuning("priv_dry", 1 if w < 0 else 0)
-                    w = max(w, 0)
+                for w, sp in ((0, 0),):
+                    _lib.set_tuning("priv_split", sp)
                     _lib.set_tuning("priv_vl", vl)
                     _lib.set_tuning("priv_cw", cw)
                     _lib.set_tuning("scatter_cc", w)
                     got = A.group_points_grad(gout, idx, n)
                     ok = (got - ref).abs().max().item() <= 1e-5 * max(ref.abs().max().item(), 1.0)
                     t = timeit(lambda: A.group_points_grad(gout, idx, n), iters=7)
-                    row = {"shape": label, "vl": vl, "cw": cw, "W": w, "dry": _lib.get_tuning("priv_dry"), "us": round(t, 1), "hbm_frac": round(nbytes / (t * 1e-6) / 1e9 / HBM, 3),
+                    row = {"shape": label, "vl": vl, "cw": cw, "W": w, "split": sp, "us": round(t, 1), "hbm_frac": round(nbytes / (t * 1e-6) / 1e9 / HBM, 3),
                            "ok": bool(ok)}
                     rows.append(row)
                     print(json.dumps(row), flush=True)
-    for k in ("priv_vl", "priv_cw", "scatter_cc", "priv_dry"):
+    for k in ("priv_vl", "priv_cw", "scatter_cc", "priv_split"):
         _lib.set_tuning(k, 0)
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     with open(args.out, "w") as f:
