@@ -520,6 +520,7 @@ def main():
     ap.add_argument("--strong-total", type=int, default=32, help="scenes in total of the strong-scaling leg")
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the reference-kernels leg (oracle/_ref on this GPU)")
     ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE configs 1-4 leg")
+    ap.add_argument("--tune", action="append", default=[], metavar="KEY=VALUE", help="libgbops tuning knob for experiments (gb_set_tuning)")
     ap.add_argument("--baseline-batch", type=int, default=8, help="scenes per step of the reference-kernels leg")
     ap.add_argument("--no-overlap", action="store_true", help="run the sampling chain and the collision tests on the main stream")
     ap.add_argument("--unfused-crops", action="store_true",
@@ -543,6 +544,9 @@ def main():
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: graspbalance_b200 has no CPU fallback (use --impl reference for the CPU arm)")
     _lib.lib()  # fail loudly now if libgbops.so is missing
+    for kv in args.tune:
+        key, _, val = kv.partition("=")
+        _lib.set_tuning(key, int(val))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:

@@ -76,6 +76,10 @@ bool scatter_private_supported(int b, int c, int n, int npoints, int nsample, si
 int scatter_private(const float *src, size_t src_stride, const int *idx, float *grad, int b, int c, int n, int npoints, int nsample,
                     int overwrite, cudaStream_t s);
 
+// query.cu: three nearest neighbours through the uniform cell grid (exact: same indices and distances as the full scan)
+bool three_nn_grid_worth(int b, int n, int m);
+int three_nn_grid(const float *unknown, const float *known, float *dist2, int *idx, float *weight, int b, int n, int m, cudaStream_t s);
+
 // squared distance exactly as nvcc contracts the reference's (a-b)*(a-b)+(c-d)*(c-d)+(e-f)*(e-f):
 // FMUL on the y term, then FFMA x, then FFMA z (SASS of ball_query_gpu.cu / sampling_gpu.cu / interpolate_gpu.cu).
 __device__ __forceinline__ float sqdist3(float dx, float dy, float dz) {

@@ -140,6 +140,11 @@ __global__ void __launch_bounds__(kGridThreads) grid_build_kernel(const float *_
     h.maxabs = maxabs, h.pad0 = h.pad1 = h.pad2 = 0.f;
     // cell edge = cell_frac x the reach of a query (its box then spans <= 2 / cell_frac + 1 cells per axis), >= extent / 32,
     // <= 4096 cells in total
+    if (reach < 0.f) {  // nearest-neighbour search: twice the spacing n points have on a surface spanning the two largest extents
+      const float e0 = fmaxf(ext[0], fmaxf(ext[1], ext[2])), e2 = fminf(ext[0], fminf(ext[1], ext[2]));
+      const float e1 = ext[0] + ext[1] + ext[2] - e0 - e2;
+      reach = 2.f * sqrtf(fmaxf(e0 * fmaxf(e1, 1e-3f * e0), 1e-30f) / (float)max(n, 1));
+    }
     const float E = __fmaf_rn(reach, 1.0001f, 1e-5f * maxabs);
     float s = fmaxf(E * cell_frac, emax / kGridMaxDim);
     h.gx = h.gy = h.gz = 1, h.inv = 0.f;
@@ -653,6 +658,113 @@ static int launch_query(const float *new_xyz, const float *xyz, const float *rot
   count_launch();
   const int rc = finish_launch();
   if (scratch) cudaFreeAsync(scratch, s);
+  return rc;
+}
+
+
+// ---- three nearest neighbours through the cell grid -----------------------------------------------------------------------
+// three_nn_kernel (three_nn.cu) tests every unknown point against all m known points (20.5 M tests per 20k-point scene).
+// Here the known points are sorted into the uniform grid above (cell edge ~ the spacing of m points on a surface) and a
+// thread scans the box of (2R+1)^3 cells around its point, R = 1, 2, 4, ... until its third-best squared distance is
+// strictly below the squared distance to the nearest face of the box that still has cells behind it (minus a margin far
+// above fp32 rounding) -- then no point outside the box can enter the result or tie with it.  Candidates arrive in cell
+// order, so insertion compares (distance, index) lexicographically: exactly the result of the reference's ascending scan
+// with strict `<` (interpolate_gpu.cu:38-56), bit for bit (same sqdist3 arithmetic).  NaN coordinates never win (d < b is
+// false), as in the full scan.
+constexpr int kNNGridThreads = 256;
+
+template <bool WEIGHTS>
+__global__ void __launch_bounds__(kNNGridThreads) three_nn_grid_kernel(const float *__restrict__ unknown, const float4 *__restrict__ sorted,
+                                                                       const int *__restrict__ cell_start,
+                                                                       const GridHeader *__restrict__ hdr, float *__restrict__ dist2,
+                                                                       int *__restrict__ idx, float *__restrict__ weight, int n, int m) {
+  const int scene = blockIdx.y;
+  const int j = blockIdx.x * kNNGridThreads + threadIdx.x;
+  if (j >= n) return;
+  const GridHeader h = hdr[scene];
+  sorted += (size_t)scene * m;
+  cell_start += (size_t)scene * (kGridMaxCells + 1);
+  const size_t uj = (size_t)scene * n + j;
+  const float ux = __ldg(unknown + uj * 3), uy = __ldg(unknown + uj * 3 + 1), uz = __ldg(unknown + uj * 3 + 2);
+  const float inf = __int_as_float(0x7f800000);
+  const float s = h.inv > 0.f ? 1.0f / h.inv : inf;  // cell edge
+  const int cx = grid_cell(ux, h.ox, h.inv, h.gx), cy = grid_cell(uy, h.oy, h.inv, h.gy), cz = grid_cell(uz, h.oz, h.inv, h.gz);
+  float b1, b2, b3;
+  int i1, i2, i3;
+  for (int R = 1;; R <<= 1) {
+    b1 = b2 = b3 = inf;
+    i1 = i2 = i3 = 0;
+    const int x0 = max(cx - R, 0), x1 = min(cx + R, h.gx - 1), y0 = max(cy - R, 0), y1 = min(cy + R, h.gy - 1);
+    const int z0 = max(cz - R, 0), z1 = min(cz + R, h.gz - 1);
+    for (int z = z0; z <= z1; ++z) {
+      for (int y = y0; y <= y1; ++y) {
+        const int row = (z * h.gy + y) * h.gx;
+        const int e1 = __ldg(cell_start + row + x1 + 1);
+        for (int e = __ldg(cell_start + row + x0); e < e1; ++e) {
+          const float4 p = __ldg(sorted + e);
+          const float d = sqdist3(ux - p.x, uy - p.y, uz - p.z);
+          const int k = __float_as_int(p.w);
+          if (d < b3 || (d == b3 && k < i3)) {  // (distance, index) ascending: what the reference's index-order scan keeps
+            if (d < b1 || (d == b1 && k < i1)) {
+              b3 = b2, i3 = i2, b2 = b1, i2 = i1, b1 = d, i1 = k;
+            } else if (d < b2 || (d == b2 && k < i2)) {
+              b3 = b2, i3 = i2, b2 = d, i2 = k;
+            } else {
+              b3 = d, i3 = k;
+            }
+          }
+        }
+      }
+    }
+    // distance to the nearest face of the box with cells behind it
+    float dmin = inf;
+    if (x0 > 0) dmin = fminf(dmin, ux - (h.ox + (float)x0 * s));
+    if (x1 < h.gx - 1) dmin = fminf(dmin, (h.ox + (float)(x1 + 1) * s) - ux);
+    if (y0 > 0) dmin = fminf(dmin, uy - (h.oy + (float)y0 * s));
+    if (y1 < h.gy - 1) dmin = fminf(dmin, (h.oy + (float)(y1 + 1) * s) - uy);
+    if (z0 > 0) dmin = fminf(dmin, uz - (h.oz + (float)z0 * s));
+    if (z1 < h.gz - 1) dmin = fminf(dmin, (h.oz + (float)(z1 + 1) * s) - uz);
+    if (dmin == inf) break;  // the box is the whole grid
+    const float safe = dmin * 0.999f - 1e-4f * (h.maxabs + s);  // cell assignment and face positions are rounded in fp32
+    if (safe > 0.f && b3 < safe * safe) break;
+    if (!(ux == ux && uy == uy && uz == uz)) R = max(R, kGridMaxDim);  // a NaN query never terminates early: one pass over everything
+  }
+  // fewer than three finite distances: the reference leaves (inf, index 0) in the unfilled slots; an unfilled slot here holds
+  // (inf, 0) as well because no candidate ever compared below inf.  But a known point whose distance is NaN is skipped by
+  // both scans, and one at distance +inf ties with the initial state: the reference keeps index 0 (strict <), so do we.
+  if (WEIGHTS) {
+    b1 = __fsqrt_rn(b1), b2 = __fsqrt_rn(b2), b3 = __fsqrt_rn(b3);
+    const float r1 = __frcp_rn(__fadd_rn(b1, 1e-8f)), r2 = __frcp_rn(__fadd_rn(b2, 1e-8f)), r3 = __frcp_rn(__fadd_rn(b3, 1e-8f));
+    const float norm = __fadd_rn(__fadd_rn(r1, r3), r2);  // torch.sum over a 3-element inner dimension: (r0 + r2) + r1
+    weight[uj * 3] = __fdiv_rn(r1, norm), weight[uj * 3 + 1] = __fdiv_rn(r2, norm), weight[uj * 3 + 2] = __fdiv_rn(r3, norm);
+  }
+  dist2[uj * 3] = b1, dist2[uj * 3 + 1] = b2, dist2[uj * 3 + 2] = b3;
+  idx[uj * 3] = i1, idx[uj * 3 + 1] = i2, idx[uj * 3 + 2] = i3;
+}
+
+// Grid path of gb_three_nn / gb_three_nn_weights: worth its build (one CTA per scene) when many unknowns meet many knowns.
+bool three_nn_grid_worth(int b, int n, int m) {
+  if (g_tuning.query_mode == 1) return false;
+  return m >= 256 && m < (1 << 24) && (long long)n * m >= (1LL << 21) && b <= 65535;
+}
+
+int three_nn_grid(const float *unknown, const float *known, float *dist2, int *idx, float *weight, int b, int n, int m, cudaStream_t s) {
+  void *scratch = nullptr;
+  const size_t sorted_bytes = (size_t)b * m * sizeof(float4);
+  const size_t cells_bytes = (((size_t)b * (kGridMaxCells + 1) * sizeof(int)) + 15) & ~(size_t)15;
+  cudaError_t e = scratch_alloc(&scratch, sorted_bytes + cells_bytes + (size_t)b * sizeof(GridHeader), s);
+  if (e != cudaSuccess) return (int)e;
+  float4 *sorted = reinterpret_cast<float4 *>(scratch);
+  int *cell_start = reinterpret_cast<int *>(reinterpret_cast<unsigned char *>(scratch) + sorted_bytes);
+  GridHeader *hdr = reinterpret_cast<GridHeader *>(reinterpret_cast<unsigned char *>(scratch) + sorted_bytes + cells_bytes);
+  grid_build_kernel<<<b, kGridThreads, 0, s>>>(known, m, -1.f, 1, 1.0f, sorted, cell_start, hdr);
+  count_launch();
+  const dim3 grid((n + kNNGridThreads - 1) / kNNGridThreads, b);
+  if (weight) three_nn_grid_kernel<true><<<grid, kNNGridThreads, 0, s>>>(unknown, sorted, cell_start, hdr, dist2, idx, weight, n, m);
+  else three_nn_grid_kernel<false><<<grid, kNNGridThreads, 0, s>>>(unknown, sorted, cell_start, hdr, dist2, idx, nullptr, n, m);
+  count_launch();
+  const int rc = finish_launch();
+  cudaFreeAsync(scratch, s);
   return rc;
 }
 

@@ -26,6 +26,9 @@
 namespace gb {
 
 constexpr size_t kPrivSmemBudget = 227u * 1024u;
+#ifndef GB_PRIV_RING_NUM
+#define GB_PRIV_RING_NUM 3  // two-channel units: ring depth x 3/2
+#endif
 
 
 template <int CW, int VL>
@@ -411,7 +414,7 @@ static int scatter_private_cw(const float *src, size_t src_stride, const int *id
   // half as large, so their rings are deeper
 #define GB_PRIV(SV, VV, NV, R8, R16_)                                                                                                \
   return W <= 8 ? launch_private<CW, SV, VV, NV, R8, 256>(src, src_stride, idx, grad, c, n, per, groups, tasks, W, split, overwrite, nsample, s)    \
-                : launch_private<CW, SV, VV, NV, (CW == 2 ? (R16_ * 3) / 2 : R16_), 512>(src, src_stride, idx, grad, c, n, per, groups, tasks, W, split, overwrite, nsample, s)
+                : launch_private<CW, SV, VV, NV, (CW == 2 ? (R16_ * GB_PRIV_RING_NUM) / 2 : R16_), 512>(src, src_stride, idx, grad, c, n, per, groups, tasks, W, split, overwrite, nsample, s)
   if (S == 32 && VL == 4 && NRG == 4) GB_PRIV(32, 4, 4, 8, 4);
   if (S == 32 && VL == 4 && NRG == 2) GB_PRIV(32, 4, 2, 8, 4);
   if (S == 32 && VL == 4) GB_PRIV(32, 4, 1, 8, 4);

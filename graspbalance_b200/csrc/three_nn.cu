@@ -78,6 +78,7 @@ extern "C" int gb_three_nn(const float *unknown, const float *known, float *dist
   if (b < 0 || n < 0 || m < 0) return (int)cudaErrorInvalidValue;
   if (b == 0 || n == 0) return 0;  // nothing to do (empty tensors have null data pointers)
   if (!unknown || (m > 0 && !known) || !dist2 || !idx) return (int)cudaErrorInvalidValue;
+  if (gb::three_nn_grid_worth(b, n, m)) return gb::three_nn_grid(unknown, known, dist2, idx, nullptr, b, n, m, (cudaStream_t)stream);
   for (int b0 = 0; b0 < b; b0 += 65535) {  // the batch rides on gridDim.y: slabs of 65535 scenes
     const int bb = b - b0 < 65535 ? b - b0 : 65535;
     dim3 grid((n + gb::kNNThreads - 1) / gb::kNNThreads, bb);
@@ -96,6 +97,7 @@ extern "C" int gb_three_nn_weights(const float *unknown, const float *known, flo
   if (b < 0 || n < 0 || m < 0) return (int)cudaErrorInvalidValue;
   if (b == 0 || n == 0) return 0;
   if (!unknown || (m > 0 && !known) || !dist || !idx || !weight) return (int)cudaErrorInvalidValue;
+  if (gb::three_nn_grid_worth(b, n, m)) return gb::three_nn_grid(unknown, known, dist, idx, weight, b, n, m, (cudaStream_t)stream);
   for (int b0 = 0; b0 < b; b0 += 65535) {
     const int bb = b - b0 < 65535 ? b - b0 : 65535;
     dim3 grid((n + gb::kNNThreads - 1) / gb::kNNThreads, bb);
