@@ -70,15 +70,19 @@ def furthest_point_sampling(points, nsamples):
     return out
 
 
-def furthest_point_sampling_xyz(points, nsamples):
+def furthest_point_sampling_xyz(points, nsamples, max_cluster=0):
     """furthest_point_sampling + the coordinates of the samples (what gather_points fetches from the transposed cloud,
-    pointnet2_modules.py:151-158) in one launch: ([B,nsamples] i32, [B,nsamples,3] f32)."""
+    pointnet2_modules.py:151-158) in one launch: ([B,nsamples] i32, [B,nsamples,3] f32).  max_cluster > 0: at most that many
+    CTAs per scene (background sampling beside other kernels: fewer SMs touched, slower rounds, same picks)."""
     _contig(points, "points"); _is_float(points, "points")
     _need_cuda(points)
     B, N = points.shape[0], points.shape[1]
     out = torch.empty((B, int(nsamples)), dtype=torch.int32, device=points.device)
     new_xyz = torch.empty((B, int(nsamples), 3), dtype=torch.float32, device=points.device)
-    _lib.call("gb_fps_xyz", points, points.data_ptr(), None, out.data_ptr(), new_xyz.data_ptr(), B, N, int(nsamples), 0)
+    if max_cluster:
+        _lib.call("gb_fps_xyz_hint", points, points.data_ptr(), None, out.data_ptr(), new_xyz.data_ptr(), B, N, int(nsamples), 0, int(max_cluster))
+    else:
+        _lib.call("gb_fps_xyz", points, points.data_ptr(), None, out.data_ptr(), new_xyz.data_ptr(), B, N, int(nsamples), 0)
     return out, new_xyz
 
 

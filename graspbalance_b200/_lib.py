@@ -22,6 +22,7 @@ SIGNATURES = {
     "gb_error_string": [_i],
     "gb_fps": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "gb_fps_xyz": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "gb_fps_xyz_hint": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "gb_fps_segments": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "gb_gather_fwd": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "gb_gather_bwd": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
@@ -106,6 +107,7 @@ PROFILER = None
 ALGO_BYTES = {
     "gb_fps": lambda a: a[3] * (12 * a[4] + 4 * a[5]),                                   # b*(12n + 4m)
     "gb_fps_xyz": lambda a: a[4] * (12 * a[5] + 16 * a[6]),                               # b*(12n + 4m + 12m)
+    "gb_fps_xyz_hint": lambda a: a[4] * (12 * a[5] + 16 * a[6]),
     "gb_fps_segments": lambda a: a[4] * (12 * a[5] + 4 * a[6]),                           # <= nseg*(12 max_n + 4 max_m)
     "gb_gather_fwd": lambda a: a[3] * (4 * a[4] * a[5] + 4 * a[6] + 4 * a[4] * a[6]),     # b*(4cn + 4m + 4cm)
     "gb_gather_bwd": lambda a: a[3] * (4 * a[4] * a[5] + 4 * a[6] + 4 * a[4] * a[6]),

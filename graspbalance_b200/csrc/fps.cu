@@ -355,7 +355,8 @@ static int floor_log2(int v) {
 
 using namespace gb;
 
-static int fps_impl(const float *xyz, float *temp, int *idx, float *new_xyz, int b, int n, int m, int variant, gb_stream_t stream) {
+static int fps_impl(const float *xyz, float *temp, int *idx, float *new_xyz, int b, int n, int m, int variant, gb_stream_t stream,
+                    int max_cluster = 0) {
   if (b < 0 || n < 0 || m < 0 || (variant != GB_FPS_A && variant != GB_FPS_B)) return (int)cudaErrorInvalidValue;
   if (b == 0 || m == 0) return 0;  // nothing to do (empty tensors have null data pointers)
   if (n == 0 || !xyz || !idx) return (int)cudaErrorInvalidValue;  // samples of an empty cloud are undefined (the reference reads out of bounds)
@@ -378,6 +379,9 @@ static int fps_impl(const float *xyz, float *temp, int *idx, float *new_xyz, int
     // sweep saves).  Measured on B200, 32 scenes of 20000 points: C=4 x 256 threads 0.75 us/round, C=8 x 1024 3.3 us.
     C = 8;
     while (C > 1 && ((long)b * C > (long)sms || n / C < 1024)) C >>= 1;
+    // background sampling (the caller has the whole step to hide the rounds' latency): fewer, fuller CTAs -- each takes a
+    // whole SM's registers, so the SMs they do not use are entirely free for the kernels they run beside
+    if (max_cluster > 0 && C > max_cluster) C = max_cluster;
     // capacity: the largest per-CTA register tile is 256 threads x 40 points (= 512 x 20 = 1024 x 10)
     while (C < 16 && (long)C * 256 * 40 < n) C <<= 1;
   }
@@ -434,6 +438,17 @@ extern "C" int gb_fps(const float *xyz, float *temp, int *idx, int b, int n, int
 extern "C" int gb_fps_xyz(const float *xyz, float *temp, int *idx, float *new_xyz, int b, int n, int m, int variant, gb_stream_t stream) {
   if (!new_xyz && b > 0 && m > 0) return (int)cudaErrorInvalidValue;
   return fps_impl(xyz, temp, idx, new_xyz, b, n, m, variant, stream);
+}
+
+/* gb_fps_xyz with a footprint hint: at most max_cluster (1, 2, 4, 8; 0 = automatic) CTAs per scene, as far as a scene still
+ * fits their registers.  The automatic choice minimises the latency of the m - 1 dependent rounds (one CTA per SM, 4 CTAs per
+ * scene for 32 scenes of 20000 points); a caller that samples the NEXT step's clouds beside the current step's work
+ * (pipeline.OpPipeline.run(prefetch=...)) prefers 2: the rounds get 40 % slower but only 64 SMs are touched, and the
+ * register-heavy kernels of the step keep the other 84 to themselves (B200, 32 scenes: 11.3 -> 10.9 ms per step).  Same picks. */
+extern "C" int gb_fps_xyz_hint(const float *xyz, float *temp, int *idx, float *new_xyz, int b, int n, int m, int variant, int max_cluster,
+                               gb_stream_t stream) {
+  if (max_cluster < 0 || max_cluster > 16) return (int)cudaErrorInvalidValue;
+  return fps_impl(xyz, temp, idx, new_xyz, b, n, m, variant, stream, max_cluster);
 }
 
 /* Segmented FPS: nseg independent point sets of different sizes packed in one array, one launch -- the per-object loop of

@@ -134,12 +134,15 @@ class OpPipeline:
         return [(torch.empty((self.B, m), dtype=torch.int32, device=self.device),
                  torch.empty((self.B, m, 3), dtype=torch.float32, device=self.device)) for (m, _, _, _) in SA_SPECS]
 
-    def sampling_chain(self, xyz, into):
+    def sampling_chain(self, xyz, into, background=False):
         """The four furthest_point_sample + gather_operation calls of a step (pointnet2_modules.py:151-158), which depend on
-        the coordinates only, on the CURRENT stream, results written into the buffers of alloc_samples()."""
+        the coordinates only, on the CURRENT stream, results written into the buffers of alloc_samples().  background: the
+        chain runs beside a whole step of other kernels, so it is launched with at most two CTAs per scene -- slower rounds
+        on 64 SMs instead of faster ones on 128, and the register-heavy kernels of the step keep the other SMs to themselves."""
         cur = xyz
         for (inds_buf, xyz_buf), (npoint, _, _, _) in zip(into, SA_SPECS):
-            inds, new_xyz = pu.furthest_point_sample_xyz(cur, npoint)
+            # (a shard of fewer than 8 scenes has no step long enough to hide slower rounds: automatic shape)
+            inds, new_xyz = pu.furthest_point_sample_xyz(cur, npoint, 2 if background and self.B >= 8 else 0)
             inds_buf.copy_(inds)
             xyz_buf.copy_(new_xyz)
             cur = xyz_buf
@@ -238,7 +241,7 @@ class OpPipeline:
                     with torch.cuda.stream(self._fps_stream):
                         if len(prefetch) > 2 and prefetch[2] is not None:
                             self._fps_stream.wait_event(prefetch[2])  # the next step's coordinates have arrived
-                        self.sampling_chain(prefetch[0], prefetch[1])
+                        self.sampling_chain(prefetch[0], prefetch[1], background=True)
                         prefetch_done = torch.cuda.Event()
                         prefetch_done.record(self._fps_stream)
                 self._aux_stream.wait_event(start)

@@ -40,17 +40,19 @@ class FurthestPointSamplingXYZ(Function):
     gradient to xyz on this path (callers that need one use gather_operation)."""
 
     @staticmethod
-    def forward(ctx, xyz, npoint):
-        inds, new_xyz = _ext.furthest_point_sampling_xyz(xyz, npoint)
+    def forward(ctx, xyz, npoint, max_cluster=0):
+        inds, new_xyz = _ext.furthest_point_sampling_xyz(xyz, npoint, max_cluster)
         ctx.mark_non_differentiable(inds, new_xyz)
         return inds, new_xyz
 
     @staticmethod
     def backward(ctx, a=None, b=None):
-        return None, None
+        return None, None, None
 
 
-furthest_point_sample_xyz = FurthestPointSamplingXYZ.apply
+def furthest_point_sample_xyz(xyz, npoint, max_cluster=0):
+    """max_cluster > 0: background sampling -- at most that many CTAs per scene (gb_fps_xyz_hint); same picks."""
+    return FurthestPointSamplingXYZ.apply(xyz, npoint, max_cluster)
 
 
 def furthest_point_sample_segments(points, counts, nsamples):

@@ -54,6 +54,13 @@ GB_API int gb_fps(const float *xyz, float *temp, int *idx, int b, int n, int m, 
 GB_API int gb_fps_xyz(const float *xyz, float *temp, int *idx, float *new_xyz, int b, int n, int m, int variant,
                gb_stream_t stream);
 
+/* gb_fps_xyz (new_xyz may be NULL: gb_fps) with a footprint hint: at most max_cluster (0 = automatic, else 1..16) CTAs per
+ * scene, as far as a scene still fits their registers.  The automatic shape minimises the latency of the m - 1 dependent
+ * rounds; a caller that samples the NEXT step's clouds beside the current step's kernels prefers fewer, fuller CTAs, which
+ * leave whole SMs free.  Same picks whatever the hint. */
+GB_API int gb_fps_xyz_hint(const float *xyz, float *temp, int *idx, float *new_xyz, int b, int n, int m, int variant, int max_cluster,
+                    gb_stream_t stream);
+
 /* Segmented FPS: nseg independent point sets of different sizes packed in one array, one launch -- the per-object loop of
  * ObjectBalanceSampling (TrainModel/modules.py:186-213 calls furthest_point_sample once per object of every scene).
  * seg [nseg,4] i32 on the DEVICE (16-byte aligned) = (first point, points, samples, first output slot) per segment; idx and
