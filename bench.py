@@ -614,6 +614,9 @@ def main():
                 ev.record(copy_stream)
             return ev
 
+        # the device input sets were allocated on the compute stream's pool: whatever pending compute-stream work last used
+        # those blocks must finish before the copy stream writes into them
+        copy_stream.wait_stream(main)
         ready = upload(0)
         if pf["on"]:
             main.wait_event(ready)
