@@ -240,7 +240,11 @@ GB_API int gb_voxel_means(const double *points, const long long *order, const lo
  *   "interp_mode"  bit 0: plain stores; bit 1: generic fwd kernel; bit 2: atomic backward
  *   "query_qpw"    0 = auto, else 1/2/4 queries per warp in the full-scan query kernel
  *   "query_mode"   0 = auto, 1 = full scan only, 2 = always build the cell grid
- *   "scatter_cc"   0 = auto, else 1/2/4 channels per CTA in the sorted backward
+ *   "scatter_cc"   0 = auto, else 1/2/4 channels per CTA in the sorted backward (warps per block in the warp-private one)
+ *   "scatter_mode" bit 0: no dense sorted backward; bit 2: targets in index order; bit 3: never the warp-private backward;
+ *                  bit 4: the warp-private backward for any number of tasks
+ *   "priv_vl" / "priv_cw" / "priv_split"  warp-private backward: positions per lane and load (1/2/4), channels per warp
+ *                  (2/4), warps sharing a task (1/2/4); 0 = auto
  */
 GB_API int gb_set_tuning(const char *key, int value);
 GB_API int gb_get_tuning(const char *key, int *value);

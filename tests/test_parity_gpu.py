@@ -760,3 +760,17 @@ def test_collision_pack_culling_never_changes_the_counts(dev):
         want = oracle.collision_counts(pts, Tm, Rm, gs["heights"], gs["depths"], gs["widths"], 0.05)
         np.testing.assert_array_equal(got, want)
     assert int(want[:, 0].sum()) > 0
+
+
+@pytest.mark.parametrize("B,N,m", [(3, 20000, 512), (2, 2048, 300), (4, 9000, 64)])
+def test_fps_footprint_hint_never_changes_the_picks(dev, B, N, m):
+    """gb_fps_xyz_hint: fewer, fuller CTAs per scene for a sampling chain that runs beside other kernels -- any cap gives the
+    oracle's picks and coordinates (the tie order does not depend on the decomposition)."""
+    xyz_np = scenes.scene_batch(range(B), N, "tabletop")
+    xyz_np[:, N // 2:N // 2 + 200] = xyz_np[:, :200]  # duplicated points: ties
+    xyz = T(xyz_np, dev)
+    want = oracle.furthest_point_sample(xyz_np, m, "A")
+    for cap in (0, 1, 2, 4, 8, 16):
+        inds, new_xyz = pu.furthest_point_sample_xyz(xyz, m, cap)
+        np.testing.assert_array_equal(inds.cpu().numpy(), want)
+        assert torch.equal(new_xyz, torch.gather(xyz, 1, inds.long().unsqueeze(-1).expand(-1, -1, 3)))
