@@ -29,6 +29,9 @@ constexpr size_t kPrivSmemBudget = 227u * 1024u;
 #ifndef GB_PRIV_RING_NUM
 #define GB_PRIV_RING_NUM 3  // two-channel units: ring depth x 3/2
 #endif
+#ifndef GB_PRIV_TWOSET
+#define GB_PRIV_TWOSET -1  // experiments: 0 / 1 force the slot ring / the two register sets for every shape
+#endif
 
 
 template <int CW, int VL>
@@ -87,10 +90,11 @@ struct PrivAcc<2> {
 
 // Padded rows (an ascending run followed by copies of the row's first target t0: how ball_query_gpu.cu:31-40 and
 // cylinder_query_gpu.cu:68-75 fill rows with fewer than nsample hits): every lane hands over the sum of its copies' values;
-// the LG lanes of a row (and plane) add them up and the row's first lane updates t0 once.  Out of line: scalar arguments
-// only, the unrolled hot loop stays small.
+// the LG lanes of a row (and plane) add them up and the row's first lane updates t0 once.  Two forms: inline (a call waits
+// for every scoreboard, i.e. drains all loads in flight: the kernels with many padded rows) and out of line behind scalar
+// arguments (keeps the unrolled hot loop small: everything else).
 template <int CW, int NRG, int LG>
-__device__ __noinline__ void priv_add_copies(typename PrivAcc<CW>::T *acc, int t0, float s0, float s1, float s2, float s3) {
+__device__ __forceinline__ void priv_add_copies(typename PrivAcc<CW>::T *acc, int t0, float s0, float s1, float s2, float s3) {
   float sum[CW];
   sum[0] = s0, sum[1] = s1;
   if (CW == 4) sum[CW - 2] = s2, sum[CW - 1] = s3;
@@ -109,6 +113,10 @@ __device__ __noinline__ void priv_add_copies(typename PrivAcc<CW>::T *acc, int t
     }
     __syncwarp();
   }
+}
+template <int CW, int NRG, int LG>
+__device__ __noinline__ void priv_add_copies_call(typename PrivAcc<CW>::T *acc, int t0, float s0, float s1, float s2, float s3) {
+  priv_add_copies<CW, NRG, LG>(acc, t0, s0, s1, s2, s3);
 }
 
 // Rows that are neither ascending nor padded (kNN order, arbitrary caller tensors, out-of-range entries), out of line: per
@@ -173,6 +181,9 @@ __global__ void __launch_bounds__(MAXT, 1) scatter_private_kernel(const float *_
                                                                   int tasks, int overwrite, size_t src_stride, int ns, int split,
                                                                   int dry) {
   constexpr int H = 32 / S, PU = S * VL, LG = S == 32 ? 32 / NRG : S;  // LG lanes hold one row (piece)
+  // how the loads run ahead (see the main loop): two register sets for the few-wide-loads-per-unit shape of the 2048-target
+  // level (B200: 614 us against 698 with the slot ring), the slot ring for the rest (n = 1024: 242 us against 266)
+  constexpr bool kTwoSets = GB_PRIV_TWOSET >= 0 ? GB_PRIV_TWOSET != 0 : (CW == 2 && VL == 4);
   static_assert(S == 32 || (VL == 1 && NRG == 1), "planes take one position per lane");
   typedef typename PrivAcc<CW>::T AccT;
   extern __shared__ __align__(16) unsigned char s_raw[];
@@ -279,7 +290,8 @@ __global__ void __launch_bounds__(MAXT, 1) scatter_private_kernel(const float *_
 #pragma unroll
       for (int j = 0; j < CW; ++j) sum[j] += pad[q] ? u.v[j][q] : 0.f;
     }
-    priv_add_copies<CW, NRG, LG>(acc, t0, sum[0], sum[1], sum[2], sum[3]);
+    if (kTwoSets) priv_add_copies<CW, NRG, LG>(acc, t0, sum[0], sum[1], sum[2], sum[3]);
+    else priv_add_copies_call<CW, NRG, LG>(acc, t0, sum[0], sum[1], sum[2], sum[3]);
 #pragma unroll 1
     for (int r = 0; r < NRG; ++r) {
       if (NRG == 1 || rg == r) {
@@ -299,15 +311,43 @@ __global__ void __launch_bounds__(MAXT, 1) scatter_private_kernel(const float *_
     }
   };
 
-  PrivUnit<CW, VL> ring[R];
+  // Loads run ahead in a register ring (the only latency hiding a 7..14-warp SM has).  ptxas tracks every global load of
+  // this kernel with ONE scoreboard, so the first use of a loaded register after the loop's back edge waits for ALL loads in
+  // flight, the youngest included: the slot-by-slot ring stalls for a full memory latency once per round (14-17 % of a
+  // warp's time in ncu's source view).  Two register sets of G units avoid that -- a set is refilled right after the FIRST
+  // unit of the other set, so whatever is in flight at a wait is G - 1 units old -- at the price of load bursts, which the
+  // shapes with many narrow loads per unit do not like (their LDS latency doubles).
   const int my_units = live ? (units - part + split - 1) / split : 0;  // units part, part + split, ...
+  constexpr int G = R / 2;
+  PrivUnit<CW, VL> ring[kTwoSets ? 2 * G : R];
+  if (kTwoSets) {
 #pragma unroll
-  for (int r = 0; r < R; ++r) load(ring[r], part + r * split);
-  for (int u0 = 0; u0 < my_units; u0 += R) {
+    for (int g = 0; g < G; ++g) load(ring[g], part + g * split);
+    for (int u0 = 0; u0 < my_units; u0 += 2 * G) {
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      if (u0 + r < my_units) process(ring[r]);  // warp-uniform
-      load(ring[r], part + (u0 + R + r) * split);
+      for (int g = 0; g < G; ++g) {
+        if (u0 + g < my_units) process(ring[g]);  // warp-uniform
+#pragma unroll
+        for (int q = 0; q < G; ++q)
+          if ((GB_PRIV_TWOSET == 2 ? q * (G - 2) / G : 0) == g) load(ring[G + q], part + (u0 + G + q) * split);
+      }
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        if (u0 + G + g < my_units) process(ring[G + g]);
+#pragma unroll
+        for (int q = 0; q < G; ++q)
+          if ((GB_PRIV_TWOSET == 2 ? q * (G - 2) / G : 0) == g) load(ring[q], part + (u0 + 2 * G + q) * split);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < R; ++r) load(ring[r], part + r * split);
+    for (int u0 = 0; u0 < my_units; u0 += R) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        if (u0 + r < my_units) process(ring[r]);
+        load(ring[r], part + (u0 + R + r) * split);
+      }
     }
   }
   __syncwarp();
