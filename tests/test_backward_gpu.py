@@ -114,3 +114,23 @@ def test_group_bwd_dispatch_small_batches_keep_the_sorted_path(dev):
     want = torch.zeros((1, 16, 512), dtype=torch.float64, device=dev)
     want.scatter_add_(2, idx.long().reshape(1, 1, -1).expand(-1, 16, -1), gout.double().reshape(1, 16, -1))
     _close(got, want)
+
+
+@pytest.mark.parametrize("B,C,n,m,ns", [(16, 3, 20000, 1024, 64), (50, 1, 700, 33, 3), (24, 2, 5000, 128, 16)])
+def test_group_bwd_few_channels_single_launch(dev, B, C, n, m, ns):
+    """c < 4 (the grouped coordinates' gradient) with at least 48 output rows: one launch with the row sums in shared memory,
+    set and accumulate forms, 16-byte aligned and ragged entry counts, against an fp64 scatter_add."""
+    g = torch.Generator(device="cpu").manual_seed(11)
+    idx = torch.randint(0, n, (B, m, ns), generator=g, dtype=torch.int32)
+    idx[:, :, ns // 2:] = idx[:, :, :1]  # padded rows: many copies of one target
+    gout = torch.randn((B, C, m, ns), generator=g)
+    want = torch.zeros((B, C, n), dtype=torch.float64)
+    want.scatter_add_(2, idx.long().reshape(B, 1, -1).expand(-1, C, -1), gout.double().reshape(B, C, -1))
+    idx, gout = idx.to(dev), gout.to(dev)
+    l0 = _lib.launch_count()
+    got = gb_a.group_points_grad(gout, idx, n)
+    assert _lib.launch_count() - l0 == 1
+    _close(got.cpu(), want.float())
+    acc = torch.full((B, C, n), -0.5, device=dev)
+    gb_b.group_points_grad_wrapper(B, C, n, m, ns, gout, idx, acc)
+    _close(acc.cpu() + 0.5, want.float())
