@@ -97,7 +97,7 @@ class ClockSampler:
                 self.rows.append((time.time(), sm, self.max_sm, [name for name, b in bits if mask & b]))
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.02)
 
     def _pump(self):
         for line in self.proc.stdout:
@@ -509,7 +509,7 @@ def workload_name(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="gbops", choices=["gbops", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="scenes per GPU per step")
