@@ -68,6 +68,7 @@ static std::atomic<int> *tuning_slot(const char *key) {
   if (!strcmp(key, "priv_vl")) return &gb::g_tuning.priv_vl;
   if (!strcmp(key, "priv_dry")) return &gb::g_tuning.priv_dry;
   if (!strcmp(key, "priv_split")) return &gb::g_tuning.priv_split;
+  if (!strcmp(key, "priv_rows")) return &gb::g_tuning.priv_rows;
   if (!strcmp(key, "priv_cw")) return &gb::g_tuning.priv_cw;
   if (!strcmp(key, "query_mode")) return &gb::g_tuning.query_mode;
   if (!strcmp(key, "grid_cell_pct")) return &gb::g_tuning.grid_cell_pct;

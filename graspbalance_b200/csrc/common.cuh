@@ -57,6 +57,7 @@ struct Tuning {
   std::atomic<int> priv_vl{0};     // warp-private backward: positions per lane and load (1, 2, 4), 0 = automatic
   std::atomic<int> priv_dry{0};    // experiment: 1 = the warp-private backward only streams its inputs (wrong results)
   std::atomic<int> priv_split{0};  // warp-private backward: warps that share a task (1, 2, 4), 0 = automatic
+  std::atomic<int> priv_rows{0};   // warp-private backward, nsample 8 / 16: 1 = channel planes share a row (S = nsample), 2 = several rows per unit (S = 32), 0 = automatic
   std::atomic<int> priv_cw{0};     // warp-private backward: channels per warp and plane (2, 4), 0 = automatic
   std::atomic<int> query_mode{0};  // 1: never use the cell grid, 2: always use it (when the shape allows)
   std::atomic<int> grid_cell_pct{0};  // cell edge as a percentage of the query reach (0 = default 50)

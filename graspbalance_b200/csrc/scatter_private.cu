@@ -30,7 +30,7 @@ constexpr size_t kPrivSmemBudget = 227u * 1024u;
 #define GB_PRIV_RING_NUM 3  // two-channel units: ring depth x 3/2
 #endif
 #ifndef GB_PRIV_TWOSET
-#define GB_PRIV_TWOSET -1  // experiments: 0 / 1 force the slot ring / the two register sets for every shape
+#define GB_PRIV_TWOSET -1  // experiments: 0 = slot ring, 1 = two sets refilled in one burst, 2 = two sets, spread refill -- for every shape
 #endif
 
 
@@ -181,10 +181,10 @@ __global__ void __launch_bounds__(MAXT, 1) scatter_private_kernel(const float *_
                                                                   int tasks, int overwrite, size_t src_stride, int ns, int split,
                                                                   int dry) {
   constexpr int H = 32 / S, PU = S * VL, LG = S == 32 ? 32 / NRG : S;  // LG lanes hold one row (piece)
-  // how the loads run ahead (see the main loop): two register sets for the few-wide-loads-per-unit shape of the 2048-target
-  // level (B200: 614 us against 698 with the slot ring), the slot ring for the rest (n = 1024: 242 us against 266)
-  constexpr bool kTwoSets = GB_PRIV_TWOSET >= 0 ? GB_PRIV_TWOSET != 0 : (CW == 2 && VL == 4);
-  static_assert(S == 32 || (VL == 1 && NRG == 1), "planes take one position per lane");
+  // how the loads run ahead (see the main loop): two register sets for the kernels whose lanes span rows (S = 32), the slot
+  // ring for the channel-plane kernels (short rows, few targets)
+  constexpr bool kTwoSets = GB_PRIV_TWOSET >= 0 ? GB_PRIV_TWOSET != 0 : S == 32;
+  constexpr bool kSpread = GB_PRIV_TWOSET != 1;  // refill spread over the first G - 2 units of the other set
   typedef typename PrivAcc<CW>::T AccT;
   extern __shared__ __align__(16) unsigned char s_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -311,12 +311,12 @@ __global__ void __launch_bounds__(MAXT, 1) scatter_private_kernel(const float *_
     }
   };
 
-  // Loads run ahead in a register ring (the only latency hiding a 7..14-warp SM has).  ptxas tracks every global load of
-  // this kernel with ONE scoreboard, so the first use of a loaded register after the loop's back edge waits for ALL loads in
-  // flight, the youngest included: the slot-by-slot ring stalls for a full memory latency once per round (14-17 % of a
-  // warp's time in ncu's source view).  Two register sets of G units avoid that -- a set is refilled right after the FIRST
-  // unit of the other set, so whatever is in flight at a wait is G - 1 units old -- at the price of load bursts, which the
-  // shapes with many narrow loads per unit do not like (their LDS latency doubles).
+  // Loads run ahead in registers (the only latency hiding a 7..14-warp SM has).  ptxas tracks every global load of this
+  // kernel with ONE scoreboard, so the first use of a loaded register after the loop's back edge waits for ALL loads in
+  // flight, the youngest included: a slot-by-slot ring stalls for a full memory latency once per round (14-17 % of a warp's
+  // time in ncu's source view).  Hence two register sets of G units: set B is refilled while the first G - 2 units of set A
+  // are processed (spread over them: one burst of all G units doubles the latency of the shared-memory reads behind it), so
+  // whatever is in flight when B's wait comes is at least two units old; then the roles swap.
   const int my_units = live ? (units - part + split - 1) / split : 0;  // units part, part + split, ...
   constexpr int G = R / 2;
   PrivUnit<CW, VL> ring[kTwoSets ? 2 * G : R];
@@ -329,14 +329,14 @@ __global__ void __launch_bounds__(MAXT, 1) scatter_private_kernel(const float *_
         if (u0 + g < my_units) process(ring[g]);  // warp-uniform
 #pragma unroll
         for (int q = 0; q < G; ++q)
-          if ((GB_PRIV_TWOSET == 2 ? q * (G - 2) / G : 0) == g) load(ring[G + q], part + (u0 + G + q) * split);
+          if ((kSpread ? q * (G - 2) / G : 0) == g) load(ring[G + q], part + (u0 + G + q) * split);
       }
 #pragma unroll
       for (int g = 0; g < G; ++g) {
         if (u0 + G + g < my_units) process(ring[G + g]);
 #pragma unroll
         for (int q = 0; q < G; ++q)
-          if ((GB_PRIV_TWOSET == 2 ? q * (G - 2) / G : 0) == g) load(ring[q], part + (u0 + 2 * G + q) * split);
+          if ((kSpread ? q * (G - 2) / G : 0) == g) load(ring[q], part + (u0 + 2 * G + q) * split);
       }
     }
   } else {
@@ -383,6 +383,17 @@ __global__ void __launch_bounds__(MAXT, 1) scatter_private_kernel(const float *_
   }
 }
 
+// lanes that span a row piece: 32 for nsample >= 32; short rows (nsample 8 / 16) either share the warp between 32 / nsample
+// channel planes (S = nsample, one position per lane) or sit several to a unit like the long ones (S = 32, VL = 2, NRG rows)
+// B200, 32 scenes, nsample 16: four rows per unit 86 / 88 / 50 us (n = 512, C = 256 / n = 1024, m = 512 / n = 512, m = 256)
+// against 101 / 114 / 60 us with planes (26 warp instructions per 32 elements drop to ~18); n = 256: 49 against 45 us.
+static int priv_lanes(int nsample, long long npoints, int n) {
+  if (nsample >= 32) return 32;
+  const int knob = g_tuning.priv_rows;
+  const bool rows = knob == 2 || (knob == 0 && nsample == 16 && n >= 512);
+  return rows && (npoints * nsample) % 64 == 0 ? 32 : nsample;  // whole units of 64 positions
+}
+
 // channels per warp and plane: 4 (float4 accumulators) while at least eight warps' worth fits in shared memory, else 2
 static int priv_cw(int n, int H) {
   const int knob = g_tuning.priv_cw;
@@ -394,7 +405,7 @@ static int priv_cw(int n, int H) {
 // of accumulators per SM, enough (scene, channel group) tasks to fill the GPU
 bool scatter_private_supported(int b, int c, int n, int npoints, int nsample, size_t src_stride, const float *src, const int *idx) {
   if (g_tuning.scatter_mode & 8) return false;
-  const int S = nsample >= 32 ? 32 : nsample;
+  const int S = priv_lanes(nsample, npoints, n);
   if (nsample < 8 || (nsample & (nsample - 1)) != 0) return false;  // rows are pieces of a warp step: a power of two
   const int H = 32 / S, CW = priv_cw(n, H);
   if ((size_t)6 * H * n * 4 * CW > kPrivSmemBudget) return false;
@@ -423,7 +434,7 @@ static int launch_private(const float *src, size_t src_stride, const int *idx, f
 template <int CW>
 static int scatter_private_cw(const float *src, size_t src_stride, const int *idx, float *grad, int b, int c, int n, int npoints,
                               int nsample, int overwrite, cudaStream_t s) {
-  const int S = nsample >= 32 ? 32 : nsample, H = 32 / S;
+  const int S = priv_lanes(nsample, npoints, n), H = 32 / S;
   const int per = npoints * nsample;
   const int groups = (c + CW * H - 1) / (CW * H);
   const int tasks = b * groups;
@@ -444,9 +455,9 @@ static int scatter_private_cw(const float *src, size_t src_stride, const int *id
   // positions per lane and load; a unit of 32 * VL positions holds NRG = 32 * VL / nsample whole rows (or a piece of one)
   int VL = 1;
   if (S == 32) {
-    VL = nsample >= 64 ? 4 : 2;  // a unit of two rows either way (B200 sweep: profiles/r02_bwd_private_sweep.json)
+    VL = nsample >= 64 ? 4 : 2;  // a unit of two rows for nsample 32 / 64 (B200 sweep: profiles/r02_bwd_private_sweep.json)
     const int knob = g_tuning.priv_vl;
-    if ((knob == 1 || knob == 2 || knob == 4) && (nsample % (32 * knob) == 0 || (32 * knob) % nsample == 0)) VL = knob;
+    if ((knob == 1 || knob == 2 || knob == 4) && (nsample % (32 * knob) == 0 || (32 * knob) % nsample == 0) && (nsample >= 32 || knob > 1)) VL = knob;
     while (VL > 1 && per % (32 * VL) != 0) VL >>= 1;  // units are whole: an odd number of short rows takes narrower loads
   }
   const int NRG = S == 32 && nsample < 32 * VL ? 32 * VL / nsample : 1;
@@ -455,9 +466,12 @@ static int scatter_private_cw(const float *src, size_t src_stride, const int *id
 #define GB_PRIV(SV, VV, NV, R8, R16_)                                                                                                \
   return W <= 8 ? launch_private<CW, SV, VV, NV, R8, 256>(src, src_stride, idx, grad, c, n, per, groups, tasks, W, split, overwrite, nsample, s)    \
                 : launch_private<CW, SV, VV, NV, (CW == 2 ? (R16_ * GB_PRIV_RING_NUM) / 2 : R16_), 512>(src, src_stride, idx, grad, c, n, per, groups, tasks, W, split, overwrite, nsample, s)
+  if (S == 32 && VL == 4 && NRG == 8) GB_PRIV(32, 4, 8, 8, 4);
   if (S == 32 && VL == 4 && NRG == 4) GB_PRIV(32, 4, 4, 8, 4);
   if (S == 32 && VL == 4 && NRG == 2) GB_PRIV(32, 4, 2, 8, 4);
   if (S == 32 && VL == 4) GB_PRIV(32, 4, 1, 8, 4);
+  if (S == 32 && VL == 2 && NRG == 8) GB_PRIV(32, 2, 8, 12, 8);
+  if (S == 32 && VL == 2 && NRG == 4) GB_PRIV(32, 2, 4, 12, 8);
   if (S == 32 && VL == 2 && NRG == 2) GB_PRIV(32, 2, 2, 12, 8);
   if (S == 32 && VL == 2) GB_PRIV(32, 2, 1, 12, 8);
   if (S == 32) GB_PRIV(32, 1, 1, 16, 10);
@@ -468,7 +482,7 @@ static int scatter_private_cw(const float *src, size_t src_stride, const int *id
 
 int scatter_private(const float *src, size_t src_stride, const int *idx, float *grad, int b, int c, int n, int npoints, int nsample,
                     int overwrite, cudaStream_t s) {
-  const int H = 32 / (nsample >= 32 ? 32 : nsample);
+  const int H = 32 / priv_lanes(nsample, npoints, n);
   if (priv_cw(n, H) == 2) return scatter_private_cw<2>(src, src_stride, idx, grad, b, c, n, npoints, nsample, overwrite, s);
   return scatter_private_cw<4>(src, src_stride, idx, grad, b, c, n, npoints, nsample, overwrite, s);
 }

@@ -134,3 +134,26 @@ def test_group_bwd_few_channels_single_launch(dev, B, C, n, m, ns):
     acc = torch.full((B, C, n), -0.5, device=dev)
     gb_b.group_points_grad_wrapper(B, C, n, m, ns, gout, idx, acc)
     _close(acc.cpu() + 0.5, want.float())
+
+
+@pytest.mark.parametrize("rows_mode", [1, 2])
+@pytest.mark.parametrize("B,C,n,m,ns,kind", [(2, 8, 512, 64, 16, "sorted"), (2, 6, 1024, 128, 16, "padded"), (3, 5, 700, 32, 16, "random"),
+                                             (2, 12, 600, 64, 8, "padded"), (2, 4, 512, 48, 16, "oob"), (2, 9, 256, 64, 16, "knn")])
+def test_group_bwd_private_short_rows_both_layouts(dev, force_private, rows_mode, B, C, n, m, ns, kind):
+    """nsample 8 / 16: channel planes sharing a row (priv_rows = 1) and several rows per unit (priv_rows = 2) give the same sums."""
+    g = torch.Generator(device="cpu").manual_seed(5)
+    idx = _make_idx(kind, B, n, m, ns, g).to(dev)
+    gout = torch.randn((B, C, m, ns), generator=g).to(dev)
+    safe = idx.long().reshape(B, 1, m * ns)
+    safe = torch.where((safe < 0) | (safe >= n), torch.full_like(safe, n), safe)
+    want = torch.zeros((B, C, n + 1), dtype=torch.float64, device=dev)
+    want.scatter_add_(2, safe.expand(-1, C, -1), gout.double().reshape(B, C, m * ns))
+    _lib.set_tuning("priv_rows", rows_mode)
+    try:
+        l0 = _lib.launch_count()
+        got = gb_a.group_points_grad(gout, idx, n)
+        assert _lib.launch_count() - l0 == 1
+        _close(got, want[:, :, :n])
+        assert torch.equal(got, gb_a.group_points_grad(gout, idx, n))
+    finally:
+        _lib.set_tuning("priv_rows", 0)
