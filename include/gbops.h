@@ -236,7 +236,8 @@ GB_API int gb_voxel_means(const double *points, const long long *order, const lo
  *   "fps_cluster"  0 = auto, else 1/2/4/8/16 CTAs per scene
  *   "fps_threads"  0 = auto, else 256/512/1024
  *   "group_split"  0 = auto, else output splits per (scene, channel chunk)
- *   "group_mode"   bit 0: plain (not streaming) stores in group fwd; bit 1: generic fwd kernel; bit 2: atomic backward
+ *   "group_mode"   bit 0: plain (not streaming) stores in group fwd; bit 1: generic fwd kernel; bit 2: atomic backward;
+ *                  bit 3: never the one-launch row kernel of the few-channel backward
  *   "interp_mode"  bit 0: plain stores; bit 1: generic fwd kernel; bit 2: atomic backward
  *   "query_qpw"    0 = auto, else 1/2/4 queries per warp in the full-scan query kernel
  *   "query_mode"   0 = auto, 1 = full scan only, 2 = always build the cell grid
@@ -245,6 +246,7 @@ GB_API int gb_voxel_means(const double *points, const long long *order, const lo
  *                  bit 4: the warp-private backward for any number of tasks
  *   "priv_vl" / "priv_cw" / "priv_split"  warp-private backward: positions per lane and load (1/2/4), channels per warp
  *                  (2/4), warps sharing a task (1/2/4); 0 = auto
+ *   "priv_rows"    warp-private backward, nsample 8 / 16: 1 = channel planes share a row, 2 = several rows per unit; 0 = auto
  */
 GB_API int gb_set_tuning(const char *key, int value);
 GB_API int gb_get_tuning(const char *key, int *value);
