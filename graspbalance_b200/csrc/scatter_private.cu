@@ -17,10 +17,13 @@
 //     that are not ascending (padding, kNN order, arbitrary caller indices) go through a match.any pass that sums
 //     duplicates in registers first, so any index tensor gives the exact sum.
 // The summation order is fixed (storage order per target), so the result is bit-reproducible run to run.
-// nsample 16 / 8: a row fills half / a quarter of the warp; the warp then owns 8 / 16 channels as 2 / 4 planes of float4.
+// Short rows: nsample 16 with n >= 512 packs four rows into a unit of 64 positions (8 lanes per row), updated one row after the
+// other; nsample 8 (and 16 with few targets) lets a row fill a quarter / half of the warp, which then owns 16 / 8 channels as
+// 4 / 2 planes of float4.
 //
-// Loads run R row pieces ahead in a register ring (the only latency hiding a 7-warp SM has).  HBM traffic is the
-// algorithmic minimum: gout once, grad once; idx is re-read from L2 once per channel group.
+// Loads run R units ahead in registers (the only latency hiding a 7..14-warp SM has), as two alternating register sets --
+// ptxas tracks all of this kernel's global loads with one scoreboard, see the main loop.  HBM traffic is the algorithmic
+// minimum: gout once, grad once; idx is re-read from L2 once per channel group.
 #include "common.cuh"
 
 namespace gb {
