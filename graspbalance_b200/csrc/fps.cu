@@ -377,8 +377,9 @@ static int fps_impl(const float *xyz, float *temp, int *idx, float *new_xyz, int
     // as many CTAs per scene as the chip holds at ONE CTA per SM (co-resident CTAs would share the issue slots of the
     // register sweep), but not fewer than ~1024 points per CTA (below that the DSMEM hop costs more than the shorter
     // sweep saves).  Measured on B200, 32 scenes of 20000 points: C=4 x 256 threads 0.75 us/round, C=8 x 1024 3.3 us.
+    // (four CTAs of 128 threads pay from 512 points each: 2048 -> 1024 on 4-8 scenes 408 us against 434 us with two of 256)
     C = 8;
-    while (C > 1 && ((long)b * C > (long)sms || n / C < 1024)) C >>= 1;
+    while (C > 1 && ((long)b * C > (long)sms || n / C < (C == 4 ? 512 : 1024))) C >>= 1;
     // background sampling (the caller has the whole step to hide the rounds' latency): fewer, fuller CTAs -- each takes a
     // whole SM's registers, so the SMs they do not use are entirely free for the kernels they run beside
     if (max_cluster > 0 && C > max_cluster) C = max_cluster;
@@ -387,11 +388,15 @@ static int fps_impl(const float *xyz, float *temp, int *idx, float *new_xyz, int
   }
   for (; C >= 1; C >>= 1) {
     int T = g_tuning.fps_threads;
-    if (T != 256 && T != 512 && T != 1024) {
+    if (T == 128 && (C * 4 > 32 || (n + C - 1) / C > 128 * 40)) T = 0;  // 128 threads: direct mode only, <= 40 points per thread
+    if (T != 128 && T != 256 && T != 512 && T != 1024) {
       // the fewest warps that hold the CTA's points in registers: the per-round barrier and the redundant per-warp
       // reduction grow with the warp count, the sweep itself is issue-bound whatever the split
       const int per_cta = (n + C - 1) / C;
       T = per_cta <= 256 * 40 ? 256 : (per_cta <= 512 * 20 ? 512 : 1024);
+      // 128 threads where that keeps every warp's winner on its own lane of the exchange (C * W <= 32: no CTA-level stage):
+      // eight CTAs per scene (small shards: 20000 -> 2048 on 4 scenes 1089 us against 1212 us), or four CTAs of few points
+      if (g_tuning.fps_direct != 1 && ((C == 8 && per_cta <= 128 * 40) || (C == 4 && per_cta <= 1024))) T = 128;
     }
     int Ce = C;
     while (Ce * T < bs && T < 1024) T <<= 1;
@@ -407,6 +412,8 @@ static int fps_impl(const float *xyz, float *temp, int *idx, float *new_xyz, int
     GB_FPS_CASE(8, 512) GB_FPS_CASE(10, 512) GB_FPS_CASE(12, 512) GB_FPS_CASE(16, 512) GB_FPS_CASE(20, 512)
     GB_FPS_CASE(1, 256) GB_FPS_CASE(2, 256) GB_FPS_CASE(4, 256) GB_FPS_CASE(6, 256) GB_FPS_CASE(8, 256) GB_FPS_CASE(10, 256)
     GB_FPS_CASE(12, 256) GB_FPS_CASE(16, 256) GB_FPS_CASE(20, 256) GB_FPS_CASE(24, 256) GB_FPS_CASE(32, 256) GB_FPS_CASE(40, 256)
+    GB_FPS_CASE(4, 128) GB_FPS_CASE(8, 128) GB_FPS_CASE(10, 128) GB_FPS_CASE(12, 128) GB_FPS_CASE(16, 128) GB_FPS_CASE(20, 128)
+    GB_FPS_CASE(24, 128) GB_FPS_CASE(32, 128) GB_FPS_CASE(40, 128)
 #undef GB_FPS_CASE
     if (rc == kFpsRetrySmallerCluster) continue;     // this cluster size cannot be scheduled: halve it
     if (rc == kFpsRetrySmallerCluster - 1) break;    // scene does not fit in the registers of C CTAs

@@ -72,8 +72,8 @@ def test_fps_norm_skip_and_ties(dev):
 
 
 @pytest.mark.parametrize("cluster", [1, 2, 4, 8, 16])
-@pytest.mark.parametrize("threads", [256, 512, 1024])
-def test_fps_every_decomposition_gives_the_same_picks(dev, cluster, threads):
+@pytest.mark.parametrize("threads", [128, 256, 512, 1024])
+def test_fps_every_decomposition_gives_the_same_picks(dev, cluster, threads):  # (128 threads: honoured for 4 and 8 CTAs only)
     xyz = scenes.scene_batch([5, 6], 20000, "tabletop")
     want = oracle.furthest_point_sample(xyz, 300, "A")
     _lib.set_tuning("fps_cluster", cluster)
@@ -86,6 +86,18 @@ def test_fps_every_decomposition_gives_the_same_picks(dev, cluster, threads):
         _lib.set_tuning("fps_threads", 0)
     np.testing.assert_array_equal(got, want)
     np.testing.assert_array_equal(gotb, oracle.furthest_point_sample(xyz, 300, "B"))
+
+
+@pytest.mark.parametrize("B", [1, 4, 8])
+def test_fps_small_shards_take_the_128_thread_shapes_and_match_the_reference(dev, ref_a, B):
+    """Shards of a few scenes (BASELINE config 5 split over 4-8 GPUs) launch eight CTAs of 128 threads per scene, four for the
+    2048-point level: the whole sampling chain against the unmodified reference module A."""
+    cur = T(scenes.scene_batch(range(20, 20 + B), 20000, "tabletop"), dev)
+    for m in (2048, 1024, 512, 256):
+        want = ref_a.furthest_point_sampling(cur, m)
+        got, new_xyz = pu.furthest_point_sample_xyz(cur, m)
+        assert torch.equal(got, want)
+        cur = new_xyz
 
 
 def test_fps_full_size_vs_reference(dev, ref_a, ref_b):
