@@ -830,7 +830,7 @@ def main():
     fam = {}
     for name, evs in prof.items():
         tot_ms = sum(a.elapsed_time(b) for a, b, _, _ in evs)
-        base = name.replace("_set", "").replace("_strided", "").replace("_multi_radius", "").replace("_multi", "").replace("_batched", "")  # entry-point variants of one op share its kernels
+        base = name.replace("gb_group_xyz_feat", "gb_group_fwd").replace("_set", "").replace("_strided", "").replace("_multi_radius", "").replace("_multi", "").replace("_batched", "")  # entry-point variants of one op share its kernels
         f = fam.setdefault(base, {"launches": 0, "ms": 0.0, "bytes": 0, "big": None})
         f["launches"] += len(evs)
         f["ms"] += tot_ms

@@ -37,6 +37,7 @@ SIGNATURES = {
     "gb_group_fwd_strided": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _ll, _vp],
     "gb_group_bwd_strided": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _ll, _i, _vp],
     "gb_group_xyz": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _ll, _vp],
+    "gb_group_xyz_feat": [_vp, _vp, _vp, _vp, _ll, _f, _i, _vp, _vp, _ll, _i, _i, _i, _i, _i, _vp],
     "gb_three_nn": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp],
     "gb_three_nn_weights": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp],
     "gb_three_interp_fwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
@@ -126,6 +127,9 @@ ALGO_BYTES = {
     "gb_group_fwd_strided": lambda a: a[3] * (4 * a[4] * a[5] + 4 * a[6] * a[7] + 4 * a[4] * a[6] * a[7]),
     "gb_group_bwd_strided": lambda a: a[3] * (4 * a[4] * a[5] + 4 * a[6] * a[7] + 4 * a[4] * a[6] * a[7]),
     "gb_group_xyz": lambda a: a[5] * (12 * a[6] + 12 * a[7] + (36 * a[7] if a[3] else 0) + 16 * a[7] * a[8]),  # b*(12n+12m(+36m)+(4+12) m ns)
+    # b*(4cn + 4 m ns + 4c m ns) for the features + b*(12n + 12m + 12 m ns) for the coordinates (idx read once)
+    "gb_group_xyz_feat": lambda a: a[10] * (4 * a[11] * a[12] + 4 * a[13] * a[14] + 4 * a[11] * a[13] * a[14]
+                                            + 12 * a[12] + 12 * a[13] + 12 * a[13] * a[14]),
     "gb_knn": lambda a: a[3] * (4 * a[4] * (a[5] + a[6]) + 8 * a[7] * a[6]),              # b*(4d(R+Q) + 8kQ)
     "gb_group_max_fwd": lambda a: a[4] * (4 * a[5] * a[6] + 4 * a[7] * a[8] + (8 if a[3] else 4) * a[5] * a[7]),
     "gb_group_max_bwd": lambda a: a[3] * (8 * a[4] * a[6] + 4 * a[4] * a[5]),

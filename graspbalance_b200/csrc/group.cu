@@ -41,17 +41,87 @@ template <> __device__ __forceinline__ float vget<1>(const float &a, int) { retu
 template <> __device__ __forceinline__ float vget<2>(const float2 &a, int v) { return v == 0 ? a.x : a.y; }
 template <> __device__ __forceinline__ float vget<4>(const float4 &a, int v) { return v == 0 ? a.x : (v == 1 ? a.y : (v == 2 ? a.z : a.w)); }
 
+// ---- grouped coordinates of QueryAndGroup / CylinderQueryAndGroup in one pass ------------------------------------------
+// out[b, :, j, k] = ((xyz[b, idx[b,j,k]] - new_xyz[b,j]) * scale) . R[b,j]: what pointnet2_utils.py:178-190,281-291 build
+// from transpose + grouping_operation + subtract + divide + permute + matmul + permute (seven passes over [B,3,m,ns] and a
+// batched 3x3 sgemm).  Each op rounds as the torch op it replaces: fp32 subtract, multiply by the fp32 reciprocal of the
+// radius (ATen divides by a CPU scalar that way), dot product accumulated over k = 0, 1, 2 with fma.
+// VEC = 4: one thread per 4 consecutive samples of a query (nsample % 4 == 0), 128-bit idx load and stores.
+// Items t0, t0 + tstep, ... < total of the flattened (scene, query, sample group) space.
+template <bool ROT, int VEC>
+__device__ __forceinline__ void group_xyz_items(const float *__restrict__ xyz, const float *__restrict__ new_xyz,
+                                                const int *__restrict__ idx, const float *__restrict__ rot, float *__restrict__ out,
+                                                int n, int m, int ns, float scale, int use_scale, size_t out_stride, size_t total,
+                                                size_t t0, size_t tstep) {
+  const size_t per = (size_t)m * ns;
+  const int nsv = ns / VEC;
+  for (size_t t = t0; t < total; t += tstep) {
+    const size_t qrow = t / nsv;  // scene * m + j
+    const int kq = (int)(t - qrow * nsv);
+    const size_t scene = qrow / m;
+    const float qx = __ldg(new_xyz + qrow * 3), qy = __ldg(new_xyz + qrow * 3 + 1), qz = __ldg(new_xyz + qrow * 3 + 2);
+    float r[9];
+    if (ROT) {
+#pragma unroll
+      for (int e = 0; e < 9; ++e) r[e] = __ldg(rot + qrow * 9 + e);
+    }
+    int id[VEC];
+    if (VEC == 4) {
+      const int4 v = ld_nc_i4(idx + qrow * ns + (size_t)kq * 4);
+      id[0] = v.x, id[VEC > 1 ? 1 : 0] = v.y, id[VEC > 2 ? 2 : 0] = v.z, id[VEC > 3 ? 3 : 0] = v.w;
+    } else {
+      id[0] = __ldg(idx + qrow * ns + kq);
+    }
+    float o[3][VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      const float *p = xyz + (scene * n + (size_t)id[e]) * 3;
+      float dx = __fsub_rn(__ldg(p), qx), dy = __fsub_rn(__ldg(p + 1), qy), dz = __fsub_rn(__ldg(p + 2), qz);
+      if (use_scale) dx = __fmul_rn(dx, scale), dy = __fmul_rn(dy, scale), dz = __fmul_rn(dz, scale);
+      if (ROT) {
+        o[0][e] = __fmaf_rn(dz, r[6], __fmaf_rn(dy, r[3], __fmul_rn(dx, r[0])));
+        o[1][e] = __fmaf_rn(dz, r[7], __fmaf_rn(dy, r[4], __fmul_rn(dx, r[1])));
+        o[2][e] = __fmaf_rn(dz, r[8], __fmaf_rn(dy, r[5], __fmul_rn(dx, r[2])));
+      } else {
+        o[0][e] = dx, o[1][e] = dy, o[2][e] = dz;
+      }
+    }
+    float *dst = out + scene * out_stride + (qrow - scene * m) * ns + (size_t)kq * VEC;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      if (VEC == 4) st_cs_f4(dst + ch * per, make_float4(o[ch][0], o[ch][VEC > 1 ? 1 : 0], o[ch][VEC > 2 ? 2 : 0], o[ch][VEC > 3 ? 3 : 0]));
+      else dst[ch * per] = o[ch][0];
+    }
+  }
+}
+
+// The grouped coordinates of a grouper folded into its feature-grouping launch (gb_group_xyz_feat): every CTA of
+// group_fwd_kernel first takes its grid-stride share of the (scene, query, 4 samples) items -- ~3 / C of the launch's
+// output, gathered straight from the L2-resident xyz -- so a QueryAndGroup is ONE launch instead of a 10-17 us
+// latency-bound coordinate launch in front of the bandwidth-bound one.  total = 0: no fold.
+struct XyzFold {
+  const float *xyz, *new_xyz;
+  float *out;
+  int m, ns;
+  float scale;
+  int use_scale;
+  size_t out_stride, total;
+};
+
 // points [b,c,n]; idx [b,per]; out [b,c,per]; per % 4 == 0.  CH = channels staged per fill (multiple of V),
 // chunks = ceil(c / CH), per4 = per / 4, wpc = work (quads) per CTA.
 template <int V>
 __global__ void __launch_bounds__(kGroupThreads) group_fwd_kernel(const float *__restrict__ points, const int *__restrict__ idx,
                                                                  float *__restrict__ out, int c, int n, int per4, int CH, int chunks,
                                                                  long long total, long long wpc, int streaming, size_t out_stride,
-                                                                 int ranges) {
+                                                                 int ranges, const XyzFold fold) {
   extern __shared__ __align__(16) float s_rows[];  // [CH/V][n][V]
   using Vec = typename VecT<V>::type;
   Vec *srow = reinterpret_cast<Vec *>(s_rows);
   const int tid = threadIdx.x;
+  if (fold.total)
+    group_xyz_items<false, 4>(fold.xyz, fold.new_xyz, idx, nullptr, fold.out, n, fold.m, fold.ns, fold.scale, fold.use_scale,
+                              fold.out_stride, fold.total, (size_t)blockIdx.x * kGroupThreads + tid, (size_t)gridDim.x * kGroupThreads);
   long long w = (long long)blockIdx.x * wpc;
   long long wend = min(total, w + wpc);
   if (ranges > 0) {  // aligned partition: CTA = (pair, r), the r-th of `ranges` equal position ranges of ONE (scene, chunk) pair
@@ -301,57 +371,14 @@ __global__ void group_bwd_generic_kernel(const float *__restrict__ grad_out, con
   }
 }
 
-// ---- grouped coordinates of QueryAndGroup / CylinderQueryAndGroup in one pass ------------------------------------------
-// out[b, :, j, k] = ((xyz[b, idx[b,j,k]] - new_xyz[b,j]) * scale) . R[b,j]: what pointnet2_utils.py:178-190,281-291 build
-// from transpose + grouping_operation + subtract + divide + permute + matmul + permute (seven passes over [B,3,m,ns] and a
-// batched 3x3 sgemm).  Each op rounds as the torch op it replaces: fp32 subtract, multiply by the fp32 reciprocal of the
-// radius (ATen divides by a CPU scalar that way), dot product accumulated over k = 0, 1, 2 with fma.
-// VEC = 4: one thread per 4 consecutive samples of a query (nsample % 4 == 0), 128-bit idx load and stores.
+// ---- grouped coordinates as a launch of their own (no features, rotated crops, unaligned shapes): group_xyz_items above ----
 template <bool ROT, int VEC>
 __global__ void __launch_bounds__(256) group_xyz_kernel(const float *__restrict__ xyz, const float *__restrict__ new_xyz,
                                                         const int *__restrict__ idx, const float *__restrict__ rot,
                                                         float *__restrict__ out, int n, int m, int ns, float scale, int use_scale,
                                                         size_t out_stride, size_t total) {
-  const size_t per = (size_t)m * ns;
-  const int nsv = ns / VEC;
-  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
-    const size_t qrow = t / nsv;  // scene * m + j
-    const int kq = (int)(t - qrow * nsv);
-    const size_t scene = qrow / m;
-    const float qx = __ldg(new_xyz + qrow * 3), qy = __ldg(new_xyz + qrow * 3 + 1), qz = __ldg(new_xyz + qrow * 3 + 2);
-    float r[9];
-    if (ROT) {
-#pragma unroll
-      for (int e = 0; e < 9; ++e) r[e] = __ldg(rot + qrow * 9 + e);
-    }
-    int id[VEC];
-    if (VEC == 4) {
-      const int4 v = ld_nc_i4(idx + qrow * ns + (size_t)kq * 4);
-      id[0] = v.x, id[VEC > 1 ? 1 : 0] = v.y, id[VEC > 2 ? 2 : 0] = v.z, id[VEC > 3 ? 3 : 0] = v.w;
-    } else {
-      id[0] = __ldg(idx + qrow * ns + kq);
-    }
-    float o[3][VEC];
-#pragma unroll
-    for (int e = 0; e < VEC; ++e) {
-      const float *p = xyz + (scene * n + (size_t)id[e]) * 3;
-      float dx = __fsub_rn(__ldg(p), qx), dy = __fsub_rn(__ldg(p + 1), qy), dz = __fsub_rn(__ldg(p + 2), qz);
-      if (use_scale) dx = __fmul_rn(dx, scale), dy = __fmul_rn(dy, scale), dz = __fmul_rn(dz, scale);
-      if (ROT) {
-        o[0][e] = __fmaf_rn(dz, r[6], __fmaf_rn(dy, r[3], __fmul_rn(dx, r[0])));
-        o[1][e] = __fmaf_rn(dz, r[7], __fmaf_rn(dy, r[4], __fmul_rn(dx, r[1])));
-        o[2][e] = __fmaf_rn(dz, r[8], __fmaf_rn(dy, r[5], __fmul_rn(dx, r[2])));
-      } else {
-        o[0][e] = dx, o[1][e] = dy, o[2][e] = dz;
-      }
-    }
-    float *dst = out + scene * out_stride + (qrow - scene * m) * ns + (size_t)kq * VEC;
-#pragma unroll
-    for (int ch = 0; ch < 3; ++ch) {
-      if (VEC == 4) st_cs_f4(dst + ch * per, make_float4(o[ch][0], o[ch][VEC > 1 ? 1 : 0], o[ch][VEC > 2 ? 2 : 0], o[ch][VEC > 3 ? 3 : 0]));
-      else dst[ch * per] = o[ch][0];
-    }
-  }
+  group_xyz_items<ROT, VEC>(xyz, new_xyz, idx, rot, out, n, m, ns, scale, use_scale, out_stride, total,
+                            blockIdx.x * (size_t)blockDim.x + threadIdx.x, (size_t)gridDim.x * blockDim.x);
 }
 
 // ---- gather (C x m, tiny) ------------------------------------------------------------------------------------------
@@ -380,7 +407,7 @@ static inline unsigned grid_for(size_t total, int threads) {
 
 template <int V>
 static int launch_group_fwd(const float *points, const int *idx, float *out, int b, int c, int n, size_t per, int CH, size_t out_stride,
-                            cudaStream_t s) {
+                            cudaStream_t s, const XyzFold &fold) {
   auto kern = group_fwd_kernel<V>;
   const size_t smem = (size_t)CH * n * sizeof(float);
   if (int rc_ = raise_smem_limit(kern, smem)) return rc_;
@@ -416,7 +443,7 @@ static int launch_group_fwd(const float *points, const int *idx, float *out, int
     }
   }
   kern<<<(unsigned)ctas, kGroupThreads, smem, s>>>(points, idx, out, c, n, per4, CH, chunks, total, wpc, (g_tuning.group_mode & 1) ? 0 : 1,
-                                                   out_stride, ranges);
+                                                   out_stride, ranges, fold);
   count_launch();
   return finish_launch();
 }
@@ -425,8 +452,33 @@ static int launch_group_fwd(const float *points, const int *idx, float *out, int
 
 using namespace gb;
 
+static int group_xyz_impl(const float *xyz, const float *new_xyz, const int *idx, const float *rot, float *out, int b, int n, int m,
+                            int nsample, float scale, int use_scale, long long out_scene_stride, gb_stream_t stream) {
+  if (b < 0 || n <= 0 || m < 0 || nsample < 0) return (int)cudaErrorInvalidValue;
+  const size_t per = (size_t)m * nsample;
+  if (b == 0 || per == 0) return 0;
+  if (!xyz || !new_xyz || !idx || !out) return (int)cudaErrorInvalidValue;
+  if (out_scene_stride < (long long)(3 * per)) return (int)cudaErrorInvalidValue;
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool vec = (nsample % 4 == 0) && (out_scene_stride % 4 == 0) && ((((uintptr_t)idx | (uintptr_t)out) & 15u) == 0);
+  const size_t total = vec ? (size_t)b * m * (nsample / 4) : (size_t)b * per;
+  const unsigned grid = grid_for(total, 256);
+  const size_t os = (size_t)out_scene_stride;
+  if (vec) {
+    if (rot) group_xyz_kernel<true, 4><<<grid, 256, 0, s>>>(xyz, new_xyz, idx, rot, out, n, m, nsample, scale, use_scale, os, total);
+    else group_xyz_kernel<false, 4><<<grid, 256, 0, s>>>(xyz, new_xyz, idx, rot, out, n, m, nsample, scale, use_scale, os, total);
+  } else {
+    if (rot) group_xyz_kernel<true, 1><<<grid, 256, 0, s>>>(xyz, new_xyz, idx, rot, out, n, m, nsample, scale, use_scale, os, total);
+    else group_xyz_kernel<false, 1><<<grid, 256, 0, s>>>(xyz, new_xyz, idx, rot, out, n, m, nsample, scale, use_scale, os, total);
+  }
+  count_launch();
+  return finish_launch();
+}
+
+// fold: grouped coordinates to be produced by the same launch (staged path), or by a launch of their own in front of the
+// other paths; nullptr = features only
 static int group_fwd_impl(const float *points, const int *idx, float *out, int b, int c, int n, int npoints, int nsample,
-                          long long out_scene_stride, gb_stream_t stream) {
+                          long long out_scene_stride, gb_stream_t stream, const XyzFold *fold = nullptr) {
   if (b < 0 || c < 0 || n <= 0 || npoints < 0 || nsample < 0) return (int)cudaErrorInvalidValue;
   const size_t per = (size_t)npoints * nsample;
   if (b == 0 || c == 0 || per == 0) return 0;  // nothing to do (empty tensors have null data pointers)
@@ -437,6 +489,18 @@ static int group_fwd_impl(const float *points, const int *idx, float *out, int b
   const bool aligned = (per % 4 == 0) && (ostride % 4 == 0) && (((uintptr_t)idx | (uintptr_t)out) & 15u) == 0 && per / 4 < (1u << 30);
   const size_t row_bytes = (size_t)n * sizeof(float);
   const size_t big = 200u * 1024u;
+  XyzFold nofold;
+  nofold.total = 0;
+  const bool staged = aligned && row_bytes <= big && !(g_tuning.group_mode & 2) &&
+                      !(4 * row_bytes > big && 2 * row_bytes <= big && n % 4 == 0 && (((uintptr_t)points & 15u) == 0) && !(g_tuning.group_mode & (2 | 8)));
+  const bool foldable = fold && staged && !(g_tuning.group_mode & 32) && fold->ns % 4 == 0 && fold->out_stride % 4 == 0 &&
+                        (((uintptr_t)fold->out) & 15u) == 0;
+  if (fold && !foldable) {  // coordinates as a launch of their own
+    if (int rc_ = group_xyz_impl(fold->xyz, fold->new_xyz, idx, nullptr, fold->out, b, n, fold->m, fold->ns, fold->scale, fold->use_scale,
+                                 (long long)fold->out_stride, stream))
+      return rc_;
+  }
+  const XyzFold &kf = foldable ? *fold : nofold;
   // rows too long to stage four channels at a time: TMA double-buffered single rows
   if (aligned && 4 * row_bytes > big && 2 * row_bytes <= big && n % 4 == 0 && (((uintptr_t)points & 15u) == 0) &&
       !(g_tuning.group_mode & (2 | 8))) {
@@ -470,9 +534,9 @@ static int group_fwd_impl(const float *points, const int *idx, float *out, int b
     // (B200, 32 scenes, C = 256: n = 512: 72 -> 59 us, n = 1024: 218 -> 202 us with 512 KB ranges; tests/ubench/fwd_shapes.py)
     if (row_bytes <= 4096 && CH > 16 && V == 4) CH = 16;
     if (g_tuning.group_ch > 0 && g_tuning.group_ch % V == 0 && (size_t)g_tuning.group_ch * row_bytes <= big) CH = g_tuning.group_ch;
-    if (V == 4) return launch_group_fwd<4>(points, idx, out, b, c, n, per, CH, ostride, s);
-    if (V == 2) return launch_group_fwd<2>(points, idx, out, b, c, n, per, CH, ostride, s);
-    return launch_group_fwd<1>(points, idx, out, b, c, n, per, CH, ostride, s);
+    if (V == 4) return launch_group_fwd<4>(points, idx, out, b, c, n, per, CH, ostride, s, kf);
+    if (V == 2) return launch_group_fwd<2>(points, idx, out, b, c, n, per, CH, ostride, s, kf);
+    return launch_group_fwd<1>(points, idx, out, b, c, n, per, CH, ostride, s, kf);
   }
   const size_t total = (size_t)b * c * per;
   group_fwd_generic_kernel<<<grid_for(total, 256), 256, 0, s>>>(points, idx, out, c, n, per, total, ostride);
@@ -574,23 +638,22 @@ extern "C" int gb_gather_bwd(const float *grad_out, const int *idx, float *grad_
 
 extern "C" int gb_group_xyz(const float *xyz, const float *new_xyz, const int *idx, const float *rot, float *out, int b, int n, int m,
                             int nsample, float scale, int use_scale, long long out_scene_stride, gb_stream_t stream) {
-  if (b < 0 || n <= 0 || m < 0 || nsample < 0) return (int)cudaErrorInvalidValue;
-  const size_t per = (size_t)m * nsample;
+  return group_xyz_impl(xyz, new_xyz, idx, rot, out, b, n, m, nsample, scale, use_scale, out_scene_stride, stream);
+}
+
+extern "C" int gb_group_xyz_feat(const float *xyz, const float *new_xyz, const int *idx, float *out_xyz, long long xyz_scene_stride,
+                                 float scale, int use_scale, const float *points, float *out_feat, long long feat_scene_stride, int b,
+                                 int c, int n, int npoints, int nsample, gb_stream_t stream) {
+  if (b < 0 || c < 0 || n <= 0 || npoints < 0 || nsample < 0) return (int)cudaErrorInvalidValue;
+  const size_t per = (size_t)npoints * nsample;
   if (b == 0 || per == 0) return 0;
-  if (!xyz || !new_xyz || !idx || !out) return (int)cudaErrorInvalidValue;
-  if (out_scene_stride < (long long)(3 * per)) return (int)cudaErrorInvalidValue;
-  cudaStream_t s = (cudaStream_t)stream;
-  const bool vec = (nsample % 4 == 0) && (out_scene_stride % 4 == 0) && ((((uintptr_t)idx | (uintptr_t)out) & 15u) == 0);
-  const size_t total = vec ? (size_t)b * m * (nsample / 4) : (size_t)b * per;
-  const unsigned grid = grid_for(total, 256);
-  const size_t os = (size_t)out_scene_stride;
-  if (vec) {
-    if (rot) group_xyz_kernel<true, 4><<<grid, 256, 0, s>>>(xyz, new_xyz, idx, rot, out, n, m, nsample, scale, use_scale, os, total);
-    else group_xyz_kernel<false, 4><<<grid, 256, 0, s>>>(xyz, new_xyz, idx, rot, out, n, m, nsample, scale, use_scale, os, total);
-  } else {
-    if (rot) group_xyz_kernel<true, 1><<<grid, 256, 0, s>>>(xyz, new_xyz, idx, rot, out, n, m, nsample, scale, use_scale, os, total);
-    else group_xyz_kernel<false, 1><<<grid, 256, 0, s>>>(xyz, new_xyz, idx, rot, out, n, m, nsample, scale, use_scale, os, total);
-  }
-  count_launch();
-  return finish_launch();
+  if (!xyz || !new_xyz || !idx || !out_xyz) return (int)cudaErrorInvalidValue;
+  if (xyz_scene_stride < (long long)(3 * per)) return (int)cudaErrorInvalidValue;
+  if (c == 0) return group_xyz_impl(xyz, new_xyz, idx, nullptr, out_xyz, b, n, npoints, nsample, scale, use_scale, xyz_scene_stride, stream);
+  XyzFold fold;
+  fold.xyz = xyz, fold.new_xyz = new_xyz, fold.out = out_xyz;
+  fold.m = npoints, fold.ns = nsample, fold.scale = scale, fold.use_scale = use_scale;
+  fold.out_stride = (size_t)xyz_scene_stride;
+  fold.total = (size_t)b * npoints * (size_t)(nsample / 4);
+  return group_fwd_impl(points, idx, out_feat, b, c, n, npoints, nsample, feat_scene_stride, stream, &fold);
 }

@@ -429,10 +429,34 @@ __global__ void __launch_bounds__(kSegSortThreads) seg_sort_dense_kernel(const i
   }
   for (int i = n + tid; i < seg_dense_ns(n); i += kSegSortThreads) start[i] = (unsigned short)total;
   __syncthreads();
+  // Scatter into shared memory first (the cursor order is whatever the atomics made it), then every entry finds its RANK
+  // among its target's entries by counting the smaller entry numbers of the slice: each slice leaves in ascending entry
+  // order, so the sums of seg_dense_kernel are bit-reproducible run to run.  The scan costs the slice length per entry
+  // (~6 for the interpolation backward, ~30 for a heavy ball-query target); slices beyond kStableMax entries of one tile
+  // (degenerate inputs: every neighbourhood empty) keep the cursor order.
+  constexpr int kStableMax = 256;
+  unsigned short *s_tp = reinterpret_cast<unsigned short *>(wsum + 32);
+  int pos[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) {
+    pos[r] = -1;
+    if (key[r] >= 0) {
+      pos[r] = atomicAdd(&s_bins[key[r]], 1);
+      s_tp[pos[r]] = (unsigned short)(r * kSegSortThreads + tid);
+    }
+  }
+  __syncthreads();  // s_bins[k] is now the END of target k's slice, i.e. the start of target k + 1's
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    if (key[r] < 0) continue;
     const int e = r * kSegSortThreads + tid;
-    if (key[r] >= 0) tp[atomicAdd(&s_bins[key[r]], 1)] = (unsigned short)e;
+    const int lo = key[r] ? s_bins[key[r] - 1] : 0, hi = s_bins[key[r]];
+    int at = pos[r];
+    if (hi - lo <= kStableMax) {
+      at = lo;
+      for (int i = lo; i < hi; ++i) at += (int)s_tp[i] < e;
+    }
+    tp[at] = (unsigned short)e;
   }
   for (int e = total + tid; e < kStride; e += kSegSortThreads) tp[e] = 0;
 }
@@ -717,14 +741,25 @@ static int seg_scatter_dense(const float *src, size_t src_stride, const int *key
       return (int)e;
     }
   }
-  const size_t sort_smem = ((size_t)n + 32) * sizeof(int);
+  const size_t sort_smem = ((size_t)n + 64) * sizeof(int) + (size_t)seg_dense_stride(div, mul) * sizeof(unsigned short);
   const dim3 sgrid((unsigned)tiles, b);
-  if (div == 3) seg_sort_dense_kernel<3, 1><<<sgrid, kSegSortThreads, sort_smem, s>>>(key, (int)entries, n, blobs, deg, deg_stride);
-  else if (mul == 1) seg_sort_dense_kernel<1, 1><<<sgrid, kSegSortThreads, sort_smem, s>>>(key, (int)entries, n, blobs, deg, deg_stride);
-  else if (mul == 2) seg_sort_dense_kernel<1, 2><<<sgrid, kSegSortThreads, sort_smem, s>>>(key, (int)entries, n, blobs, deg, deg_stride);
-  else seg_sort_dense_kernel<1, 4><<<sgrid, kSegSortThreads, sort_smem, s>>>(key, (int)entries, n, blobs, deg, deg_stride);
+  int rc = 0;
+#define GB_SORT_DENSE(DIVV, MULV)                                                                                        \
+  do {                                                                                                                   \
+    rc = raise_smem_limit(seg_sort_dense_kernel<DIVV, MULV>, sort_smem);                                                 \
+    if (!rc) seg_sort_dense_kernel<DIVV, MULV><<<sgrid, kSegSortThreads, sort_smem, s>>>(key, (int)entries, n, blobs, deg, deg_stride); \
+  } while (0)
+  if (div == 3) GB_SORT_DENSE(3, 1);
+  else if (mul == 1) GB_SORT_DENSE(1, 1);
+  else if (mul == 2) GB_SORT_DENSE(1, 2);
+  else GB_SORT_DENSE(1, 4);
+#undef GB_SORT_DENSE
+  if (rc) {
+    cudaFreeAsync(blobs, s);
+    return rc;
+  }
   count_launch();
-  int rc = finish_launch();
+  rc = finish_launch();
   if (!rc && balance) {
     seg_perm_kernel<<<b, kSegThreads, 0, s>>>(deg, n, perm);
     count_launch();

@@ -138,6 +138,35 @@ class BallQuery(Function):
 ball_query = BallQuery.apply
 
 
+class _GroupXyzFeatures(Function):
+    """Tail of QueryAndGroup.forward (group.py:167-179) as one launch: grouped_xyz = (support_xyz[idx] - query_xyz) (* 1/radius)
+    as (B,3,npoint,nsample) and grouping_operation(features, idx) as (B,C,npoint,nsample).  Bit-identical to gb_group_xyz +
+    GroupingOperation; coordinates carry no gradient (the caller checked that none is required), features get
+    GroupingOperation's backward."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, support_xyz, query_xyz, idx, features, inv_radius, use_scale):
+        B, npoint, nsample = idx.shape
+        _, C, N = features.shape
+        per = npoint * nsample
+        grouped_xyz = torch.empty((B, 3, npoint, nsample), dtype=torch.float32, device=idx.device)
+        grouped = torch.empty((B, C, npoint, nsample), dtype=torch.float32, device=idx.device)
+        _lib.call("gb_group_xyz_feat", features, support_xyz.data_ptr(), query_xyz.data_ptr(), idx.data_ptr(), grouped_xyz.data_ptr(),
+                  3 * per, float(inv_radius), int(use_scale), features.data_ptr(), grouped.data_ptr(), C * per, B, C, N, npoint, nsample)
+        ctx.mark_non_differentiable(grouped_xyz)
+        ctx.for_backwards = (idx, N)
+        return grouped_xyz, grouped
+
+    @staticmethod
+    def backward(ctx, _grad_xyz, grad_out):
+        idx, N = ctx.for_backwards
+        B, C, npoint, nsample = grad_out.size()
+        grad_features = torch.empty([B, C, N], dtype=torch.float, device=grad_out.device)
+        pointnet2_cuda.group_points_grad_set(B, C, N, npoint, nsample, grad_out.detach().contiguous(), idx, grad_features)
+        return None, None, None, grad_features, None, None
+
+
 class QueryAndGroup(nn.Module):
     """group.py:147-180: returns (grouped_xyz, grouped_features); argument order is (query_xyz, support_xyz, features)."""
 
@@ -156,6 +185,11 @@ class QueryAndGroup(nn.Module):
             return idx
         fusable = all(t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and not t.requires_grad
                       for t in (query_xyz, support_xyz))
+        if self.relative_xyz and fusable and features is not None and features.is_cuda and features.is_contiguous() \
+                and features.dim() == 3 and features.is_floating_point() and features.shape[2] == support_xyz.shape[1]:
+            # coordinates and features of the neighbourhoods in ONE launch (gb_group_xyz_feat); same values as below
+            inv = float(np.float32(1.0) / np.float32(self.radius)) if self.normalize_dp else 0.0
+            return _GroupXyzFeatures.apply(support_xyz, query_xyz, idx, features, inv, 1 if self.normalize_dp else 0)
         if self.relative_xyz and fusable:
             # gather + centre (+ scale) in one launch instead of transpose, group, subtract, divide (group.py:171-176);
             # ATen evaluates `/= radius` as a multiply by the fp32 reciprocal

@@ -363,8 +363,9 @@ def _fusable(*tensors):
 
 
 class _FusedQueryGroup(Function):
-    """(B, 3[+C], npoint, nsample) result of QueryAndGroup / CylinderQueryAndGroup written in place by two launches:
-    gb_group_xyz (gather + centre + scale + rotate) into rows 0..2 and gb_group_fwd_strided into rows 3.. -- instead of
+    """(B, 3[+C], npoint, nsample) result of QueryAndGroup / CylinderQueryAndGroup written in place: gb_group_xyz (gather + centre
+    + scale + rotate) into rows 0..2 and gb_group_fwd_strided into rows 3.. (one launch, gb_group_xyz_feat, when there are
+    features and no rotation) -- instead of
     transpose, group, subtract, divide, permute, matmul, permute, group, cat (pointnet2_utils.py:178-207, 281-308).
     Backward reads the feature rows' gradient from the same slice (gb_group_bwd_strided); coordinates get no gradient
     (callers that need one take the unfused path)."""
@@ -377,11 +378,17 @@ class _FusedQueryGroup(Function):
         per = npoint * nsample
         out = torch.empty((B, 3 + C, npoint, nsample), dtype=torch.float32, device=xyz.device)
         stride = (3 + C) * per
-        _lib.call("gb_group_xyz", xyz, xyz.data_ptr(), new_xyz.data_ptr(), idx.data_ptr(), None if rot is None else rot.data_ptr(),
-                  out.data_ptr(), B, N, npoint, nsample, float(inv_radius or 0.0), 1 if inv_radius is not None else 0, stride)
-        if C:
-            _lib.call("gb_group_fwd_strided", features, features.data_ptr(), idx.data_ptr(), out.data_ptr() + 12 * per, B, C,
-                      features.shape[2], npoint, nsample, stride)
+        if C and rot is None and features.shape[2] == N:
+            # one launch: every CTA of the feature kernel first writes its share of the coordinate rows
+            _lib.call("gb_group_xyz_feat", xyz, xyz.data_ptr(), new_xyz.data_ptr(), idx.data_ptr(), out.data_ptr(), stride,
+                      float(inv_radius or 0.0), 1 if inv_radius is not None else 0, features.data_ptr(), out.data_ptr() + 12 * per,
+                      stride, B, C, N, npoint, nsample)
+        else:
+            _lib.call("gb_group_xyz", xyz, xyz.data_ptr(), new_xyz.data_ptr(), idx.data_ptr(), None if rot is None else rot.data_ptr(),
+                      out.data_ptr(), B, N, npoint, nsample, float(inv_radius or 0.0), 1 if inv_radius is not None else 0, stride)
+            if C:
+                _lib.call("gb_group_fwd_strided", features, features.data_ptr(), idx.data_ptr(), out.data_ptr() + 12 * per, B, C,
+                          features.shape[2], npoint, nsample, stride)
         ctx.for_backwards = (idx, None if features is None else features.shape[2], C)
         return out
 

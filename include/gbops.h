@@ -136,6 +136,16 @@ GB_API int gb_group_bwd_strided(const float *grad_out, const int *idx, float *gr
 GB_API int gb_group_xyz(const float *xyz, const float *new_xyz, const int *idx, const float *rot, float *out, int b, int n, int m,
                  int nsample, float scale, int use_scale, long long out_scene_stride, gb_stream_t stream);
 
+/* A whole QueryAndGroup tail in ONE launch: the grouped coordinates of gb_group_xyz (no rotation) and the grouped features of
+ * gb_group_fwd_strided over the same idx -- pointnet2_utils.py:178-207 (variant A: out_xyz = rows 0..2 and out_feat = rows 3..
+ * of the [b,3+c,npoints,nsample] result, both strides (3+c)*npoints*nsample) and group.py:167-179 (variant B: two tensors,
+ * strides 3*npoints*nsample and c*npoints*nsample).  xyz [b,n,3], new_xyz [b,npoints,3], points [b,c,n].  Every CTA of the
+ * feature kernel first writes its share of the coordinate rows; shapes the staged feature kernel does not take (unaligned,
+ * rows beyond shared memory) run as the two launches.  Results are bit-identical to the two entry points. */
+GB_API int gb_group_xyz_feat(const float *xyz, const float *new_xyz, const int *idx, float *out_xyz, long long xyz_scene_stride,
+                      float scale, int use_scale, const float *points, float *out_feat, long long feat_scene_stride, int b, int c,
+                      int n, int npoints, int nsample, gb_stream_t stream);
+
 /* grouping_operation + max over nsample in one pass: PointnetSAModuleVotes_WOMLP.forward (PointNet/
  * pointnet2_modules.py:324-335) and the 'max' pooling of PointnetSAModuleVotes (:173-175) when no MLP sits between the
  * grouping and the pooling -- group_points_kernel (group_points_gpu.cu:17-36) + F.max_pool2d without the [b,c,npoints,nsample]

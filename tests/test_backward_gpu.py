@@ -22,6 +22,18 @@ def force_private():
     _lib.set_tuning("scatter_mode", 0)
 
 
+import contextlib
+
+
+@contextlib.contextmanager
+def force_sorted():
+    _lib.set_tuning("scatter_mode", 8)  # never the private path: the sorted backward (seg_sort_dense + seg_dense) answers
+    try:
+        yield
+    finally:
+        _lib.set_tuning("scatter_mode", 0)
+
+
 def _close(got, want):
     scale = max(want.abs().max().item(), 1.0)
     err = (got.double() - want.double()).abs().max().item()
@@ -157,3 +169,36 @@ def test_group_bwd_private_short_rows_both_layouts(dev, force_private, rows_mode
         assert torch.equal(got, gb_a.group_points_grad(gout, idx, n))
     finally:
         _lib.set_tuning("priv_rows", 0)
+
+
+@pytest.mark.parametrize("B,C,n,m", [(4, 256, 20000, 1024), (2, 64, 1024, 512), (3, 16, 700, 40)])
+def test_interpolate_backward_is_bit_reproducible(dev, B, C, n, m):
+    """The sorted backward orders every target's entries by entry number (seg_sort_dense_kernel ranks them after the
+    cursor scatter), so the interpolation backward returns the same bits on every run -- the reference's float atomics
+    (interpolate_gpu.cu:127-149) do not."""
+    g = torch.Generator(device="cpu").manual_seed(7)
+    idx = torch.randint(0, m, (B, n, 3), generator=g, dtype=torch.int32).to(dev)
+    w = torch.rand((B, n, 3), generator=g).to(dev)
+    gout = torch.randn((B, C, n), generator=g).to(dev)
+    first = gb_a.three_interpolate_grad(gout, idx, w, m)
+    want = torch.zeros((B, C, m), dtype=torch.float64, device=dev)
+    want.scatter_add_(2, idx.long().reshape(B, 1, -1).expand(-1, C, -1),
+                      (gout.double().unsqueeze(-1) * w.double().unsqueeze(1)).reshape(B, C, -1))
+    _close(first, want)
+    for _ in range(4):
+        assert torch.equal(gb_a.three_interpolate_grad(gout, idx, w, m), first)
+
+
+def test_sorted_group_backward_is_bit_reproducible(dev):
+    """Small batches take the sorted path (too few tasks for one warp each): same bits run to run there too."""
+    g = torch.Generator(device="cpu").manual_seed(8)
+    for (B, C, n, m, ns) in ((1, 16, 512, 64, 32), (2, 32, 2048, 2048, 64)):
+        idx = torch.randint(0, max(n // 8, 1), (B, m, ns), generator=g, dtype=torch.int32).to(dev)  # heavy targets
+        gout = torch.randn((B, C, m, ns), generator=g).to(dev)
+        with force_sorted():
+            first = gb_a.group_points_grad(gout, idx, n)
+            for _ in range(4):
+                assert torch.equal(gb_a.group_points_grad(gout, idx, n), first)
+        want = torch.zeros((B, C, n), dtype=torch.float64, device=dev)
+        want.scatter_add_(2, idx.long().reshape(B, 1, -1).expand(-1, C, -1), gout.double().reshape(B, C, -1))
+        _close(first, want)

@@ -162,6 +162,51 @@ def test_strided_group_entries_match_the_contiguous_ones(dev):
         assert (got - want_g).abs().max().item() <= 1e-5 * max(want_g.abs().max().item(), 1e-30)
 
 
+@pytest.mark.parametrize("B,C,N,m,ns,scale", [
+    (32, 128, 2048, 2048, 64, None),   # InvResMLP level 0 of the bench step: aligned partition, many waves
+    (4, 256, 1024, 1024, 32, 5.0),     # 16-channel fills
+    (2, 5, 2048, 96, 32, 10.0),        # flattened equal split, ragged channel chunk
+    (3, 2, 700, 40, 8, None),          # V = 2 kernel
+    (1, 1, 300, 8, 4, 2.0),            # V = 1 kernel
+    (2, 16, 20000, 128, 64, 25.0),     # rows beyond shared memory four at a time: coordinates as a launch of their own
+    (2, 7, 500, 17, 6, 4.0),           # nsample % 4 != 0: generic kernels
+])
+def test_group_xyz_feat_is_the_two_launches_in_one(dev, B, C, N, m, ns, scale):
+    """gb_group_xyz_feat against gb_group_xyz + gb_group_fwd_strided, bit for bit, in the layouts of both grouper variants:
+    variant A writes rows 0..2 and 3.. of one [B,3+C,m,ns] tensor, variant B two tensors (group.py:167-179)."""
+    from graspbalance_b200 import _lib
+    rng = np.random.default_rng(B * 1000 + C)
+    xyz = T(rng.uniform(-1, 1, (B, N, 3)).astype(np.float32), dev)
+    new_xyz = T(rng.uniform(-1, 1, (B, m, 3)).astype(np.float32), dev)
+    feats = T(rng.normal(size=(B, C, N)).astype(np.float32), dev)
+    idx = T(rng.integers(0, N, (B, m, ns)).astype(np.int32), dev)
+    per = m * ns
+    sc, use = (float(scale), 1) if scale is not None else (0.0, 0)
+    # variant A layout
+    want = torch.full((B, 3 + C, m, ns), -7.0, device=dev)
+    _lib.call("gb_group_xyz", xyz, xyz.data_ptr(), new_xyz.data_ptr(), idx.data_ptr(), None, want.data_ptr(), B, N, m, ns, sc, use, (3 + C) * per)
+    _lib.call("gb_group_fwd_strided", feats, feats.data_ptr(), idx.data_ptr(), want.data_ptr() + 12 * per, B, C, N, m, ns, (3 + C) * per)
+    got = torch.full((B, 3 + C, m, ns), -9.0, device=dev)
+    n0 = _lib.launch_count()
+    _lib.call("gb_group_xyz_feat", xyz, xyz.data_ptr(), new_xyz.data_ptr(), idx.data_ptr(), got.data_ptr(), (3 + C) * per, sc, use,
+              feats.data_ptr(), got.data_ptr() + 12 * per, (3 + C) * per, B, C, N, m, ns)
+    launches = _lib.launch_count() - n0
+    assert torch.equal(got, want)
+    staged = ns % 4 == 0 and N * 16 <= 200 * 1024
+    assert launches == (1 if staged else 2)
+    # variant B layout
+    gx, gf = torch.full((B, 3, m, ns), -9.0, device=dev), torch.full((B, C, m, ns), -9.0, device=dev)
+    _lib.call("gb_group_xyz_feat", xyz, xyz.data_ptr(), new_xyz.data_ptr(), idx.data_ptr(), gx.data_ptr(), 3 * per, sc, use,
+              feats.data_ptr(), gf.data_ptr(), C * per, B, C, N, m, ns)
+    assert torch.equal(gx, want[:, :3]) and torch.equal(gf, want[:, 3:])
+    # no features: coordinates only; empty batch: nothing
+    gx.fill_(-9.0)
+    _lib.call("gb_group_xyz_feat", xyz, xyz.data_ptr(), new_xyz.data_ptr(), idx.data_ptr(), gx.data_ptr(), 3 * per, sc, use,
+              None, None, 0, B, 0, N, m, ns)
+    assert torch.equal(gx, want[:, :3])
+    _lib.call("gb_group_xyz_feat", xyz, None, None, None, None, 0, sc, use, None, None, 0, 0, C, N, m, ns)
+
+
 # ---- multi-depth grasp crop (SURVEY.md 8f-1; TrainModel/modules.py:87-124) -------------------------------------------------
 def _crop_inputs(dev, B, N, m, seed, kind="tabletop"):
     xyz, new_xyz, _ = _inputs(dev, B, N, m, 0, seed, kind)
