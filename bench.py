@@ -688,8 +688,13 @@ def main():
     # holds that lock at the same moment the step stalls for 40-120 ms (measured: one step of ten at 70-128 ms instead of
     # 13.3 ms in a third of the runs).  Kernel launches do not take the lock, so with no allocation inside the timed region
     # the clock sampling is harmless.
-    slack = [torch.empty(max(torch.cuda.memory_reserved(dev), 1 << 30), dtype=torch.uint8, device=dev)]
-    slack += [torch.empty(64 << 10, dtype=torch.uint8, device=dev) for _ in range(2048)]
+    main_line = getattr(pipe, "_main_stream", None) or torch.cuda.current_stream(dev)  # the stream the step's big tensors come from
+    with torch.cuda.stream(main_line):
+        slack = [torch.empty(max(torch.cuda.memory_reserved(dev), 1 << 30), dtype=torch.uint8, device=dev)]
+        slack += [torch.empty(64 << 10, dtype=torch.uint8, device=dev) for _ in range(2048)]
+    if main_line is not torch.cuda.current_stream(dev):
+        slack += [torch.empty(1 << 30, dtype=torch.uint8, device=dev)]
+        slack += [torch.empty(64 << 10, dtype=torch.uint8, device=dev) for _ in range(512)]
     for st in (getattr(pipe, n, None) for n in ("_fps_stream", "_col_stream", "_aux_stream")):  # pools are per stream
         if st is not None:
             with torch.cuda.stream(st):
@@ -886,7 +891,8 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args), "scenes_per_gpu": B, "n_points": N_POINTS, "parallelism": f"scene-sharded x{world}",
                        "headline": "`value` / `e2e` = 32 scenes per GPU (weak scaling: the configuration that fills a B200); `strong` = BASELINE config 5 as written, 32 scenes in total over the N GPUs",
-                       "streams": "sampling chain + collision tests on side streams" if pipe.overlap else "single stream",
+                       "streams": ("sampling chain, collision tests, crops + interpolation on side streams; the main line (group forward / backward) on a stream of higher priority"
+                                   if pipe.overlap else "single stream"),
                        "sampling": ("the sampling chain of step k + 1 runs beside step k (it needs the coordinates only); `no_prefetch` = every step samples first"
                                     if pf["on"] else "every step runs its own sampling chain first"),
                        "l2": "per-step working set (>10 GB of grouped features) exceeds the 126 MB L2; no explicit flush",

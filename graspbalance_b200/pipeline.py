@@ -61,10 +61,14 @@ class OpPipeline:
         # overlap: the sampling chain (4 x FPS + gather: latency-bound, a few warps per SM, depends on xyz only) and the
         # collision tests (independent of everything else) run on side streams next to the bandwidth-bound grouping work
         self.overlap = overlap and self.device.type == "cuda"
+        self._main_stream = None
         if self.overlap:
-            self._fps_stream = torch.cuda.Stream(self.device)
-            self._col_stream = torch.cuda.Stream(self.device)
-            self._aux_stream = torch.cuda.Stream(self.device)  # grasp crops + FP/up-sampling chain (compute-bound scans)
+            prio = lambda name: int(os.environ.get(name, "0"))  # CUDA stream priority (0 = default, -1.. = higher)
+            main_prio = int(os.environ.get("GB_PRIO_MAIN", "-1"))
+            self._main_stream = torch.cuda.Stream(self.device, priority=main_prio) if main_prio else None
+            self._fps_stream = torch.cuda.Stream(self.device, priority=prio("GB_PRIO_FPS"))
+            self._col_stream = torch.cuda.Stream(self.device, priority=prio("GB_PRIO_COL"))
+            self._aux_stream = torch.cuda.Stream(self.device, priority=prio("GB_PRIO_AUX"))  # grasp crops + FP/up-sampling chain (compute-bound scans)
         gen = torch.Generator(device=self.device).manual_seed(seed)
         B = batch
         self.sa_groupers = [pu.QueryAndGroup(r, ns, use_xyz=True, ret_grouped_xyz=True, normalize_xyz=True)
@@ -153,6 +157,23 @@ class OpPipeline:
             cur = xyz_buf
 
     def run(self, xyz, view_rot, grasps=None, collect=None, samples=None, prefetch=None):
+        """One step (see _run).  With the overlapped schedule the step's main line -- the bandwidth-bound group forward /
+        backward launches, its critical path -- is issued on a stream of HIGHER PRIORITY than the side streams (sampling
+        chain, collision tests, crops + interpolation), forked from and joined back into the caller's current stream: when
+        SMs free up the block scheduler places the main line's CTAs first and the compute-bound scans fill what is left
+        (B200, 32 scenes: 10.36 -> 10.17 ms per step; the side streams above the main line instead: 10.53)."""
+        if not (self.overlap and self._main_stream is not None):
+            return self._run(xyz, view_rot, grasps, collect, samples, prefetch)
+        caller = torch.cuda.current_stream(self.device)
+        self._main_stream.wait_stream(caller)
+        with torch.cuda.stream(self._main_stream):
+            out = self._run(xyz, view_rot, grasps, collect, samples, prefetch)
+        caller.wait_stream(self._main_stream)
+        for t in out.values():  # allocated in the main line's pool, consumed on the caller's stream
+            t.record_stream(caller)
+        return out
+
+    def _run(self, xyz, view_rot, grasps=None, collect=None, samples=None, prefetch=None):
         """xyz [B,N,3] f32 CUDA; view_rot [B,1024,3,3] f32 CUDA (approach frames of the seeds); grasps = optional dict of
         per-scene fp64 CUDA tensors {scene_points: list of [N'_b,3], T [B,G,3], R [B,G,3,3], thr [B,G,10]}.
         Returns a dict of the per-scene outputs a caller would keep.  collect: optional dict that receives every index
