@@ -54,6 +54,8 @@ class OpPipeline:
     fused_fp = False
     # Schedule of the groupers' backward launches: right after each forward (False) or after every forward of the step, last
     # grouping first -- the order loss.backward() visits them in (True).
+    # CTAs per scene of the background sampling chain (gb_fps_xyz_hint; 0 = the latency-optimal shape)
+    background_cluster = int(os.environ.get("GB_FPS_BG_CLUSTER", "2"))
     backward_last = os.environ.get("GB_BACKWARD_LAST", "1") == "1"  # B200, 32 scenes: 10.62 ms per step against 10.67
 
     def __init__(self, batch, n_points=20000, device="cuda", seed=0, backward=True, overlap=True, fused_crops=True, fused_sampling=True, batched_collision=True):
@@ -151,7 +153,7 @@ class OpPipeline:
         cur = xyz
         for (inds_buf, xyz_buf), (npoint, _, _, _) in zip(into, SA_SPECS):
             # (a shard of fewer than 8 scenes has no step long enough to hide slower rounds: automatic shape)
-            inds, new_xyz = pu.furthest_point_sample_xyz(cur, npoint, 2 if background and self.B >= 8 else 0)
+            inds, new_xyz = pu.furthest_point_sample_xyz(cur, npoint, self.background_cluster if background and self.B >= 8 else 0)
             inds_buf.copy_(inds)
             xyz_buf.copy_(new_xyz)
             cur = xyz_buf
