@@ -155,11 +155,14 @@ class _GroupXyzFeatures(Function):
         _lib.call("gb_group_xyz_feat", features, support_xyz.data_ptr(), query_xyz.data_ptr(), idx.data_ptr(), grouped_xyz.data_ptr(),
                   3 * per, float(inv_radius), int(use_scale), features.data_ptr(), grouped.data_ptr(), C * per, B, C, N, npoint, nsample)
         ctx.mark_non_differentiable(grouped_xyz)
+        ctx.set_materialize_grads(False)  # no zero-filled [B,3,npoint,nsample] gradient for the coordinate output
         ctx.for_backwards = (idx, N)
         return grouped_xyz, grouped
 
     @staticmethod
     def backward(ctx, _grad_xyz, grad_out):
+        if grad_out is None:
+            return None, None, None, None, None, None
         idx, N = ctx.for_backwards
         B, C, npoint, nsample = grad_out.size()
         grad_features = torch.empty([B, C, N], dtype=torch.float, device=grad_out.device)
