@@ -202,3 +202,25 @@ def test_sorted_group_backward_is_bit_reproducible(dev):
         want = torch.zeros((B, C, n), dtype=torch.float64, device=dev)
         want.scatter_add_(2, idx.long().reshape(B, 1, -1).expand(-1, C, -1), gout.double().reshape(B, C, -1))
         _close(first, want)
+
+
+def test_sorted_backward_with_slices_beyond_the_ranking_limit(dev):
+    """Targets that receive more than 256 entries of one tile (every neighbourhood empty: ball_query answers index 0) keep the
+    cursor order inside seg_sort_dense_kernel; the sums stay within tolerance for the group and the interpolation backward."""
+    g = torch.Generator(device="cpu").manual_seed(9)
+    idx = torch.randint(0, 3, (2, 1024, 32), generator=g, dtype=torch.int32).to(dev)
+    idx[0, :512] = 0
+    gout = torch.randn((2, 16, 1024, 32), generator=g).to(dev)
+    with force_sorted():
+        got = gb_a.group_points_grad(gout, idx, 700)
+    want = torch.zeros((2, 16, 700), dtype=torch.float64, device=dev)
+    want.scatter_add_(2, idx.long().reshape(2, 1, -1).expand(-1, 16, -1), gout.double().reshape(2, 16, -1))
+    assert (got.double() - want).abs().max().item() <= 1e-4 * max(want.abs().max().item(), 1.0)  # ~10^4 addends per target
+    idx3 = torch.randint(0, 2, (2, 5000, 3), generator=g, dtype=torch.int32).to(dev)
+    w = torch.rand((2, 5000, 3), generator=g).to(dev)
+    go = torch.randn((2, 8, 5000), generator=g).to(dev)
+    got3 = gb_a.three_interpolate_grad(go, idx3, w, 64)
+    want3 = torch.zeros((2, 8, 64), dtype=torch.float64, device=dev)
+    want3.scatter_add_(2, idx3.long().reshape(2, 1, -1).expand(-1, 8, -1), (go.double().unsqueeze(-1) * w.double().unsqueeze(1)).reshape(2, 8, -1))
+    scale = max(want3.abs().max().item(), 1.0)
+    assert (got3.double() - want3).abs().max().item() <= 1e-4 * scale  # thousands of addends per target
