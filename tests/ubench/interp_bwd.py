@@ -12,6 +12,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 from graspbalance_b200 import _ext as A, pointnet2_utils as pu, scenes  # noqa: E402
 
+from graspbalance_b200 import _lib  # noqa: E402
+
+for kv in filter(None, os.environ.get("GB_TUNE", "").split(",")):  # GB_TUNE=scatter_mode=4,scatter_cc=4
+    k, v = kv.split("=")
+    _lib.set_tuning(k, int(v))
 HBM = 6542.4
 dev = torch.device("cuda:0")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -45,4 +50,4 @@ for B in (32, 4):
         us = timeit(lambda: A.three_interpolate_grad(gout, idx, w, m))
         by = B * (4 * C * n + 24 * n + 4 * C * m)
         out[f"B{B}_n{n}_m{m}"] = {"us": round(us, 1), "hbm_frac": round(by / (us * 1e-6) / 1e9 / HBM, 3)}
-print(json.dumps({"lib": os.environ.get("GBOPS_LIB", "default"), "interp_bwd": out}))
+print(json.dumps({"lib": os.environ.get("GBOPS_LIB", "default"), "tune": os.environ.get("GB_TUNE", ""), "interp_bwd": out}))
