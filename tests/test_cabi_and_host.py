@@ -193,3 +193,22 @@ def test_segment_table_and_balance_plan_host_logic():
         balance_plan([0], [20000], 1024)
     with pytest.raises(IndexError):  # upstream assumes label 0 exists; without it its per-object list is one short
         balance_plan([1, 2], [10, 10], 1024)
+
+
+def test_every_entry_point_the_package_calls_has_a_signature_and_a_byte_formula():
+    """bench.py's roofline pass brackets every _lib.call with events and looks its algorithmic bytes up by entry-point name:
+    an entry point added to the package without a ctypes signature or a formula would only fail on the GPU box."""
+    import re
+    from graspbalance_b200 import _lib
+    pkg = os.path.join(ROOT, "graspbalance_b200")
+    called = set()
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            called |= set(re.findall(r'_lib\.call\(\s*"(gb_[a-z0-9_]+)"', open(os.path.join(pkg, fn)).read()))
+    assert "gb_group_xyz_feat" in called and "gb_group_fwd" in called
+    for name in sorted(called):
+        assert name in _lib.SIGNATURES, name
+        assert name in _lib.ALGO_BYTES, name
+    # the fused grouper entry: coordinates + features, one idx read (DESIGN.md section 4)
+    a = [None] * 10 + [2, 8, 100, 10, 4]  # b, c, n, npoints, nsample at the positions _lib.call passes them
+    assert _lib.ALGO_BYTES["gb_group_xyz_feat"](a) == 2 * (4 * 8 * 100 + 4 * 10 * 4 + 4 * 8 * 10 * 4 + 12 * 100 + 12 * 10 + 12 * 10 * 4)
